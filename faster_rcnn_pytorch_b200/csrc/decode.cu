@@ -1,0 +1,141 @@
+// A2 + P1 + P2 + P3: anchors, fg softmax, box decode, clamp and min-size test in one pass.
+//
+// Reference: anchor.py:34-55, models/model.py:20,31-41, utils/util.py:15-26,46-50.
+// HBM-bound streaming kernel: per anchor it reads reg (16 B) + logits (8 B) and writes the box
+// (16 B), the score (4 B) and a validity byte -> 44 B/anchor algorithmic.  Anchors
+// are rebuilt in registers from the 9x4 table (kernel parameter) so no anchor tensor is read.
+// Parity-critical arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction).
+#include "frr_common.cuh"
+
+namespace frr {
+
+__device__ __forceinline__ float4 make_anchor(const AnchorTable& tab, int cell, int a, int fw, float stride, float W,
+                                              float H) {
+    const int y = cell / fw, x = cell - y * fw;
+    const float sx = (float)x * stride, sy = (float)y * stride;  // exact: small integers
+    float4 r;
+    r.x = __fdiv_rn(__fadd_rn(tab.v[4 * a + 0], sx), W);
+    r.y = __fdiv_rn(__fadd_rn(tab.v[4 * a + 1], sy), H);
+    r.z = __fdiv_rn(__fadd_rn(tab.v[4 * a + 2], sx), W);
+    r.w = __fdiv_rn(__fadd_rn(tab.v[4 * a + 3], sy), H);
+    return r;
+}
+
+__global__ void __launch_bounds__(256) anchors_kernel(float4* __restrict__ out, AnchorTable tab, int n, int fw,
+                                                      float stride, float W, float H) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cell = i / tab.A, a = i - cell * tab.A;
+    out[i] = make_anchor(tab, cell, a, fw, stride, W, H);
+}
+
+// one thread per (image, anchor); grid.y = image
+template <bool kLogits, bool kGenAnchors>
+__global__ void __launch_bounds__(256)
+    rpn_decode_kernel(const float4* __restrict__ reg, const float* __restrict__ cls, const float4* __restrict__ anchors,
+                      AnchorTable tab, int N, int fw, float stride, float W, float H, float min_size,
+                      float4* __restrict__ boxes, float* __restrict__ scores, uint8_t* __restrict__ valid) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const size_t g = (size_t)blockIdx.y * N + i;
+
+    float4 an;
+    if (kGenAnchors) {
+        const int cell = i / tab.A, a = i - cell * tab.A;
+        an = make_anchor(tab, cell, a, fw, stride, W, H);
+    } else {
+        an = anchors[i];
+    }
+    const float4 t = ld_stream(reg + g);
+
+    float s;
+    if (kLogits) {
+        const float2 l = *reinterpret_cast<const float2*>(cls + 2 * g);
+        const float m = fmaxf(l.x, l.y);
+        const float e0 = expf(__fsub_rn(l.x, m)), e1 = expf(__fsub_rn(l.y, m));
+        s = __fdiv_rn(e1, __fadd_rn(e0, e1));
+    } else {
+        s = cls[g];
+    }
+
+    // xy_to_cxcy(anchor): c = (hi + lo)/2, wh = hi - lo
+    const float acx = __fmul_rn(__fadd_rn(an.z, an.x), 0.5f), acy = __fmul_rn(__fadd_rn(an.w, an.y), 0.5f);
+    const float aw = __fsub_rn(an.z, an.x), ah = __fsub_rn(an.w, an.y);
+    // decode: c = t_xy * a_wh + a_c ; wh = exp(t_wh) * a_wh
+    const float cx = __fadd_rn(__fmul_rn(t.x, aw), acx), cy = __fadd_rn(__fmul_rn(t.y, ah), acy);
+    const float w = __fmul_rn(expf(t.z), aw), h = __fmul_rn(expf(t.w), ah);
+    // cxcy_to_xy + clamp(0,1)
+    const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
+    float4 b;
+    b.x = fminf(fmaxf(__fsub_rn(cx, hw), 0.f), 1.f);
+    b.y = fminf(fmaxf(__fsub_rn(cy, hh), 0.f), 1.f);
+    b.z = fminf(fmaxf(__fadd_rn(cx, hw), 0.f), 1.f);
+    b.w = fminf(fmaxf(__fadd_rn(cy, hh), 0.f), 1.f);
+    const bool ok = (__fsub_rn(b.w, b.y) >= min_size) && (__fsub_rn(b.z, b.x) >= min_size);
+
+    st_stream(boxes + g, b);
+    scores[g] = s;
+    valid[g] = ok ? 1 : 0;
+}
+
+}  // namespace frr
+
+extern "C" {
+
+int frr_anchors(float* anchors, int img_h, int img_w, int stride, const float* base_table_host, int A,
+                frr_stream_t stream) {
+    using namespace frr;
+    FRR_CHECK_ARG(anchors && img_h > 0 && img_w > 0 && stride > 0, "frr_anchors: bad arguments");
+    FRR_CHECK_ARG(aligned16(anchors), "frr_anchors: output must be 16-byte aligned");
+    AnchorTable tab;
+    int rc = fill_anchor_table(&tab, base_table_host, A, stride);
+    if (rc) return rc;
+    const int fh = img_h / stride, fw = img_w / stride;
+    const int n = fh * fw * tab.A;
+    if (n == 0) return FRR_OK;
+    anchors_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((float4*)anchors, tab, n, fw, (float)stride,
+                                                                       (float)img_w, (float)img_h);
+    count_launch();
+    FRR_CHECK_LAUNCH("anchors_kernel");
+    return FRR_OK;
+}
+
+int frr_rpn_decode(const float* reg, const float* cls, int cls_is_logits, const float* anchors,
+                   const float* base_table_host, int A, int img_h, int img_w, int stride, float min_size, float* boxes,
+                   float* scores, uint8_t* valid, int B, int N, frr_stream_t stream) {
+    using namespace frr;
+    FRR_CHECK_ARG(reg && cls && boxes && scores && valid, "frr_rpn_decode: null pointer");
+    FRR_CHECK_ARG(B >= 0 && N >= 0 && B <= 65535, "frr_rpn_decode: bad B=%d N=%d", B, N);
+    FRR_CHECK_ARG(aligned16(reg) && aligned16(boxes) && (anchors == nullptr || aligned16(anchors)),
+                  "frr_rpn_decode: reg/boxes/anchors must be 16-byte aligned");
+    FRR_CHECK_ARG((reinterpret_cast<uintptr_t>(cls) & 7u) == 0, "frr_rpn_decode: cls must be 8-byte aligned");
+    AnchorTable tab;
+    tab.A = 1;
+    int fw = 1;
+    if (anchors == nullptr) {
+        FRR_CHECK_ARG(img_h > 0 && img_w > 0 && stride > 0, "frr_rpn_decode: bad image size");
+        int rc = fill_anchor_table(&tab, base_table_host, A, stride);
+        if (rc) return rc;
+        fw = img_w / stride;
+        FRR_CHECK_ARG((img_h / stride) * fw * tab.A == N, "frr_rpn_decode: N=%d does not match %dx%d/%d x A=%d", N,
+                      img_h, img_w, stride, tab.A);
+    }
+    if (B == 0 || N == 0) return FRR_OK;
+    dim3 grid((N + 255) / 256, B);
+    cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(L, G)                                                                                              \
+    rpn_decode_kernel<L, G><<<grid, 256, 0, st>>>((const float4*)reg, cls, (const float4*)anchors, tab, N, fw,   \
+                                                  (float)stride, (float)img_w, (float)img_h, min_size,           \
+                                                  (float4*)boxes, scores, valid)
+    if (cls_is_logits) {
+        if (anchors) LAUNCH(true, false); else LAUNCH(true, true);
+    } else {
+        if (anchors) LAUNCH(false, false); else LAUNCH(false, true);
+    }
+#undef LAUNCH
+    count_launch();
+    FRR_CHECK_LAUNCH("rpn_decode_kernel");
+    return FRR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+/*
+ * frr.h -- C ABI of libfrr.so: the B200-native (sm_100a) Faster R-CNN region stage.
+ *
+ * Drop-in boundary for the region stage of csm-kr/faster_rcnn_pytorch.
+ * The reference has no FFI layer; its boundary is the Python call sites in
+ * models/model.py:6-9,288-298 (torchvision.ops.nms / RoIPool, FRCNNAnchorMaker, the
+ * utils.util box helpers and the RegionProposal / *TargetMaker modules).  Every entry
+ * point below cites the reference lines it replaces.  The Python mirror of those call
+ * sites lives in faster_rcnn_pytorch_b200/ and binds this header with ctypes
+ * (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer on the current CUDA device unless named *_host;
+ *  - the library never allocates, frees or synchronises: the caller owns outputs and
+ *    workspaces and passes the stream (cudaStream_t as void*); all calls are
+ *    graph-capturable;
+ *  - ragged results use fixed-capacity buffers + int32 counts on the device;
+ *  - boxes are fp32 (x1,y1,x2,y2); box arrays must be 16-byte aligned;
+ *  - return value: 0 = ok, negative = error (FRR_E_*); frr_last_error() returns a
+ *    thread-local message.  No C++ exception crosses the boundary.
+ */
+#ifndef FRR_H_
+#define FRR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#pragma GCC visibility push(default)
+#endif
+
+#define FRR_ABI_VERSION 1
+
+#define FRR_OK 0
+#define FRR_E_INVALID (-1)   /* bad argument (shape, alignment, range)        */
+#define FRR_E_LAUNCH (-2)    /* CUDA launch / runtime error                   */
+#define FRR_E_WORKSPACE (-3) /* workspace too small                           */
+#define FRR_E_UNSUPPORTED (-4)
+
+typedef void* frr_stream_t; /* cudaStream_t */
+
+int frr_abi_version(void);
+const char* frr_last_error(void);
+/* Number of kernels this library has launched in the calling process (bench "gpu_launches"). */
+uint64_t frr_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * A1/A2  anchors -- anchor.py:15-32 (generate_anchor_base), :34-55 (_enumerate_shifted_anchor)
+ * ------------------------------------------------------------------------------------- */
+/* Host helper: the reference's 9x4 base table (ratio-major, float64 math stored to fp32). */
+int frr_anchor_base_host(float* table_host /* [9*4] */, int base_size);
+/* anchors[(y*fw+x)*A+a] = fl32(base[a] + stride*(x,y,x,y)) / (W,H,W,H);  fh=H/stride, fw=W/stride.
+ * base_table_host: [A*4] host floats or NULL for the reference table (A=9).  A <= 16. */
+int frr_anchors(float* anchors /* [fh*fw*A,4] */, int img_h, int img_w, int stride,
+                const float* base_table_host, int A, frr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * P1-P3  fused RPN decode -- models/model.py:20 (softmax fg), :31-34 (decode, clamp),
+ *        :37-41 (min-size filter); utils/util.py:15-26,46-50.  Anchors are generated in
+ *        registers (A2) unless `anchors` is given.
+ * ------------------------------------------------------------------------------------- */
+int frr_rpn_decode(const float* reg /* [B,N,4] */, const float* cls /* [B,N,2] logits or [B,N] scores */,
+                   int cls_is_logits, const float* anchors /* [N,4] or NULL */,
+                   const float* base_table_host /* [A*4] or NULL */, int A, int img_h, int img_w,
+                   int stride, float min_size /* reference: 0.001f */, float* boxes /* [B,N,4] */,
+                   float* scores /* [B,N] */, uint8_t* valid /* [B,N] */, int B, int N,
+                   frr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * P4  pre-NMS top-k, sorted descending -- models/model.py:44-49.  Radix select + in-smem
+ *     sort, one CTA per image.  Ties: lower index first.  Entries past count[b] are padded
+ *     (idx -1, score -inf, box 0).  out_cidx = index into the min-size-compacted array (what
+ *     the reference's sort returns), out_idx = index into the full N.  k <= 16384.
+ * ------------------------------------------------------------------------------------- */
+int frr_topk_desc(const float* scores /* [B,N] */, const uint8_t* valid /* [B,N] or NULL */,
+                  const float* boxes /* [B,N,4] or NULL */, int B, int N, int k,
+                  float* out_scores /* [B,k] or NULL */, int32_t* out_idx /* [B,k] */,
+                  int32_t* out_cidx /* [B,k] or NULL */, float* out_boxes /* [B,k,4] or NULL */,
+                  int32_t* out_count /* [B] */, frr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * N1  greedy NMS on score-sorted boxes -- torchvision.ops.nms at models/model.py:53-55
+ *     (IoU 0.7, keep[:2000|300]) with torchvision's CPU semantics: fp32 IoU, suppress when
+ *     (double)iou > iou_thr.  Keep-list algorithm on a thread-block cluster per image,
+ *     stops at max_keep.  keep = positions in the sorted list, ascending, -1 padded.
+ *     cluster_size: 0 = auto, else 1,2,4,8,16.
+ * ------------------------------------------------------------------------------------- */
+int frr_nms_sorted(const float* boxes /* [B,n,4] */, const int32_t* counts /* [B] or NULL (=n) */, int B,
+                   int n, double iou_thr, int max_keep, int32_t* keep /* [B,max_keep] */,
+                   int32_t* keep_count /* [B] */, float* out_boxes /* [B,max_keep,4] or NULL */,
+                   int cluster_size, frr_stream_t stream);
+
+#ifdef __cplusplus
+#pragma GCC visibility pop
+}
+#endif
+#endif /* FRR_H_ */
