@@ -8,14 +8,19 @@
 //   themselves (warp-ballot predecessor masks + a parallel fix-point) and appends the newly
 //   kept boxes to its slice.  The walk stops at max_keep, so with the RPN's 12000 -> 2000
 //   only the first ~5-6k candidates are ever touched and each is tested against kept boxes
-//   only (~5.5 M pair tests instead of the 72 M of the full upper triangle).
+//   only (~5 M pair tests instead of the 72 M of the full upper triangle).
+//
+// Phase 1 is register tiled: a thread holds 4 candidates and streams kept boxes from shared
+// memory (one broadcast LDS.128 feeds 128 pair tests), because the un-tiled version was bound
+// by shared-memory wavefronts, not by the FP32/ALU pipes.
 //
 // Bit-exactness vs the CPU kernel: IoU = inter / ((area_i + area_j) - inter) in fp32 with IEEE
-// division and no FMA contraction; suppress when (double)iou > thr  <=>  iou >= thr_up, where
-// thr_up is the smallest fp32 strictly above thr.  Almost every pair is decided without the
-// division by a guarded product test (inter vs thr_up*(1 -+ 2^-20)*union); only pairs inside
-// the guard band take the exact division.  Degenerate boxes carry a NaN "fast area" so that
-// they always fall through to the exact path.
+// division and no FMA contraction; suppress when (double)iou > thr  <=>  iou >= up, where up is
+// the smallest fp32 strictly above thr.  Almost every pair is rejected without the division by
+// a conservative 10-instruction screen:  inter/union < up  <=  inter < c2*(area_a + area_b) with
+// c2 = up/(1+up)*(1 - 2^-19)  (the 2^-19 margin covers every fp32 rounding in the screen and in
+// the exact formula, see suppress_screen()); the ~0.3 % of pairs that pass the screen take the exact
+// division.  Degenerate / tiny boxes carry a NaN screening area, which always fails the screen.
 #include <cooperative_groups.h>
 #include <math.h>
 
@@ -25,28 +30,30 @@ namespace cg = cooperative_groups;
 
 namespace frr {
 
-constexpr int kNmsThreads = 256;  // = chunk size
-constexpr int kNmsWarps = kNmsThreads / 32;
+constexpr int kChunk = 256;  // candidates per chunk
+constexpr int kChunkWords = kChunk / 32;
 constexpr int kMaxCluster = 16;
+constexpr int kTile = 4;                // candidates per thread in phase 1
+constexpr int kGroup = kChunk / kTile;  // threads that together cover one chunk (64)
 
 struct NmsThr {
-    float up;    // smallest fp32 with (double)up > thr
-    float c_lo;  // up * (1 - 2^-20): below -> certainly not suppressed
-    float c_hi;  // up * (1 + 2^-20): above -> certainly suppressed
-    int fast;    // guarded product test usable (thr > 0 and finite)
+    float up;  // smallest fp32 with (double)up > thr
+    float c2;  // up/(1+up) * (1 - 2^-19): screening constant
+    int fast;  // screening usable (1e-6 <= thr, finite)
 };
 
 __device__ __forceinline__ float box_area(const float4& b) {
     return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
 }
-// area used by the fast path: NaN for boxes that are not well formed (forces the exact path)
-__device__ __forceinline__ float fast_area(const float4& b) {
+// c2-scaled area used by the screen: NaN for boxes that are not well formed or tiny (forces the exact path)
+__device__ __forceinline__ float screen_area(const float4& b, float c2) {
     const float a = box_area(b);
-    const bool ok = (b.z >= b.x) && (b.w >= b.y) && (a <= 3.0e38f);
-    return ok ? a : __int_as_float(0x7fc00000);
+    const bool ok = (b.z >= b.x) && (b.w >= b.y) && (a <= 3.0e38f) && (a >= 1.0e-30f);
+    return ok ? __fmul_rn(c2, a) : __int_as_float(0x7fc00000);
 }
 
-__device__ __noinline__ bool suppress_exact(const float4& a, const float4& b, float up) {
+// The exact torchvision CPU decision for one pair (a = earlier box).  Rare path.
+__device__ __noinline__ bool suppress_exact(float4 a, float4 b, float up) {
     const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
     const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
     const float inter = __fmul_rn(w, h);
@@ -55,42 +62,60 @@ __device__ __noinline__ bool suppress_exact(const float4& a, const float4& b, fl
     return ovr >= up;  // false for NaN, as (double)NaN > thr
 }
 
-// a = earlier (kept) box, b = candidate; fa/fb = fast areas.  Symmetric in (a,b).
-__device__ __forceinline__ bool suppresses(const float4& a, float fa, const float4& b, float fb, const NmsThr& t) {
-    const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
+// Screen: returns false only when the pair is certainly NOT suppressed.
+//   exact:  ovr = RN(I / U),  U = RN(RN(Aa+Ab) - I) = (Aa+Ab-I)(1+e), |e| <= 2^-22 (I <= (Aa+Ab)/2)
+//   ovr < up  <=  I/U < up(1-2^-23)  <=  I < u'(Aa+Ab-I), u' = up(1-2^-21)  <=>  I < u'/(1+u') (Aa+Ab)
+//   screen:  T = RN(RN(c2 Aa) + RN(c2 Ab)) <= c2 (Aa+Ab)(1+2^-22), and c2 (1+2^-22) < u'/(1+u').
+// Only one of w/h is clamped: if w < 0 then I <= 0 < T (the true intersection is 0: not suppressed).
+// sa/sb are the c2-scaled areas (NaN if degenerate -> T is NaN -> the screen reports "maybe").
+__device__ __forceinline__ bool suppress_screen(const float4& a, float sa, const float4& b, float sb) {
+    const float w = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
     const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
-    const float inter = __fmul_rn(w, h);
-    const float uni = __fsub_rn(__fadd_rn(fa, fb), inter);
-    // !(inter < lo) is also true when uni is NaN (degenerate box) -> exact path
-    if (!(inter < __fmul_rn(t.c_lo, uni))) {
-        if (inter > __fmul_rn(t.c_hi, uni)) return true;
-        return suppress_exact(a, b, t.up);
-    }
-    return false;
+    return !(__fmul_rn(w, h) < __fadd_rn(sa, sb));
 }
 
 struct NmsSmem {
-    unsigned int supp[2][kMaxCluster][kNmsWarps];  // [parity][source rank][warp]: suppressed-by-slice words
-    unsigned int warp_cnt[kNmsWarps];
-    unsigned int kept_w[kNmsWarps];     // fix-point state: survivor bit sets (<= 256 survivors)
-    unsigned int removed_w[kNmsWarps];
-    unsigned int pred[kNmsThreads][kNmsWarps];  // pred[i][q]: bit j of word q set if survivor 32q+j (< i) suppresses i
-    float4 sbox[kNmsThreads];                   // survivor boxes (compacted)
-    float sarea[kNmsThreads];
-    short ssrc[kNmsThreads];                    // survivor -> position inside the chunk
-    int undecided;
+    unsigned int supp[2][kMaxCluster][kChunkWords];  // [parity][src rank][word]: suppressed-by-slice words
+    unsigned int acc[2][kChunkWords];                // [parity][word]: this CTA's words (OR over its parts)
+    unsigned int warp_cnt[kChunkWords];
+    unsigned int kept_w[2][kChunkWords];  // fix-point state, double buffered
+    unsigned int removed_w[2][kChunkWords];
+    unsigned int pred[kChunk][kChunkWords];  // pred[i][q]: bit j set if survivor 32q+j (< i) suppresses survivor i
+    float4 cbox[kChunk];                     // the chunk's candidates
+    float carea[kChunk];
+    float4 sbox[kChunk];  // survivor boxes (compacted)
+    float sarea[kChunk];
+    short ssrc[kChunk];  // survivor -> position inside the chunk
 };
 
-template <bool kFast>
-__global__ void __launch_bounds__(kNmsThreads)
+// barrier over the first `n` threads of the CTA with an OR reduction of `pred`
+__device__ __forceinline__ bool bar_or(int id, int n, bool pred) {
+    int r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.s32 q, %1, 0;\n\tbar.red.or.pred p, %2, %3, q;\n\tselp.s32 %0, 1, 0, p;\n\t}"
+        : "=r"(r)
+        : "r"((int)pred), "r"(id), "r"(n)
+        : "memory");
+    return r != 0;
+}
+
+enum { DBG_CHUNKS = 0, DBG_LOAD, DBG_P1, DBG_SYNC, DBG_P2, DBG_P3, DBG_P4, DBG_P5, DBG_SURV, DBG_ITERS, DBG_N };
+
+template <int kThreads, bool kFast>
+__global__ void __launch_bounds__(kThreads)
     nms_keeplist_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ counts, int n, int max_keep,
                         int slice_cap, NmsThr thr, int32_t* __restrict__ keep, int32_t* __restrict__ keep_count,
-                        float4* __restrict__ out_boxes) {
+                        float4* __restrict__ out_boxes, long long* __restrict__ dbg) {
+    static_assert(kThreads >= kChunk && kThreads % kGroup == 0, "bad thread count");
+    constexpr int kWarps = kThreads / 32;
+    constexpr int kParts = kThreads / kGroup;  // interleaved parts of the kept slice
     cg::cluster_group cluster = cg::this_cluster();
     const int S = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
     const int img = blockIdx.x / S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int part = tid / kGroup;  // which interleaved part of the kept slice this thread scans
+    const int u = tid % kGroup;     // candidates u, u+64, u+128, u+192 of the chunk
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmsSmem* sm = reinterpret_cast<NmsSmem*>(smem_raw);
@@ -101,144 +126,233 @@ __global__ void __launch_bounds__(kNmsThreads)
     const float4* ib = boxes + (size_t)img * n;
     int32_t* ikeep = keep + (size_t)img * max_keep;
     float4* iout = out_boxes ? out_boxes + (size_t)img * max_keep : nullptr;
+    const bool prof = (dbg != nullptr) && blockIdx.x == 0 && tid == 0;
+    long long t0 = 0;
+#define FRR_TICK(slot)                  \
+    if (prof) {                         \
+        const long long t1 = clock64(); \
+        dbg[slot] += t1 - t0;           \
+        t0 = t1;                        \
+    }
 
     int nk = 0;  // kept so far (identical in every CTA of the cluster)
     int par = 0;
-    for (int base = 0; base < cnt && nk < max_keep; base += kNmsThreads, par ^= 1) {
-        const int i = base + tid;
-        const bool has = i < cnt;
-        float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has) bx = ib[i];
-        const float fa = fast_area(bx);
+    float4 nbx = make_float4(0.f, 0.f, 0.f, 0.f);  // prefetched candidate of the next chunk (first kChunk threads)
+    if (tid < kChunk && tid < cnt) nbx = ib[tid];
+    if (tid < 2 * kChunkWords) (&sm->acc[0][0])[tid] = 0u;
+    for (int base = 0; base < cnt && nk < max_keep; base += kChunk, par ^= 1) {
+        if (prof) { t0 = clock64(); dbg[DBG_CHUNKS] += 1; }
+        // ---- phase 0: stage the chunk's candidates in shared memory, prefetch the next chunk ----------
+        if (tid < kChunk) {
+            sm->cbox[tid] = nbx;
+            sm->carea[tid] = screen_area(nbx, thr.c2);
+            const int nx = base + kChunk + tid;
+            if (nx < cnt) nbx = ib[nx];
+        }
+        __syncthreads();
+        FRR_TICK(DBG_LOAD);
 
-        // ---- phase 1: candidate vs this CTA's slice of the kept list -----------------------------
+        // ---- phase 1: 4 candidates per thread vs this CTA's slice of the kept list ----------------------
         const int ns = (nk - rank + S - 1) / S;  // kept ordinals o with o % S == rank
-        bool sup = !has;
         {
-            int k = 0;
-            for (; k + 4 <= ns; k += 4) {
-                bool s0, s1, s2, s3;
-                if (kFast) {
-                    s0 = suppresses(kbox[k], karea[k], bx, fa, thr);
-                    s1 = suppresses(kbox[k + 1], karea[k + 1], bx, fa, thr);
-                    s2 = suppresses(kbox[k + 2], karea[k + 2], bx, fa, thr);
-                    s3 = suppresses(kbox[k + 3], karea[k + 3], bx, fa, thr);
-                } else {
-                    s0 = suppress_exact(kbox[k], bx, thr.up);
-                    s1 = suppress_exact(kbox[k + 1], bx, thr.up);
-                    s2 = suppress_exact(kbox[k + 2], bx, thr.up);
-                    s3 = suppress_exact(kbox[k + 3], bx, thr.up);
-                }
-                sup |= (s0 | s1) | (s2 | s3);
-                if ((k & 31) == 28 && __all_sync(0xffffffffu, sup)) { k = ns; break; }
-            }
-            for (; k < ns; ++k)
-                sup |= kFast ? suppresses(kbox[k], karea[k], bx, fa, thr) : suppress_exact(kbox[k], bx, thr.up);
-        }
-        const unsigned int word = __ballot_sync(0xffffffffu, sup);
-        if (lane < S) {
-            unsigned int* dst = cluster.map_shared_rank(&sm->supp[par][rank][warp], lane);
-            *dst = word;
-        }
-        cluster.sync();
-
-        // ---- phase 2: combine, compact survivors ---------------------------------------------------
-        unsigned int all = 0;
-        for (int r = 0; r < S; ++r) all |= sm->supp[par][r][warp];
-        const bool alive = !((all >> lane) & 1u);
-        const unsigned int am = __ballot_sync(0xffffffffu, alive);
-        if (lane == 0) sm->warp_cnt[warp] = __popc(am);
-        if (tid < kNmsWarps) { sm->kept_w[tid] = 0; sm->removed_w[tid] = 0; }
-        __syncthreads();
-        int soff = 0, s = 0;
+            float4 cb[kTile];
+            float ca[kTile];
+            bool has[kTile], sup[kTile];
 #pragma unroll
-        for (int w2 = 0; w2 < kNmsWarps; ++w2) {
-            const int c = (int)sm->warp_cnt[w2];
-            if (w2 < warp) soff += c;
-            s += c;
-        }
-        if (alive) {
-            const int si = soff + __popc(am & ((1u << lane) - 1u));
-            sm->sbox[si] = bx;
-            sm->sarea[si] = fa;
-            sm->ssrc[si] = (short)tid;
-        }
-        __syncthreads();
-
-        // ---- phase 3: predecessor masks among survivors (warp item = (row i, 32-column word q)) -----
-        const int nw = (s + 31) >> 5;
-        for (int it = warp; it < s * nw; it += kNmsWarps) {
-            const int row = it / nw, q = it - row * nw;
-            if (q * 32 >= row) continue;  // only columns j < row
-            const int j = q * 32 + lane;
-            bool hit = false;
-            if (j < row) {
-                hit = kFast ? suppresses(sm->sbox[j], sm->sarea[j], sm->sbox[row], sm->sarea[row], thr)
-                            : suppress_exact(sm->sbox[j], sm->sbox[row], thr.up);
+            for (int j = 0; j < kTile; ++j) {
+                cb[j] = sm->cbox[u + j * kGroup];
+                ca[j] = sm->carea[u + j * kGroup];
+                has[j] = base + u + j * kGroup < cnt;
+                sup[j] = !has[j];
             }
-            const unsigned int m = __ballot_sync(0xffffffffu, hit);
-            if (lane == 0) sm->pred[row][q] = m;
+            if (kFast) {
+                // Screen every kept box of the slice; remember only the FIRST one that passes the screen and
+                // evaluate it exactly after the loop (all lanes together).  The screen is tight (2^-19), so a
+                // pass is almost always a true suppression; the rare lane whose exact test fails rescans.
+                int pk[kTile];
+#pragma unroll
+                for (int j = 0; j < kTile; ++j) pk[j] = has[j] ? -1 : 0;
+#pragma unroll 2
+                for (int k = part; k < ns; k += kParts) {
+                    const float4 kb = kbox[k];
+                    const float ka = karea[k];
+#pragma unroll
+                    for (int j = 0; j < kTile; ++j)
+                        if (suppress_screen(kb, ka, cb[j], ca[j]) && pk[j] < 0) pk[j] = k;
+                }
+#pragma unroll
+                for (int j = 0; j < kTile; ++j) {
+                    if (has[j] && pk[j] >= 0) {
+                        sup[j] = suppress_exact(kbox[pk[j]], cb[j], thr.up);
+                        for (int k2 = pk[j] + kParts; k2 < ns && !sup[j]; k2 += kParts)
+                            if (suppress_screen(kbox[k2], karea[k2], cb[j], ca[j]))
+                                sup[j] = suppress_exact(kbox[k2], cb[j], thr.up);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < kTile; ++j)
+                    for (int k = part; k < ns && !sup[j]; k += kParts) sup[j] = suppress_exact(kbox[k], cb[j], thr.up);
+            }
+            // warp covers candidates u in [32*(warp&1), +32) + 64 j  ->  word (warp&1) + 2 j
+#pragma unroll
+            for (int j = 0; j < kTile; ++j) {
+                const unsigned int wj = __ballot_sync(0xffffffffu, sup[j]);
+                if (lane == 0 && wj != 0u) atomicOr(&sm->acc[par][(warp & 1) + 2 * j], wj);
+            }
         }
         __syncthreads();
+        // publish this CTA's 8 words to every CTA of the cluster (distributed shared memory)
+        if (tid < kChunkWords * S) {
+            const int wd = tid % kChunkWords, dstr = tid / kChunkWords;
+            unsigned int* dst = cluster.map_shared_rank(&sm->supp[par][rank][wd], dstr);
+            *dst = sm->acc[par][wd];
+        }
+        FRR_TICK(DBG_P1);
+        cluster.sync();
+        FRR_TICK(DBG_SYNC);
 
-        // ---- phase 4: parallel fix-point.  survivor i is kept when every predecessor that
-        //      suppresses it is removed; removed as soon as one such predecessor is kept. --------------
+        // ---- phase 2: combine the S words per 32 candidates, compact survivors (first kChunk threads) ---
+        bool alive = false;
+        unsigned int am = 0;
+        float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+        float fa = 0.f;
+        if (tid < kChunk) {
+            const unsigned int v = (lane < S) ? sm->supp[par][lane][warp] : 0u;
+            const unsigned int all = __reduce_or_sync(0xffffffffu, v);
+            alive = !((all >> lane) & 1u);
+            am = __ballot_sync(0xffffffffu, alive);
+            if (lane == 0) sm->warp_cnt[warp] = __popc(am);
+            if (tid < kChunkWords) {
+                sm->kept_w[0][tid] = 0;
+                sm->removed_w[0][tid] = 0;
+                sm->acc[par ^ 1][tid] = 0;  // for the next chunk
+            }
+            bx = sm->cbox[tid];
+            fa = sm->carea[tid];
+        }
+        __syncthreads();
+        int s = 0;
         {
-            const bool mine = tid < s;
-            const int myw = (tid >> 5) + 1;  // words that can hold predecessors of `tid`
-            int state = mine ? 0 : 3;        // 0 undecided, 1 kept, 2 removed, 3 n/a
+            int soff = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < kChunkWords; ++w2) {
+                const int cc = (int)sm->warp_cnt[w2];
+                if (w2 < warp) soff += cc;
+                s += cc;
+            }
+            if (alive) {
+                const int si = soff + __popc(am & ((1u << lane) - 1u));
+                sm->sbox[si] = bx;
+                sm->sarea[si] = fa;
+                sm->ssrc[si] = (short)tid;
+            }
+        }
+        __syncthreads();
+        FRR_TICK(DBG_P2);
+        if (prof) dbg[DBG_SURV] += s;
+
+        // ---- phase 3: predecessor masks among survivors: warp item = (row, 32-column word), two words
+        //      per iteration for ILP ------------------------------------------------------------------------
+        for (int row = warp; row < s; row += kWarps) {
+            const float4 rb = sm->sbox[row];
+            const float ra = sm->sarea[row];
+            for (int q = 0; q * 32 < row; q += 2) {
+                const int j0 = q * 32 + lane, j1 = j0 + 32;  // j1 <= 255
+                bool h0 = false, h1 = false;
+                if (kFast) {
+                    const bool m0 = (j0 < row) && suppress_screen(sm->sbox[j0], sm->sarea[j0], rb, ra);
+                    const bool m1 = (j1 < row) && suppress_screen(sm->sbox[j1], sm->sarea[j1], rb, ra);
+                    if (m0) h0 = suppress_exact(sm->sbox[j0], rb, thr.up);
+                    if (m1) h1 = suppress_exact(sm->sbox[j1], rb, thr.up);
+                } else {
+                    if (j0 < row) h0 = suppress_exact(sm->sbox[j0], rb, thr.up);
+                    if (j1 < row) h1 = suppress_exact(sm->sbox[j1], rb, thr.up);
+                }
+                const unsigned int b0 = __ballot_sync(0xffffffffu, h0);
+                const unsigned int b1 = __ballot_sync(0xffffffffu, h1);
+                if (lane == 0) {
+                    sm->pred[row][q] = b0;
+                    sm->pred[row][q + 1] = b1;
+                }
+            }
+        }
+        __syncthreads();
+        FRR_TICK(DBG_P3);
+
+        // ---- phase 4: parallel fix-point over the survivors (first kChunk threads, named barrier 1).
+        //      survivor i is kept once every predecessor that suppresses it is removed; removed as soon
+        //      as one such predecessor is kept.  State words are double buffered: one barrier / round. ----
+        int fin = 0;
+        if (tid < kChunk) {
+            int state = (tid < s) ? 0 : 3;  // 0 undecided, 1 kept, 2 removed, 3 n/a
+            unsigned int p[kChunkWords];
+#pragma unroll
+            for (int q = 0; q < kChunkWords; ++q) p[q] = (state == 0 && q * 32 < tid) ? sm->pred[tid][q] : 0u;
+            int cur = 0;
             for (;;) {
                 if (state == 0) {
                     bool hit_kept = false, pending = false;
-                    for (int q = 0; q < myw && q < nw; ++q) {
-                        if (q * 32 >= tid) break;
-                        const unsigned int p = sm->pred[tid][q];
-                        hit_kept |= (p & sm->kept_w[q]) != 0u;
-                        pending |= (p & ~(sm->kept_w[q] | sm->removed_w[q])) != 0u;
+#pragma unroll
+                    for (int q = 0; q < kChunkWords; ++q) {
+                        const unsigned int kw = sm->kept_w[cur][q], rw = sm->removed_w[cur][q];
+                        hit_kept |= (p[q] & kw) != 0u;
+                        pending |= (p[q] & ~(kw | rw)) != 0u;
                     }
                     if (hit_kept) state = 2;
                     else if (!pending) state = 1;
                 }
-                __syncthreads();  // all reads of kept_w/removed_w done before they are updated
                 const unsigned int km = __ballot_sync(0xffffffffu, state == 1);
                 const unsigned int rm = __ballot_sync(0xffffffffu, state == 2);
-                if (lane == 0) { sm->kept_w[warp] = km; sm->removed_w[warp] = rm; }
-                if (__syncthreads_or(state == 0) == 0) break;
+                if (lane == 0) {
+                    sm->kept_w[cur ^ 1][warp] = km;
+                    sm->removed_w[cur ^ 1][warp] = rm;
+                }
+                cur ^= 1;
+                if (prof) dbg[DBG_ITERS] += 1;
+                if (!bar_or(1, kChunk, state == 0)) break;
             }
+            fin = cur;
         }
-        // kept_w now final (visible after the barrier inside __syncthreads_or)
+        // every thread needs the final buffer index: it is uniform over the first kChunk threads
+        fin = __syncthreads_or(fin);
+        FRR_TICK(DBG_P4);
 
-        // ---- phase 5: append kept survivors ---------------------------------------------------------
+        // ---- phase 5: append kept survivors --------------------------------------------------------------
         {
             int koff = 0, ktot = 0;
 #pragma unroll
-            for (int w2 = 0; w2 < kNmsWarps; ++w2) {
-                const int c = __popc(sm->kept_w[w2]);
-                if (w2 < warp) koff += c;
-                ktot += c;
+            for (int w2 = 0; w2 < kChunkWords; ++w2) {
+                const int cc = __popc(sm->kept_w[fin][w2]);
+                if (w2 < warp) koff += cc;
+                ktot += cc;
             }
-            const unsigned int kw = sm->kept_w[warp];
-            if ((kw >> lane) & 1u) {
-                const int o = nk + koff + __popc(kw & ((1u << lane) - 1u));
-                if (o < max_keep) {
-                    const float4 kb = sm->sbox[tid];
-                    if (o % S == rank) {
-                        kbox[o / S] = kb;
-                        karea[o / S] = sm->sarea[tid];
-                    }
-                    if (rank == 0) {
-                        ikeep[o] = base + (int)sm->ssrc[tid];
-                        if (iout) iout[o] = kb;
+            if (tid < kChunk) {
+                const unsigned int kw = sm->kept_w[fin][warp];
+                if ((kw >> lane) & 1u) {
+                    const int o = nk + koff + __popc(kw & ((1u << lane) - 1u));
+                    if (o < max_keep) {
+                        const float4 kb = sm->sbox[tid];
+                        if (o % S == rank) {
+                            kbox[o / S] = kb;
+                            karea[o / S] = sm->sarea[tid];
+                        }
+                        if (rank == 0) {
+                            ikeep[o] = base + (int)sm->ssrc[tid];
+                            if (iout) iout[o] = kb;
+                        }
                     }
                 }
             }
             nk = min(nk + ktot, max_keep);
         }
         __syncthreads();
+        FRR_TICK(DBG_P5);
     }
+#undef FRR_TICK
 
     if (rank == 0) {
-        for (int o = nk + tid; o < max_keep; o += kNmsThreads) {
+        for (int o = nk + tid; o < max_keep; o += kThreads) {
             ikeep[o] = -1;
             if (iout) iout[o] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -255,9 +369,9 @@ static NmsThr make_thr(double thr) {
         if (!((double)f > thr)) f = nextafterf(f, INFINITY);
         t.up = f;
     }
-    t.fast = (thr > 0.0) && isfinite(thr) && (t.up < 1.0e30f) ? 1 : 0;
-    t.c_lo = t.up * (1.0f - 9.5367431640625e-07f);
-    t.c_hi = t.up * (1.0f + 9.5367431640625e-07f);
+    t.fast = (thr >= 1.0e-6) && isfinite(thr) && (t.up < 1.0e30f) ? 1 : 0;
+    const double u = (double)t.up;
+    t.c2 = t.fast ? (float)(u / (1.0 + u) * (1.0 - 1.9073486328125e-06)) : 0.f;
     return t;
 }
 
@@ -265,20 +379,16 @@ static size_t nms_smem_bytes(int slice_cap) {
     return ((sizeof(NmsSmem) + 15) & ~(size_t)15) + (size_t)slice_cap * (sizeof(float4) + sizeof(float));
 }
 
-}  // namespace frr
-
-extern "C" int frr_nms_sorted(const float* boxes, const int32_t* counts, int B, int n, double iou_thr, int max_keep,
-                              int32_t* keep, int32_t* keep_count, float* out_boxes, int cluster_size,
-                              frr_stream_t stream) {
-    using namespace frr;
+static int nms_launch(const float* boxes, const int32_t* counts, int B, int n, double iou_thr, int max_keep,
+                      int32_t* keep, int32_t* keep_count, float* out_boxes, int cluster_size, int threads,
+                      long long* dbg, frr_stream_t stream) {
     FRR_CHECK_ARG(keep && keep_count, "frr_nms_sorted: null output");
     FRR_CHECK_ARG(B >= 0 && n >= 0 && max_keep >= 0, "frr_nms_sorted: bad sizes B=%d n=%d max_keep=%d", B, n, max_keep);
     FRR_CHECK_ARG(n == 0 || (boxes && aligned16(boxes)), "frr_nms_sorted: boxes must be non-null, 16-byte aligned");
     FRR_CHECK_ARG(out_boxes == nullptr || aligned16(out_boxes), "frr_nms_sorted: out_boxes must be 16-byte aligned");
+    FRR_CHECK_ARG(threads == 0 || threads == 256 || threads == 512 || threads == 1024,
+                  "frr_nms_sorted: threads %d not in {0,256,512,1024}", threads);
     if (B == 0) return FRR_OK;
-    if (max_keep > n) {
-        // keep buffers are [B,max_keep]; more than n can never be kept, but the stride stays max_keep
-    }
     const int kcap = max_keep < n ? max_keep : n;  // most boxes that can ever be kept
     int S = cluster_size;
     if (S == 0) {
@@ -288,6 +398,7 @@ extern "C" int frr_nms_sorted(const float* boxes, const int32_t* counts, int B, 
         while (S * 2 <= per && S < 8) S *= 2;
     }
     FRR_CHECK_ARG(S == 1 || S == 2 || S == 4 || S == 8 || S == 16, "frr_nms_sorted: cluster_size %d not in {1,2,4,8,16}", S);
+    if (threads == 0) threads = 1024;
     // grow the cluster until a slice of the kept list fits in shared memory
     const size_t limit = 227 * 1024;
     while (nms_smem_bytes((kcap + S - 1) / S + 1) > limit && S < 16) S *= 2;
@@ -296,13 +407,20 @@ extern "C" int frr_nms_sorted(const float* boxes, const int32_t* counts, int B, 
     FRR_CHECK_ARG(smem <= limit, "frr_nms_sorted: max_keep=%d does not fit the kept list in shared memory", max_keep);
 
     const NmsThr thr = make_thr(iou_thr);
-    auto kern = thr.fast ? nms_keeplist_kernel<true> : nms_keeplist_kernel<false>;
+    using kern_t = void (*)(const float4*, const int32_t*, int, int, int, NmsThr, int32_t*, int32_t*, float4*, long long*);
+    kern_t kern = nullptr;
+    if (thr.fast)
+        kern = threads == 256 ? nms_keeplist_kernel<256, true>
+                              : threads == 512 ? nms_keeplist_kernel<512, true> : nms_keeplist_kernel<1024, true>;
+    else
+        kern = threads == 256 ? nms_keeplist_kernel<256, false>
+                              : threads == 512 ? nms_keeplist_kernel<512, false> : nms_keeplist_kernel<1024, false>;
     FRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
     if (S > 8) FRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
 
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(B * S), 1, 1);
-    cfg.blockDim = dim3(kNmsThreads, 1, 1);
+    cfg.blockDim = dim3((unsigned)threads, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
@@ -313,8 +431,24 @@ extern "C" int frr_nms_sorted(const float* boxes, const int32_t* counts, int B, 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     FRR_CUDA(cudaLaunchKernelEx(&cfg, kern, (const float4*)boxes, counts, n, max_keep, slice_cap, thr, keep, keep_count,
-                                (float4*)out_boxes));
+                                (float4*)out_boxes, dbg));
     count_launch();
     FRR_CHECK_LAUNCH("nms_keeplist_kernel");
     return FRR_OK;
+}
+
+}  // namespace frr
+
+extern "C" int frr_nms_sorted(const float* boxes, const int32_t* counts, int B, int n, double iou_thr, int max_keep,
+                              int32_t* keep, int32_t* keep_count, float* out_boxes, int cluster_size,
+                              frr_stream_t stream) {
+    return frr::nms_launch(boxes, counts, B, n, iou_thr, max_keep, keep, keep_count, out_boxes, cluster_size, 0, nullptr,
+                           stream);
+}
+
+extern "C" int frr_nms_sorted_tuned(const float* boxes, const int32_t* counts, int B, int n, double iou_thr, int max_keep,
+                                    int32_t* keep, int32_t* keep_count, float* out_boxes, int cluster_size, int threads,
+                                    int64_t* dbg_cycles, frr_stream_t stream) {
+    return frr::nms_launch(boxes, counts, B, n, iou_thr, max_keep, keep, keep_count, out_boxes, cluster_size, threads,
+                           (long long*)dbg_cycles, stream);
 }

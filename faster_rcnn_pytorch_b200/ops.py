@@ -115,7 +115,7 @@ def topk_desc(scores, k: int, valid=None, boxes=None, want_cidx: bool = False):
 
 
 def nms_sorted(boxes, iou_threshold: float, max_keep: int | None = None, counts=None, gather: bool = True,
-               cluster_size: int = 0):
+               cluster_size: int = 0, threads: int = 0, dbg=None):
     """N1 on score-sorted boxes [B,n,4].  Returns keep int32 [B,max_keep] (-1 padded), count int32 [B],
     rois [B,max_keep,4] (zero padded) or None."""
     lib = _lib.load()
@@ -131,6 +131,7 @@ def nms_sorted(boxes, iou_threshold: float, max_keep: int | None = None, counts=
         keep = torch.empty((B, mk), dtype=torch.int32, device=dev)
         cnt = torch.empty((B,), dtype=torch.int32, device=dev)
         rois = torch.empty((B, mk, 4), dtype=torch.float32, device=dev) if gather else None
-        _lib.check(lib.frr_nms_sorted(boxes.data_ptr(), _ptr(counts), B, n, float(iou_threshold), mk, keep.data_ptr(),
-                                      cnt.data_ptr(), _ptr(rois), int(cluster_size), _stream()), "frr_nms_sorted")
+        _lib.check(lib.frr_nms_sorted_tuned(boxes.data_ptr(), _ptr(counts), B, n, float(iou_threshold), mk,
+                                            keep.data_ptr(), cnt.data_ptr(), _ptr(rois), int(cluster_size), int(threads),
+                                            _ptr(dbg), _stream()), "frr_nms_sorted")
     return keep, cnt, rois

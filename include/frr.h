@@ -90,6 +90,12 @@ int frr_nms_sorted(const float* boxes /* [B,n,4] */, const int32_t* counts /* [B
                    int n, double iou_thr, int max_keep, int32_t* keep /* [B,max_keep] */,
                    int32_t* keep_count /* [B] */, float* out_boxes /* [B,max_keep,4] or NULL */,
                    int cluster_size, frr_stream_t stream);
+/* Same, with tuning / profiling knobs: threads per CTA (0 = auto, 256, 512 or 1024); dbg_cycles = NULL
+ * or int64[16] accumulating per-phase clock64() cycles of CTA 0 (slots: chunks, load, phase1, cluster
+ * sync, phase2..5, survivors, fix-point rounds).                                                  */
+int frr_nms_sorted_tuned(const float* boxes, const int32_t* counts, int B, int n, double iou_thr, int max_keep,
+                         int32_t* keep, int32_t* keep_count, float* out_boxes, int cluster_size, int threads,
+                         int64_t* dbg_cycles, frr_stream_t stream);
 
 #ifdef __cplusplus
 #pragma GCC visibility pop

@@ -1,0 +1,47 @@
+"""Developer tool: NMS kernel timing + per-phase cycle breakdown on the config-2 workload (GPU box)."""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from faster_rcnn_pytorch_b200 import ops, synth
+
+HW = (608, 1008)
+dev = torch.device("cuda:0")
+B = int(os.environ.get("NMS_B", "64"))
+ins = [synth.rpn_head_outputs(2000 + i, HW) for i in range(B)]
+reg = torch.from_numpy(np.stack([x[1] for x in ins])).to(dev)
+sc = torch.from_numpy(np.stack([x[2] for x in ins])).to(dev)
+boxes, scores, valid = ops.rpn_decode(reg, sc, image_hw=HW)
+top = ops.topk_desc(scores, 12000, valid=valid, boxes=boxes)
+tb, tc = top["boxes"], top["count"]
+names = ["chunks", "load", "p1", "sync", "p2", "p3", "p4", "p5", "surv", "iters"]
+
+
+def run(bx, cnt, S, threads, reps=20, dbg=False):
+    d = torch.zeros(16, dtype=torch.int64, device=dev) if dbg else None
+    for _ in range(3):
+        ops.nms_sorted(bx, 0.7, max_keep=2000, counts=cnt, cluster_size=S, threads=threads)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        ops.nms_sorted(bx, 0.7, max_keep=2000, counts=cnt, cluster_size=S, threads=threads)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    out = {"B": bx.shape[0], "S": S, "threads": threads, "us": round(ms * 1e3, 1)}
+    if dbg:
+        keep, c, _ = ops.nms_sorted(bx, 0.7, max_keep=2000, counts=cnt, cluster_size=S, threads=threads, dbg=d)
+        torch.cuda.synchronize()
+        out.update({k: int(v) for k, v in zip(names, d.cpu().tolist())})
+        out["kept"] = int(c[0])
+        out["last_keep_pos"] = int(keep[0, int(c[0]) - 1])
+    print(json.dumps(out), flush=True)
+
+
+for threads in (256, 512, 1024):
+    for S in (1, 2):
+        run(tb, tc, S, threads, dbg=True)
+one, onec = tb[:1].contiguous(), tc[:1].contiguous()
+for threads in (256, 512, 1024):
+    for S in (4, 8, 16):
+        run(one, onec, S, threads, reps=50, dbg=True)
