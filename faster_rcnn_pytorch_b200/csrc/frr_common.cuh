@@ -75,6 +75,33 @@ __device__ __forceinline__ float ordered_to_float(uint32_t u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
+// block-wide exclusive scan of one value per thread for a 1024-thread CTA; returns the exclusive prefix,
+// the block total in *total.  warp_tmp: 32 words of shared memory.  Must be called by all threads.
+__device__ __forceinline__ unsigned int block_exclusive_scan(unsigned int v, unsigned int* warp_tmp,
+                                                             unsigned int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = (blockDim.x + 31) >> 5;
+    unsigned int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __syncthreads();  // warp_tmp reuse
+    if (lane == 31) warp_tmp[warp] = inc;
+    __syncthreads();
+    unsigned int wsum = (lane < nwarps) ? warp_tmp[lane] : 0u;
+    unsigned int winc = wsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned int t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += t;
+    }
+    const unsigned int wexc = __shfl_sync(0xffffffffu, winc - wsum, warp);
+    *total = __shfl_sync(0xffffffffu, winc, 31);
+    return wexc + inc - v;
+}
+
 struct AnchorTable {
     float v[16 * 4];
     int A;

@@ -379,7 +379,7 @@ static size_t nms_smem_bytes(int slice_cap) {
     return ((sizeof(NmsSmem) + 15) & ~(size_t)15) + (size_t)slice_cap * (sizeof(float4) + sizeof(float));
 }
 
-static int nms_launch(const float* boxes, const int32_t* counts, int B, int n, double iou_thr, int max_keep,
+int nms_launch(const float* boxes, const int32_t* counts, int B, int n, double iou_thr, int max_keep,
                       int32_t* keep, int32_t* keep_count, float* out_boxes, int cluster_size, int threads,
                       long long* dbg, frr_stream_t stream) {
     FRR_CHECK_ARG(keep && keep_count, "frr_nms_sorted: null output");

@@ -28,31 +28,6 @@ struct TopkSmemHeader {
     unsigned int nvalid;
 };
 
-// block-wide exclusive scan of one value per thread (1024 threads); returns exclusive prefix, total in *total
-__device__ __forceinline__ unsigned int block_exclusive_scan(unsigned int v, unsigned int* warp_tmp,
-                                                             unsigned int* total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned int inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    __syncthreads();  // warp_tmp reuse
-    if (lane == 31) warp_tmp[warp] = inc;
-    __syncthreads();
-    unsigned int wsum = (lane < kTopkWarps) ? warp_tmp[lane] : 0u;
-    unsigned int winc = wsum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        unsigned int t = __shfl_up_sync(0xffffffffu, winc, o);
-        if (lane >= o) winc += t;
-    }
-    const unsigned int wexc = __shfl_sync(0xffffffffu, winc - wsum, warp);
-    *total = __shfl_sync(0xffffffffu, winc, 31);
-    return wexc + inc - v;
-}
-
 __global__ void __launch_bounds__(kTopkThreads, 1)
     topk_desc_kernel(const float* __restrict__ scores, const uint8_t* __restrict__ valid,
                      const float4* __restrict__ boxes, int N, int k, int P /* pow2 >= k */, int nchunks /* ceil(N/32) */,

@@ -1,0 +1,131 @@
+"""Drop-in replacements for the reference's region-stage call sites (models/model.py:6-9,288-298).
+
+Same class names, constructor arguments, forward signatures, return types and error behaviour as the
+reference modules, single image per call like the reference; every computation is a libfrr kernel.  The
+batched, sync-free entry points are in ``region.py`` / ``targets.py``.
+
+    from faster_rcnn_pytorch_b200.modules import nms, RoIPool, RegionProposal, RPNTargetMaker, FastRcnnTargetMaker
+    from faster_rcnn_pytorch_b200.anchor import FRCNNAnchorMaker
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops, region, targets
+
+__all__ = ["nms", "roi_pool", "roi_align", "RoIPool", "RoIAlign", "RegionProposal", "RPNTargetMaker",
+           "FastRcnnTargetMaker", "predict_tail", "suppress"]
+
+roi_pool = ops.roi_pool
+roi_align = ops.roi_align
+
+
+def _as_anchor_tensor(anchor, device):
+    if isinstance(anchor, np.ndarray):
+        anchor = torch.from_numpy(anchor)
+    return anchor.to(device=device, dtype=torch.float32).contiguous()
+
+
+def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float) -> torch.Tensor:
+    """Drop-in for ``torchvision.ops.nms`` (models/model.py:53,394): int64 indices of the kept boxes, sorted by
+    decreasing score; ties keep the lower index first (stable), IoU compared in double like the CPU kernel."""
+    if boxes.dim() != 2 or boxes.shape[1] != 4 or scores.dim() != 1 or scores.shape[0] != boxes.shape[0]:
+        raise RuntimeError("nms: boxes must be [n,4] and scores [n]")
+    n = boxes.shape[0]
+    if n == 0:
+        return torch.empty((0,), dtype=torch.int64, device=boxes.device)
+    if n > 16384:
+        raise ValueError("nms: more than 16384 boxes per call is not on the reference path (<= 12000)")
+    b = boxes.detach().to(torch.float32).contiguous()
+    top = ops.topk_desc(scores.detach().to(torch.float32).reshape(1, n), n, boxes=b.reshape(1, n, 4))
+    keep, cnt, _ = ops.nms_sorted(top["boxes"], float(iou_threshold), gather=False)
+    k = int(cnt[0])
+    return top["idx"][0].index_select(0, keep[0, :k].to(torch.int64)).to(torch.int64)
+
+
+class RoIPool(nn.Module):
+    """Drop-in for ``torchvision.ops.RoIPool`` (models/model.py:97)."""
+
+    def __init__(self, output_size, spatial_scale: float):
+        super().__init__()
+        self.output_size = output_size
+        self.spatial_scale = spatial_scale
+
+    def forward(self, input, rois):
+        return ops.roi_pool(input, rois, self.output_size, self.spatial_scale)
+
+
+class RoIAlign(nn.Module):
+    """Drop-in for ``torchvision.ops.RoIAlign`` (the 7x7, sampling_ratio=2 pooler of models/new_model.py:127)."""
+
+    def __init__(self, output_size, spatial_scale: float, sampling_ratio: int, aligned: bool = False):
+        super().__init__()
+        self.output_size, self.spatial_scale = output_size, spatial_scale
+        self.sampling_ratio, self.aligned = sampling_ratio, aligned
+
+    def forward(self, input, rois):
+        return ops.roi_align(input, rois, self.output_size, self.spatial_scale, self.sampling_ratio, self.aligned)
+
+
+class RegionProposal(nn.Module):
+    """models/model.py:12-58.  ``forward(cls [N,2], reg [N,4], anchor [N,4], mode)`` -> rois [<=2000|300, 4]."""
+
+    def __init__(self):
+        super().__init__()
+        self.min_size = 1
+
+    def forward(self, cls, reg, anchor, mode):
+        if mode not in region.PROPOSAL_MODES:
+            mode = "train"          # the reference only special-cases 'test' (:26)
+        anchor = _as_anchor_tensor(anchor, reg.device)
+        rois, count = region.rpn_proposals(cls.detach().unsqueeze(0).to(torch.float32), reg.detach().unsqueeze(0).to(torch.float32),
+                                           anchors=anchor, mode=mode)
+        return rois[0, :int(count[0])]     # ragged like the reference: one host sync
+
+
+class RPNTargetMaker(nn.Module):
+    """models/model.py:182-266.  ``forward(bbox [G,4], anchor [N,4])`` -> (rpn_tg_cls int64 [N], rpn_tg_reg [N,4])."""
+
+    def __init__(self):
+        super().__init__()
+
+    def forward(self, bbox, anchor):
+        anchor = _as_anchor_tensor(anchor, bbox.device)
+        labels, reg = targets.rpn_targets(bbox.detach().to(torch.float32).reshape(1, -1, 4), None, anchors=anchor)
+        return labels[0], reg[0]
+
+
+class FastRcnnTargetMaker(nn.Module):
+    """models/model.py:123-179.  ``forward(bbox [list of [G,4]], label [list of [G]], rois [R,4])`` ->
+    (fast_rcnn_tg_cls int64 [<=128], fast_rcnn_tg_reg [<=128,4], sample_rois [<=128,4])."""
+
+    def __init__(self):
+        super().__init__()
+
+    def forward(self, bbox, label, rois):
+        bbox = bbox[0]      # remove the list for batch (:130-131)
+        label = label[0]
+        cls, reg, srois, _, n = targets.frcnn_targets(rois.detach().to(torch.float32).unsqueeze(0), None,
+                                                      bbox.detach().to(torch.float32).unsqueeze(0), None,
+                                                      label.detach().to(torch.int64).unsqueeze(0))
+        k = int(n[0])
+        return cls[0, :k], reg[0, :k], srois[0, :k]
+
+
+def predict_tail(pred_cls, pred_reg, rois, num_classes: int):
+    """models/model.py:369-378: (prob [R,C], clamped per-class boxes [R,4C])."""
+    return ops.decode_classwise(pred_cls.detach().to(torch.float32), pred_reg.detach().to(torch.float32).reshape(-1, num_classes * 4),
+                                rois.detach().to(torch.float32), num_classes)
+
+
+def suppress(raw_cls_bbox, raw_prob, num_classes: int, thres: float):
+    """``FRCNN._suppress`` (models/model.py:382-402): numpy (bbox f32 [D,4], label i32 [D], score f32 [D])."""
+    R = raw_prob.shape[0]
+    db, dl, ds, dc = ops.class_nms(raw_prob.detach().to(torch.float32).reshape(1, R, num_classes),
+                                   raw_cls_bbox.detach().to(torch.float32).reshape(1, R, num_classes * 4), num_classes,
+                                   score_thres=thres, iou_thr=0.3)
+    d = int(dc[0])                        # one host sync (the reference: two per class)
+    return (db[0, :d].cpu().numpy().astype(np.float32), dl[0, :d].cpu().numpy().astype(np.int32),
+            ds[0, :d].cpu().numpy().astype(np.float32))

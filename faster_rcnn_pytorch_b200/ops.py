@@ -135,3 +135,303 @@ def nms_sorted(boxes, iou_threshold: float, max_keep: int | None = None, counts=
                                             keep.data_ptr(), cnt.data_ptr(), _ptr(rois), int(cluster_size), int(threads),
                                             _ptr(dbg), _stream()), "frr_nms_sorted")
     return keep, cnt, rois
+
+
+# ------------------------------------------------------------------------------------------------
+# RoIPool / RoIAlign (R1-R4): raw kernels + autograd functions
+# ------------------------------------------------------------------------------------------------
+def _feat_layout(feat: torch.Tensor):
+    """Returns (tensor usable in place, channels_last flag).  NCHW-contiguous and channels_last memory are both
+    consumed without a copy; anything else is made NCHW-contiguous."""
+    if feat.dim() != 4:
+        raise ValueError("features must be [B,C,H,W]")
+    if feat.is_contiguous():
+        return feat, 0
+    if feat.is_contiguous(memory_format=torch.channels_last):
+        return feat, 1
+    return feat.contiguous(), 0
+
+
+def convert_rois(rois, device=None) -> torch.Tensor:
+    """torchvision's convention (TV ops/_utils.py:18-25): Tensor[K,5] or list of Tensor[L,4] (one per image)."""
+    if isinstance(rois, (list, tuple)):
+        parts = []
+        for i, r in enumerate(rois):
+            idx = torch.full((r.shape[0], 1), float(i), dtype=r.dtype, device=r.device)
+            parts.append(torch.cat([idx, r], dim=1))
+        rois = torch.cat(parts, dim=0) if parts else torch.zeros((0, 5), dtype=torch.float32, device=device)
+    if rois.dim() != 2 or rois.shape[1] != 5:
+        raise ValueError("rois must be Tensor[K,5] or a list of Tensor[L,4]")
+    return rois
+
+
+def roi_pool_forward(feat, rois5, output_size=(7, 7), spatial_scale: float = 1.0, want_argmax: bool = True):
+    lib = _lib.load()
+    feat = _req(feat, "features") if feat.is_contiguous() else feat
+    if not feat.is_cuda or feat.dtype != torch.float32:
+        raise ValueError("features must be a CUDA fp32 tensor: the region stage has no CPU path")
+    feat, cl = _feat_layout(feat)
+    rois5 = _req(rois5, "rois")
+    B, C, H, W = feat.shape
+    K = rois5.shape[0]
+    PH, PW = int(output_size[0]), int(output_size[1])
+    with torch.cuda.device(feat.device):
+        out = torch.empty((K, C, PH, PW), dtype=torch.float32, device=feat.device)
+        arg = torch.empty((K, C, PH, PW), dtype=torch.int32, device=feat.device) if want_argmax else None
+        _lib.check(lib.frr_roi_pool_fwd(feat.data_ptr(), rois5.data_ptr(), K, B, C, H, W, PH, PW, float(spatial_scale), cl,
+                                        out.data_ptr(), _ptr(arg), _stream()), "frr_roi_pool_fwd")
+    return out, arg
+
+
+def roi_pool_backward(grad_out, argmax, rois5, feat_shape, spatial_scale: float = 1.0, channels_last: bool = False):
+    lib = _lib.load()
+    grad_out = _req(grad_out, "grad_out")
+    argmax = _req(argmax, "argmax", torch.int32)
+    rois5 = _req(rois5, "rois")
+    B, C, H, W = feat_shape
+    K, _, PH, PW = grad_out.shape
+    with torch.cuda.device(grad_out.device):
+        gin = torch.empty((B, C, H, W), dtype=torch.float32, device=grad_out.device,
+                          memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+        _lib.check(lib.frr_roi_pool_bwd(grad_out.data_ptr(), argmax.data_ptr(), rois5.data_ptr(), K, B, C, H, W, PH, PW,
+                                        float(spatial_scale), int(channels_last), gin.data_ptr(), _stream()),
+                   "frr_roi_pool_bwd")
+    return gin
+
+
+def roi_align_forward(feat, rois5, output_size=(7, 7), spatial_scale: float = 1.0, sampling_ratio: int = 2,
+                      aligned: bool = False):
+    lib = _lib.load()
+    if not feat.is_cuda or feat.dtype != torch.float32:
+        raise ValueError("features must be a CUDA fp32 tensor: the region stage has no CPU path")
+    feat, cl = _feat_layout(feat)
+    rois5 = _req(rois5, "rois")
+    B, C, H, W = feat.shape
+    K = rois5.shape[0]
+    PH, PW = int(output_size[0]), int(output_size[1])
+    with torch.cuda.device(feat.device):
+        out = torch.empty((K, C, PH, PW), dtype=torch.float32, device=feat.device)
+        _lib.check(lib.frr_roi_align_fwd(feat.data_ptr(), rois5.data_ptr(), K, B, C, H, W, PH, PW, float(spatial_scale),
+                                         int(sampling_ratio), int(aligned), cl, out.data_ptr(), _stream()),
+                   "frr_roi_align_fwd")
+    return out
+
+
+def roi_align_backward(grad_out, rois5, feat_shape, spatial_scale: float = 1.0, sampling_ratio: int = 2,
+                       aligned: bool = False, channels_last: bool = False):
+    lib = _lib.load()
+    grad_out = _req(grad_out, "grad_out")
+    rois5 = _req(rois5, "rois")
+    B, C, H, W = feat_shape
+    K, _, PH, PW = grad_out.shape
+    with torch.cuda.device(grad_out.device):
+        gin = torch.empty((B, C, H, W), dtype=torch.float32, device=grad_out.device,
+                          memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+        _lib.check(lib.frr_roi_align_bwd(grad_out.data_ptr(), rois5.data_ptr(), K, B, C, H, W, PH, PW, float(spatial_scale),
+                                         int(sampling_ratio), int(aligned), int(channels_last), gin.data_ptr(), _stream()),
+                   "frr_roi_align_bwd")
+    return gin
+
+
+class _RoIPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, rois5, output_size, spatial_scale):
+        feat_l, cl = _feat_layout(feat)
+        out, arg = roi_pool_forward(feat_l, rois5, output_size, spatial_scale, want_argmax=True)
+        ctx.save_for_backward(rois5, arg)
+        ctx.meta = (tuple(feat.shape), float(spatial_scale), bool(cl))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        rois5, arg = ctx.saved_tensors
+        shape, scale, cl = ctx.meta
+        return roi_pool_backward(grad_out.contiguous(), arg, rois5, shape, scale, cl), None, None, None
+
+
+class _RoIAlignFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, rois5, output_size, spatial_scale, sampling_ratio, aligned):
+        feat_l, cl = _feat_layout(feat)
+        out = roi_align_forward(feat_l, rois5, output_size, spatial_scale, sampling_ratio, aligned)
+        ctx.save_for_backward(rois5)
+        ctx.meta = (tuple(feat.shape), float(spatial_scale), int(sampling_ratio), bool(aligned), bool(cl))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (rois5,) = ctx.saved_tensors
+        shape, scale, sr, al, cl = ctx.meta
+        return roi_align_backward(grad_out.contiguous(), rois5, shape, scale, sr, al, cl), None, None, None, None, None
+
+
+def roi_pool(input, boxes, output_size, spatial_scale: float = 1.0):
+    """Drop-in for torchvision.ops.roi_pool (differentiable w.r.t. ``input``)."""
+    if isinstance(output_size, int):
+        output_size = (output_size, output_size)
+    rois5 = convert_rois(boxes, input.device).to(torch.float32)
+    return _RoIPoolFn.apply(input, rois5.contiguous(), tuple(output_size), float(spatial_scale))
+
+
+def roi_align(input, boxes, output_size, spatial_scale: float = 1.0, sampling_ratio: int = -1, aligned: bool = False):
+    """Drop-in for torchvision.ops.roi_align (differentiable w.r.t. ``input``)."""
+    if isinstance(output_size, int):
+        output_size = (output_size, output_size)
+    rois5 = convert_rois(boxes, input.device).to(torch.float32)
+    return _RoIAlignFn.apply(input, rois5.contiguous(), tuple(output_size), float(spatial_scale), int(sampling_ratio),
+                             bool(aligned))
+
+
+# ------------------------------------------------------------------------------------------------
+# target makers (T1-T4): raw two-phase kernels; the host sampling logic lives in targets.py
+# ------------------------------------------------------------------------------------------------
+_STD4 = np.array([0.1, 0.1, 0.2, 0.2], dtype=np.float32)       # models/model.py:176,372
+
+
+def rpn_targets_assign(gt, gt_count, N, image_hw=None, anchors=None, stride=16, table=None, neg_thr=0.3, pos_thr=0.7):
+    lib = _lib.load()
+    gt = _req(gt, "gt")
+    if gt.dim() != 3 or gt.shape[-1] != 4:
+        raise ValueError("gt must be [B,Gmax,4]")
+    B, G = gt.shape[0], gt.shape[1]
+    if G == 0:
+        raise IndexError("max(): Expected reduction dim 1 to have non-zero size")   # models/model.py:199
+    if gt_count is not None:
+        gt_count = _req(gt_count, "gt_count", torch.int32)
+    keep, tptr, A = _table_arg(table)
+    if anchors is not None:
+        anchors = _req(anchors, "anchors")
+        H = W = 0
+    else:
+        H, W = int(image_hw[0]), int(image_hw[1])
+    dev = gt.device
+    with torch.cuda.device(dev):
+        ws = dict(iou_max=torch.empty((B, N), dtype=torch.float32, device=dev),
+                  argmax=torch.empty((B, N), dtype=torch.int32, device=dev),
+                  label8=torch.empty((B, N), dtype=torch.int8, device=dev),
+                  pos_list=torch.empty((B, N), dtype=torch.int32, device=dev),
+                  neg_list=torch.empty((B, N), dtype=torch.int32, device=dev),
+                  counts=torch.empty((B, 2), dtype=torch.int32, device=dev))
+        _lib.check(lib.frr_rpn_targets_assign(gt.data_ptr(), _ptr(gt_count), B, G, _ptr(anchors), tptr, A, H, W, stride, N,
+                                              float(np.float32(neg_thr)), float(np.float32(pos_thr)),
+                                              ws["iou_max"].data_ptr(), ws["argmax"].data_ptr(), ws["label8"].data_ptr(),
+                                              ws["pos_list"].data_ptr(), ws["neg_list"].data_ptr(), ws["counts"].data_ptr(),
+                                              _stream()), "frr_rpn_targets_assign")
+    ws.update(gt=gt, anchors=anchors, geom=(H, W, stride, table, N))
+    return ws
+
+
+def rpn_targets_finalize(ws, disable=None, disable_off=None):
+    lib = _lib.load()
+    gt, anchors = ws["gt"], ws["anchors"]
+    H, W, stride, table, N = ws["geom"]
+    keep, tptr, A = _table_arg(table)
+    B, G = gt.shape[0], gt.shape[1]
+    dev = gt.device
+    with torch.cuda.device(dev):
+        labels = torch.empty((B, N), dtype=torch.int64, device=dev)
+        reg = torch.empty((B, N, 4), dtype=torch.float32, device=dev)
+        _lib.check(lib.frr_rpn_targets_finalize(gt.data_ptr(), B, G, _ptr(anchors), tptr, A, H, W, stride, N,
+                                                ws["argmax"].data_ptr(), ws["label8"].data_ptr(), ws["pos_list"].data_ptr(),
+                                                ws["neg_list"].data_ptr(), _ptr(disable), _ptr(disable_off),
+                                                labels.data_ptr(), reg.data_ptr(), _stream()), "frr_rpn_targets_finalize")
+    return labels, reg
+
+
+def frcnn_targets_assign(rois, roi_count, gt, gt_count, fg_thr=0.5):
+    lib = _lib.load()
+    rois = _req(rois, "rois")
+    gt = _req(gt, "gt")
+    B, R = rois.shape[0], rois.shape[1]
+    G = gt.shape[1]
+    if G == 0:
+        raise IndexError("max(): Expected reduction dim 1 to have non-zero size")
+    if roi_count is not None:
+        roi_count = _req(roi_count, "roi_count", torch.int32)
+    if gt_count is not None:
+        gt_count = _req(gt_count, "gt_count", torch.int32)
+    M = R + G
+    dev = rois.device
+    with torch.cuda.device(dev):
+        ws = dict(iou_max=torch.empty((B, M), dtype=torch.float32, device=dev),
+                  argmax=torch.empty((B, M), dtype=torch.int32, device=dev),
+                  label8=torch.empty((B, M), dtype=torch.int8, device=dev),
+                  pos_list=torch.empty((B, M), dtype=torch.int32, device=dev),
+                  neg_list=torch.empty((B, M), dtype=torch.int32, device=dev),
+                  counts=torch.empty((B, 2), dtype=torch.int32, device=dev))
+        _lib.check(lib.frr_frcnn_targets_assign(rois.data_ptr(), _ptr(roi_count), B, R, gt.data_ptr(), _ptr(gt_count), G,
+                                                float(np.float32(fg_thr)), ws["iou_max"].data_ptr(), ws["argmax"].data_ptr(),
+                                                ws["label8"].data_ptr(), ws["pos_list"].data_ptr(), ws["neg_list"].data_ptr(),
+                                                ws["counts"].data_ptr(), _stream()), "frr_frcnn_targets_assign")
+    ws.update(rois=rois, roi_count=roi_count, gt=gt)
+    return ws
+
+
+def frcnn_targets_finalize(ws, gt_label, sel, sel_n, std=_STD4):
+    lib = _lib.load()
+    rois, gt = ws["rois"], ws["gt"]
+    gt_label = _req(gt_label, "gt_label", torch.int64)
+    sel = _req(sel, "sel", torch.int32)
+    sel_n = _req(sel_n, "sel_n", torch.int32)
+    B, R, G, S = rois.shape[0], rois.shape[1], gt.shape[1], sel.shape[1]
+    std = np.ascontiguousarray(std, dtype=np.float32)
+    dev = rois.device
+    with torch.cuda.device(dev):
+        cls = torch.empty((B, S), dtype=torch.int64, device=dev)
+        reg = torch.empty((B, S, 4), dtype=torch.float32, device=dev)
+        srois = torch.empty((B, S, 4), dtype=torch.float32, device=dev)
+        kidx = torch.empty((B, S), dtype=torch.int32, device=dev)
+        _lib.check(lib.frr_frcnn_targets_finalize(rois.data_ptr(), _ptr(ws["roi_count"]), B, R, gt.data_ptr(),
+                                                  gt_label.data_ptr(), G, ws["argmax"].data_ptr(), ws["pos_list"].data_ptr(),
+                                                  ws["neg_list"].data_ptr(), sel.data_ptr(), sel_n.data_ptr(), S,
+                                                  std.ctypes.data, cls.data_ptr(), reg.data_ptr(), srois.data_ptr(),
+                                                  kidx.data_ptr(), _stream()), "frr_frcnn_targets_finalize")
+    return cls, reg, srois, kidx
+
+
+# ------------------------------------------------------------------------------------------------
+# detection post-processing (D1, D2)
+# ------------------------------------------------------------------------------------------------
+def decode_classwise(cls_logits, reg, rois, num_classes: int, std=_STD4):
+    """cls [rows,C], reg [rows,4C], rois [rows,4] -> prob [rows,C], boxes [rows,4C] (clamped to [0,1])."""
+    lib = _lib.load()
+    cls_logits = _req(cls_logits, "cls_logits")
+    reg = _req(reg, "reg")
+    rois = _req(rois, "rois")
+    rows, C = cls_logits.shape[0], int(num_classes)
+    if cls_logits.shape[1] != C or reg.numel() != rows * C * 4 or rois.numel() != rows * 4:
+        raise ValueError("decode_classwise: shape mismatch")
+    std = np.ascontiguousarray(std, dtype=np.float32)
+    dev = cls_logits.device
+    with torch.cuda.device(dev):
+        prob = torch.empty((rows, C), dtype=torch.float32, device=dev)
+        boxes = torch.empty((rows, C * 4), dtype=torch.float32, device=dev)
+        _lib.check(lib.frr_decode_classwise(cls_logits.data_ptr(), reg.data_ptr(), rois.data_ptr(), rows, C, std.ctypes.data,
+                                            prob.data_ptr(), boxes.data_ptr(), _stream()), "frr_decode_classwise")
+    return prob, boxes
+
+
+def class_nms(prob, boxes, num_classes: int, score_thres: float = 0.05, iou_thr: float = 0.3, roi_count=None, cap=None):
+    """prob [B,R,C], boxes [B,R,4C] -> det_boxes [B,cap,4], det_labels int32 [B,cap], det_scores [B,cap], count [B]."""
+    lib = _lib.load()
+    prob = _req(prob, "prob")
+    boxes = _req(boxes, "boxes")
+    B, R, C = prob.shape[0], prob.shape[1], int(num_classes)
+    if prob.shape[2] != C or boxes.numel() != B * R * C * 4:
+        raise ValueError("class_nms: shape mismatch")
+    if roi_count is not None:
+        roi_count = _req(roi_count, "roi_count", torch.int32)
+    cap = R * (C - 1) if cap is None else int(cap)
+    dev = prob.device
+    with torch.cuda.device(dev):
+        nbytes = int(lib.frr_class_nms_workspace_bytes(B, R, C))
+        ws = torch.empty((nbytes + 256,), dtype=torch.uint8, device=dev)
+        off = (-ws.data_ptr()) % 256
+        db = torch.empty((B, cap, 4), dtype=torch.float32, device=dev)
+        dl = torch.empty((B, cap), dtype=torch.int32, device=dev)
+        ds = torch.empty((B, cap), dtype=torch.float32, device=dev)
+        dc = torch.empty((B,), dtype=torch.int32, device=dev)
+        _lib.check(lib.frr_class_nms(prob.data_ptr(), boxes.data_ptr(), _ptr(roi_count), B, R, C,
+                                     float(np.float32(score_thres)), float(iou_thr), cap, db.data_ptr(), dl.data_ptr(),
+                                     ds.data_ptr(), dc.data_ptr(), ws.data_ptr() + off, nbytes, _stream()), "frr_class_nms")
+    return db, dl, ds, dc

@@ -1,0 +1,105 @@
+"""Host side of the target makers: the reference's sampling logic around the assign/finalize kernels.
+
+The reference draws its samples with ``torch.randperm`` on the host generator and the number and length of
+the draws depend on the data (models/model.py:225-236,147-156).  To reproduce the sampled indices bit for bit
+under ``torch.manual_seed`` the permutations are drawn here, on the host, in the reference's order; the device
+only needs ONE small D2H copy of the candidate counts per batch (the reference syncs >= 5 times per image).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+
+RPN_BATCH, RPN_MAX_POS = 256, 128            # models/model.py:225-236
+FRCNN_BATCH, FRCNN_MAX_POS = 128, 32         # models/model.py:144,151
+
+
+def _perm(randperm, n):
+    p = randperm(int(n))
+    return p.numpy() if isinstance(p, torch.Tensor) else np.asarray(p)
+
+
+def rpn_disable_positions(n_pos: int, n_neg: int, randperm):
+    """models/model.py:225-236: which positions of the ordered positive / negative lists become ignore (-1)."""
+    dis_pos = np.zeros((0,), np.int64)
+    dis_neg = np.zeros((0,), np.int64)
+    if n_pos > RPN_MAX_POS:
+        dis_pos = _perm(randperm, n_pos)[RPN_MAX_POS:]
+    if n_neg > RPN_BATCH - n_pos:
+        if n_pos > RPN_MAX_POS:
+            n_pos = RPN_MAX_POS
+        dis_neg = _perm(randperm, n_neg)[RPN_BATCH - n_pos:]
+    return dis_pos, dis_neg
+
+
+def frcnn_select_positions(n_pos_cand: int, n_neg_cand: int, randperm):
+    """models/model.py:144-156: both permutations are always drawn; returns (positions, n_pos)."""
+    n_pos = int(min(n_pos_cand, FRCNN_MAX_POS))
+    sel_pos = _perm(randperm, n_pos_cand)[:n_pos]
+    sel_neg = _perm(randperm, n_neg_cand)[:FRCNN_BATCH - n_pos]
+    return np.concatenate([sel_pos, sel_neg]).astype(np.int32), n_pos
+
+
+def _upload_disable(per_image, device):
+    flat, off = [], []
+    run = 0
+    for dp, dn in per_image:
+        off += [run, run + len(dp), run + len(dp) + len(dn)]
+        run += len(dp) + len(dn)
+        flat += [dp, dn]
+    flat = np.concatenate(flat).astype(np.int32) if run else np.zeros((1,), np.int32)
+    return (torch.from_numpy(flat).to(device, non_blocking=True),
+            torch.from_numpy(np.asarray(off, dtype=np.int32)).to(device, non_blocking=True))
+
+
+def _upload_select(per_image, device):
+    B = len(per_image)
+    sel = np.zeros((B, FRCNN_BATCH), np.int32)
+    sel_n = np.zeros((B, 2), np.int32)
+    for b, (s, n_pos) in enumerate(per_image):
+        sel[b, :len(s)] = s
+        sel_n[b] = (n_pos, len(s))
+    return torch.from_numpy(sel).to(device, non_blocking=True), torch.from_numpy(sel_n).to(device, non_blocking=True)
+
+
+def rpn_targets(gt, gt_count=None, image_hw=None, anchors=None, N=None, randperm=torch.randperm, **kw):
+    """Batched RPNTargetMaker: gt [B,Gmax,4] (+ gt_count) -> labels int64 [B,N], reg fp32 [B,N,4]."""
+    if N is None:
+        N = anchors.shape[0] if anchors is not None else (image_hw[0] // 16) * (image_hw[1] // 16) * 9
+    ws = ops.rpn_targets_assign(gt, gt_count, N, image_hw=image_hw, anchors=anchors, **kw)
+    counts = ws["counts"].cpu().numpy()                       # the one host sync
+    per_image = [rpn_disable_positions(int(c[0]), int(c[1]), randperm) for c in counts]
+    disable, off = _upload_disable(per_image, gt.device)
+    return ops.rpn_targets_finalize(ws, disable, off)
+
+
+def frcnn_targets(rois, roi_count, gt, gt_count, gt_label, randperm=torch.randperm):
+    """Batched FastRcnnTargetMaker: -> cls int64 [B,128], reg [B,128,4], sample_rois [B,128,4], n int32 [B] (host)."""
+    ws = ops.frcnn_targets_assign(rois, roi_count, gt, gt_count)
+    counts = ws["counts"].cpu().numpy()
+    per_image = [frcnn_select_positions(int(c[0]), int(c[1]), randperm) for c in counts]
+    sel, sel_n = _upload_select(per_image, rois.device)
+    cls, reg, srois, kidx = ops.frcnn_targets_finalize(ws, gt_label, sel, sel_n)
+    return cls, reg, srois, kidx, np.asarray([len(s) for s, _ in per_image], dtype=np.int32)
+
+
+def make_targets(gt, gt_count, gt_label, rois, roi_count, image_hw=None, anchors=None, N=None, randperm=torch.randperm):
+    """Both target makers for a batch with a single host synchronisation.  Permutations are drawn per image
+    in the reference's order (RPN positives, RPN negatives, Fast R-CNN positives, Fast R-CNN negatives)."""
+    if N is None:
+        N = anchors.shape[0] if anchors is not None else (image_hw[0] // 16) * (image_hw[1] // 16) * 9
+    ws_r = ops.rpn_targets_assign(gt, gt_count, N, image_hw=image_hw, anchors=anchors)
+    ws_f = ops.frcnn_targets_assign(rois, roi_count, gt, gt_count)
+    counts = torch.cat([ws_r["counts"], ws_f["counts"]], dim=1).cpu().numpy()       # one D2H for the batch
+    dis, sels = [], []
+    for c in counts:
+        dis.append(rpn_disable_positions(int(c[0]), int(c[1]), randperm))
+        sels.append(frcnn_select_positions(int(c[2]), int(c[3]), randperm))
+    disable, off = _upload_disable(dis, gt.device)
+    sel, sel_n = _upload_select(sels, gt.device)
+    labels, reg = ops.rpn_targets_finalize(ws_r, disable, off)
+    cls, freg, srois, kidx = ops.frcnn_targets_finalize(ws_f, gt_label, sel, sel_n)
+    return dict(rpn_cls=labels, rpn_reg=reg, frcnn_cls=cls, frcnn_reg=freg, sample_rois=srois, keep_index=kidx,
+                n_samples=np.asarray([len(s) for s, _ in sels], dtype=np.int32))

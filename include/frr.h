@@ -97,6 +97,89 @@ int frr_nms_sorted_tuned(const float* boxes, const int32_t* counts, int B, int n
                          int32_t* keep, int32_t* keep_count, float* out_boxes, int cluster_size, int threads,
                          int64_t* dbg_cycles, frr_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * R1-R3  RoIPool -- torchvision.ops.RoIPool((7,7), 1.0) at models/model.py:97,113 and its autograd
+ *        backward (train.py:36).  Schemas replaced: torchvision::roi_pool(input, rois, spatial_scale,
+ *        ph, pw) -> (out, argmax); torchvision::_roi_pool_backward(grad, rois, argmax, ...).
+ *        feat [B,C,H,W] fp32, NCHW (channels_last=0) or NHWC memory (channels_last=1);
+ *        rois [K,5] = (batch index, x1,y1,x2,y2) fp32; out/argmax [K,C,PH,PW] contiguous
+ *        (argmax int32 = h*W+w, -1 for empty bins; may be NULL in inference).
+ *        Forward max/argmax bit-exact vs torchvision CPU; backward within 1e-5 (fp32 sum order).
+ * ------------------------------------------------------------------------------------- */
+int frr_roi_pool_fwd(const float* feat, const float* rois, int K, int B, int C, int H, int W, int PH, int PW,
+                     float spatial_scale, int channels_last, float* out, int32_t* argmax, frr_stream_t stream);
+/* grad_in [B,C,H,W] (same memory format as feat) is fully written (no pre-zeroing needed). */
+int frr_roi_pool_bwd(const float* grad_out, const int32_t* argmax, const float* rois, int K, int B, int C, int H,
+                     int W, int PH, int PW, float spatial_scale, int channels_last, float* grad_in,
+                     frr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * R4  RoIAlign -- MultiScaleRoIAlign(7, sampling_ratio=2) at models/new_model.py:127,143
+ *     (torchvision::roi_align / _roi_align_backward, aligned=False on the reference path).
+ * ------------------------------------------------------------------------------------- */
+int frr_roi_align_fwd(const float* feat, const float* rois, int K, int B, int C, int H, int W, int PH, int PW,
+                      float spatial_scale, int sampling_ratio, int aligned, int channels_last, float* out,
+                      frr_stream_t stream);
+int frr_roi_align_bwd(const float* grad_out, const float* rois, int K, int B, int C, int H, int W, int PH, int PW,
+                      float spatial_scale, int sampling_ratio, int aligned, int channels_last, float* grad_in,
+                      frr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * T1  RPN target maker -- RPNTargetMaker.forward, models/model.py:186-266 (IoU: utils/util.py:66-102).
+ *     Two kernels around one small D2H copy, because the reference samples with torch.randperm on
+ *     the host generator (:228,:235):
+ *       assign   -> iou_max/argmax [B,N], label8 [B,N] (1 pos, 0 neg, -1 ignore, -2 outside image),
+ *                   order-preserving pos_list/neg_list [B,N] and counts [B,2] = (n_pos, n_neg);
+ *       finalize -> applies `disable` (positions inside pos_list / neg_list to turn into -1; per image
+ *                   disable_off[3b..3b+2] = (start of pos part, start of neg part, end)), encodes
+ *                   (utils/util.py:39-43) and writes labels int64 [B,N], reg fp32 [B,N,4].
+ *     gt [B,Gmax,4] + gt_count [B] (NULL = Gmax each); anchors [N,4] or NULL (generated, A2).
+ *     Thresholds are fp32 compares (reference 0.3f / 0.7f).
+ * ------------------------------------------------------------------------------------- */
+int frr_rpn_targets_assign(const float* gt, const int32_t* gt_count, int B, int Gmax, const float* anchors,
+                           const float* base_table_host, int A, int img_h, int img_w, int stride, int N,
+                           float neg_thr, float pos_thr, float* iou_max, int32_t* argmax, int8_t* label8,
+                           int32_t* pos_list, int32_t* neg_list, int32_t* counts, frr_stream_t stream);
+int frr_rpn_targets_finalize(const float* gt, int B, int Gmax, const float* anchors, const float* base_table_host,
+                             int A, int img_h, int img_w, int stride, int N, const int32_t* argmax, int8_t* label8,
+                             const int32_t* pos_list, const int32_t* neg_list, const int32_t* disable,
+                             const int32_t* disable_off, int64_t* labels, float* reg, frr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * T3  Fast R-CNN target maker -- FastRcnnTargetMaker.forward, models/model.py:127-179.
+ *     assign: boxes = cat(rois[:roi_count], gt[:gt_count]) (M = Rmax+Gmax slots per image), IoU row
+ *     max/argmax, pos (IoU >= fg_thr) / neg ordered lists + counts [B,2].
+ *     finalize: sel [B,S] = positions in pos_list (first n_pos) then neg_list; sel_n [B,2] =
+ *     (n_pos, n_total); writes cls int64 [B,S] (label+1 / 0 / -1 pad), reg [B,S,4] = encode / std,
+ *     sample_rois [B,S,4], keep_index int32 [B,S] (index into the concatenated boxes).
+ * ------------------------------------------------------------------------------------- */
+int frr_frcnn_targets_assign(const float* rois, const int32_t* roi_count, int B, int Rmax, const float* gt,
+                             const int32_t* gt_count, int Gmax, float fg_thr, float* iou_max, int32_t* argmax,
+                             int8_t* label8, int32_t* pos_list, int32_t* neg_list, int32_t* counts,
+                             frr_stream_t stream);
+int frr_frcnn_targets_finalize(const float* rois, const int32_t* roi_count, int B, int Rmax, const float* gt,
+                               const int64_t* gt_label, int Gmax, const int32_t* argmax, const int32_t* pos_list,
+                               const int32_t* neg_list, const int32_t* sel, const int32_t* sel_n, int S,
+                               const float* std4_host, int64_t* cls, float* reg, float* sample_rois,
+                               int32_t* keep_index, frr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * D1  predict tail -- models/model.py:369-378: prob = softmax(cls); boxes = clamp(cxcy_to_xy(
+ *     decode(reg*std, xy_to_cxcy(roi))), 0, 1) per class.  cls [rows,C], reg [rows,C,4],
+ *     rois [rows,4] -> prob [rows,C], boxes [rows,C,4].
+ * D2  FRCNN._suppress -- models/model.py:382-402 for a batch: per class l>=1, prob > score_thres,
+ *     NMS at iou_thr (double compare), class-major output.  prob [B,R,C], boxes [B,R,C,4] ->
+ *     det_boxes [B,cap,4], det_labels int32 [B,cap] (= l-1, -1 pad), det_scores [B,cap],
+ *     det_count [B].  Workspace from frr_class_nms_workspace_bytes, 256-byte aligned.
+ * ------------------------------------------------------------------------------------- */
+int frr_decode_classwise(const float* cls_logits, const float* reg, const float* rois, int rows, int C,
+                         const float* std4_host, float* prob, float* boxes, frr_stream_t stream);
+size_t frr_class_nms_workspace_bytes(int B, int R, int C);
+int frr_class_nms(const float* prob, const float* boxes, const int32_t* roi_count, int B, int R, int C,
+                  float score_thres, double iou_thr, int cap, float* det_boxes, int32_t* det_labels,
+                  float* det_scores, int32_t* det_count, void* workspace, size_t workspace_bytes,
+                  frr_stream_t stream);
+
 #ifdef __cplusplus
 #pragma GCC visibility pop
 }

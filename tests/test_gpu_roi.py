@@ -1,0 +1,136 @@
+"""GPU parity: RoIPool / RoIAlign forward + backward (C ABI) vs the CPU oracle and the torchvision-CPU goldens.
+RoIPool max + argmax bit-exact; backward and RoIAlign within 1e-5 relative (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from faster_rcnn_pytorch_b200 import ops, synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+RTOL, ATOL = 1e-5, 1e-6
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def close_accum(got, want):
+    """Gradients are sums of many signed terms accumulated in a different fp32 order than the CPU loop:
+    1e-5 relative is taken against the scale of the tensor (max |want|), the usual norm-wise bound."""
+    scale = max(float(np.abs(want).max()), 1e-30)
+    assert float(np.abs(got - want).max()) <= 1e-5 * scale
+
+
+CASES = [("a", 500, 1, 8, 37, 62, 64), ("b", 501, 2, 16, 10, 14, 40), ("c", 502, 1, 4, 5, 6, 30)]
+
+
+@pytest.mark.parametrize("name,seed,B,C,fh,fw,K", CASES)
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_roi_pool_goldens(name, seed, B, C, fh, fw, K, channels_last):
+    g = golden("roi")
+    feat = dev(synth.features(seed, B, C, fh, fw))
+    if channels_last:
+        feat = feat.contiguous(memory_format=torch.channels_last)
+    rois5 = dev(synth.random_rois(seed + 1, K, fh, fw, B))
+    go = dev(np.random.RandomState(seed + 2).standard_normal((K, C, 7, 7)).astype(np.float32))
+    out, arg = ops.roi_pool_forward(feat, rois5)
+    assert np.array_equal(out.cpu().numpy(), g[f"{name}_pool_out"])          # bit-exact max
+    assert np.array_equal(arg.cpu().numpy(), g[f"{name}_pool_argmax"])       # bit-exact argmax
+    gin = ops.roi_pool_backward(go, arg, rois5, feat.shape, channels_last=channels_last)
+    assert gin.is_contiguous(memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+    close_accum(gin.cpu().numpy(), g[f"{name}_pool_gin"])
+
+
+@pytest.mark.parametrize("name,seed,B,C,fh,fw,K", CASES)
+@pytest.mark.parametrize("scale", [1.0, 0.5])
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_roi_align_goldens(name, seed, B, C, fh, fw, K, scale, channels_last):
+    g = golden("roi")
+    feat = dev(synth.features(seed, B, C, fh, fw))
+    if channels_last:
+        feat = feat.contiguous(memory_format=torch.channels_last)
+    rois5 = dev(synth.random_rois(seed + 1, K, fh, fw, B))
+    go = dev(np.random.RandomState(seed + 2).standard_normal((K, C, 7, 7)).astype(np.float32))
+    out = ops.roi_align_forward(feat, rois5, spatial_scale=scale, sampling_ratio=2, aligned=False)
+    np.testing.assert_allclose(out.cpu().numpy(), g[f"{name}_align_out_{scale}"], rtol=RTOL, atol=ATOL)
+    gin = ops.roi_align_backward(go, rois5, feat.shape, spatial_scale=scale, sampling_ratio=2, aligned=False,
+                                 channels_last=channels_last)
+    close_accum(gin.cpu().numpy(), g[f"{name}_align_gin_{scale}"])
+
+
+def test_head_call_path_list_of_rois(oracle):
+    """models/model.py:104-113: roi * [fw,fh,fw,fh], list-of-tensors input, RoIPool((7,7), 1.0)."""
+    g = golden("roi")
+    feat = dev(synth.features(510, 1, 8, 37, 62))
+    b, _ = synth.random_boxes(511, 32)
+    scaled = dev(b) * torch.tensor([62, 37, 62, 37], dtype=torch.float32, device=DEV)
+    out = ops.roi_pool(feat, [scaled], (7, 7), 1.0)
+    assert np.array_equal(out.cpu().numpy(), g["head_pool_out"])
+
+
+@pytest.mark.parametrize("B,C,fh,fw,K", [(2, 512, 37, 62, 256), (1, 512, 50, 83, 300), (3, 24, 37, 62, 100)])
+def test_roi_pool_full_size_vs_oracle(oracle, B, C, fh, fw, K):
+    feat = synth.features(700, B, C, fh, fw)
+    rois5 = synth.random_rois(701, K, fh, fw, B)
+    go = np.random.RandomState(702).standard_normal((K, C, 7, 7)).astype(np.float32)
+    want_out, want_arg = oracle.roi_pool_forward(feat, rois5)
+    out, arg = ops.roi_pool_forward(dev(feat), dev(rois5))
+    assert np.array_equal(out.cpu().numpy(), want_out)
+    assert np.array_equal(arg.cpu().numpy(), want_arg)
+    gin = ops.roi_pool_backward(dev(go), arg, dev(rois5), feat.shape)
+    close_accum(gin.cpu().numpy(), oracle.roi_pool_backward(go, want_arg, rois5, feat.shape))
+    out_na, arg_na = ops.roi_pool_forward(dev(feat), dev(rois5), want_argmax=False)
+    assert arg_na is None and torch.equal(out_na, out)
+
+
+@pytest.mark.parametrize("B,C,fh,fw,K,scale,sr,aligned", [(2, 256, 50, 84, 200, 1.0, 2, False), (1, 256, 25, 42, 100, 0.5, 2, True),
+                                                          (1, 16, 30, 30, 50, 1.0, -1, False)])
+def test_roi_align_full_size_vs_oracle(oracle, B, C, fh, fw, K, scale, sr, aligned):
+    feat = synth.features(710, B, C, fh, fw)
+    rois5 = synth.random_rois(711, K, int(fh / scale), int(fw / scale), B)
+    go = np.random.RandomState(712).standard_normal((K, C, 7, 7)).astype(np.float32)
+    out = ops.roi_align_forward(dev(feat), dev(rois5), spatial_scale=scale, sampling_ratio=sr, aligned=aligned)
+    np.testing.assert_allclose(out.cpu().numpy(), oracle.roi_align_forward(feat, rois5, spatial_scale=scale, sampling_ratio=sr, aligned=aligned),
+                               rtol=RTOL, atol=ATOL)
+    gin = ops.roi_align_backward(dev(go), dev(rois5), feat.shape, spatial_scale=scale, sampling_ratio=sr, aligned=aligned)
+    close_accum(gin.cpu().numpy(), oracle.roi_align_backward(go, rois5, feat.shape, spatial_scale=scale, sampling_ratio=sr, aligned=aligned))
+
+
+def test_large_planes_take_the_direct_kernels(oracle):
+    """FPN level-0 sized map (200x336 = 262 KB per plane) does not fit shared memory."""
+    B, C, fh, fw, K = 1, 4, 200, 336, 60
+    feat = synth.features(720, B, C, fh, fw)
+    rois5 = synth.random_rois(721, K, fh, fw, B)
+    go = np.random.RandomState(722).standard_normal((K, C, 7, 7)).astype(np.float32)
+    out, arg = ops.roi_pool_forward(dev(feat), dev(rois5))
+    wo, wa = oracle.roi_pool_forward(feat, rois5)
+    assert np.array_equal(out.cpu().numpy(), wo) and np.array_equal(arg.cpu().numpy(), wa)
+    gin = ops.roi_pool_backward(dev(go), arg, dev(rois5), feat.shape)
+    close_accum(gin.cpu().numpy(), oracle.roi_pool_backward(go, wa, rois5, feat.shape))
+    oa = ops.roi_align_forward(dev(feat), dev(rois5), spatial_scale=1.0, sampling_ratio=2)
+    np.testing.assert_allclose(oa.cpu().numpy(), oracle.roi_align_forward(feat, rois5), rtol=RTOL, atol=ATOL)
+    ga = ops.roi_align_backward(dev(go), dev(rois5), feat.shape)
+    close_accum(ga.cpu().numpy(), oracle.roi_align_backward(go, rois5, feat.shape))
+
+
+def test_autograd_and_edge_cases(oracle):
+    feat = dev(synth.features(730, 2, 12, 9, 11)).requires_grad_(True)
+    rois5 = synth.random_rois(731, 20, 9, 11, 2)
+    rois5[0, 1:] = [-50, -50, -40, -40]      # entirely outside: empty bins -> 0 / argmax -1
+    rois5[1, 1:] = [3.2, 3.2, 3.3, 3.3]      # sub-pixel roi
+    out = ops.roi_pool(feat, dev(rois5), 7, 1.0)
+    wo, wa = oracle.roi_pool_forward(feat.detach().cpu().numpy(), rois5)
+    assert np.array_equal(out.detach().cpu().numpy(), wo)
+    go = torch.randn_like(out)
+    out.backward(go)
+    close_accum(feat.grad.cpu().numpy(), oracle.roi_pool_backward(go.cpu().numpy(), wa, rois5, tuple(feat.shape)))
+    feat2 = feat.detach().clone().requires_grad_(True)
+    oa = ops.roi_align(feat2, dev(rois5), 7, 1.0, sampling_ratio=2)
+    oa.backward(go)
+    close_accum(feat2.grad.cpu().numpy(), oracle.roi_align_backward(go.cpu().numpy(), rois5, tuple(feat.shape)))
+    empty = ops.roi_pool(feat.detach(), torch.zeros((0, 5), device=DEV), 7, 1.0)
+    assert empty.shape == (0, 12, 7, 7)
+    with pytest.raises(ValueError):
+        ops.roi_pool(feat.detach().cpu(), torch.zeros((1, 5)), 7, 1.0)
