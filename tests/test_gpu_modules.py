@@ -1,0 +1,130 @@
+"""GPU parity of the drop-in call sites (faster_rcnn_pytorch_b200.modules / .anchor): same names, arguments and
+return types as models/model.py:6-9,288-298 and anchor.py:7-55 -- these tests read like the reference's
+own forward pass, one image per call."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from faster_rcnn_pytorch_b200 import modules, ops, synth
+from faster_rcnn_pytorch_b200.anchor import FRCNNAnchorMaker
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+RTOL = 1e-5
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def test_anchor_maker_drop_in(oracle):
+    g = golden("anchors")
+    am = FRCNNAnchorMaker()
+    assert np.array_equal(am.anchor_base, g["base"])
+    a = am._enumerate_shifted_anchor((64, 96))               # host numpy, like the reference
+    assert isinstance(a, np.ndarray) and a.dtype == np.float32 and np.array_equal(a, g["full_64x96"])
+    d = am.anchors_on(DEV, (600, 1000))
+    assert d.is_cuda and d.shape == (20646, 4) and am.anchors_on(DEV, (600, 1000)) is d      # cached per size
+    assert np.array_equal(d[:27].cpu().numpy(), g["head_600x1000"])
+    am2 = FRCNNAnchorMaker(ratios=[1, 2], anchor_scales=[4, 8, 16])                          # non-default table
+    want = oracle.enumerate_anchors((64, 96), table=am2.anchor_base)
+    assert np.array_equal(am2._enumerate_shifted_anchor((64, 96)), want)
+
+
+@pytest.mark.parametrize("key", ["rand_102_1000_0.7", "rand_103_3000_0.3", "rand_104_12000_0.7", "rand_106_300_0.3",
+                                 "rand_107_1_0.7", "ties_110_500_0.5"])
+def test_nms_drop_in_unsorted_input(oracle, key):
+    """torchvision.ops.nms signature: unsorted boxes + scores -> int64 indices by decreasing score."""
+    g = golden("nms")
+    kind, seed, n, thr = key.split("_")
+    b, s = synth.random_boxes(int(seed), int(n))
+    if kind == "ties":
+        s = (np.round(s * 8) / 8).astype(np.float32)
+    keep = modules.nms(dev(b), dev(s), float(thr))
+    assert keep.dtype == torch.int64 and keep.is_cuda
+    assert np.array_equal(keep.cpu().numpy(), g[key].astype(np.int64))
+
+
+def test_nms_drop_in_edge_cases():
+    e = modules.nms(torch.zeros((0, 4), device=DEV), torch.zeros((0,), device=DEV), 0.5)
+    assert e.dtype == torch.int64 and e.numel() == 0
+    with pytest.raises(RuntimeError):
+        modules.nms(torch.zeros((3, 5), device=DEV), torch.zeros((3,), device=DEV), 0.5)
+    with pytest.raises(ValueError, match="no CPU path"):
+        modules.nms(torch.zeros((3, 4)), torch.zeros((3,)), 0.5)
+
+
+@pytest.mark.parametrize("name,hw,seed,mode", [("small_train", (160, 256), 200, "train"), ("small_test", (160, 256), 201, "test"),
+                                               ("voc_test", (600, 1000), 1000, "test"), ("rpn_train", (608, 1008), 2000, "train")])
+def test_region_proposal_module(oracle, name, hw, seed, mode):
+    """RegionProposal().forward(cls [N,2], reg [N,4], anchor [N,4], mode) -> ragged rois."""
+    g = golden("proposal")
+    logits, reg, _ = synth.rpn_head_outputs(seed, hw)
+    anchor = FRCNNAnchorMaker()._enumerate_shifted_anchor(hw)
+    rp = modules.RegionProposal()
+    rois = rp(dev(logits), dev(reg), torch.from_numpy(anchor).to(DEV), mode)
+    assert rois.dim() == 2 and rois.shape[1] == 4 and not rois.requires_grad
+    # stage-wise oracle on the GPU's own fp32 scores / boxes (softmax + exp differ CPU<->GPU by ulps)
+    boxes, scores, valid = ops.rpn_decode(dev(reg[None]), dev(logits[None]), anchors=dev(anchor))
+    want = oracle.region_proposal(logits, reg, anchor, mode, scores=scores[0].cpu().numpy())
+    if np.array_equal(want["boxes"], boxes[0].cpu().numpy()):
+        assert np.array_equal(rois.cpu().numpy(), want["rois"])
+    else:
+        bx, va, sc = boxes[0].cpu().numpy(), valid[0].cpu().numpy().astype(bool), scores[0].cpu().numpy()
+        pre_k, post_k = oracle.PROPOSAL_MODES[mode]
+        src = np.nonzero(va)[0]
+        order = oracle.sort_desc(sc[va])[:pre_k]
+        tb = bx[src[order]]
+        keep = oracle.nms(tb, -np.arange(len(tb), dtype=np.float32), 0.7)[:post_k]
+        assert np.array_equal(rois.cpu().numpy(), tb[keep])
+    # against the reference's own output: same number of rois and the same boxes up to exp() ulps, unless a
+    # borderline pair flipped (then the count differs and only the stage-wise check above applies)
+    if rois.shape[0] == int(g[f"{name}_nrois"]):
+        head = g[f"{name}_rois_head"]
+        got = rois[:len(head)].cpu().numpy()
+        if np.allclose(got, head, rtol=1e-4, atol=1e-6):
+            np.testing.assert_allclose(got, head, rtol=1e-4, atol=1e-6)
+
+
+def test_target_maker_modules_like_the_reference_forward(oracle):
+    """models/model.py:324-328 call pattern with torch.manual_seed controlling the sampling."""
+    g = golden("targets")
+    hw = (600, 1000)
+    gt = np.array([[0.1, 0.2, 0.5, 0.7], [0.3, 0.3, 0.9, 0.95]], np.float32)
+    lab = np.array([11, 14], np.int64)
+    anchor = torch.from_numpy(FRCNNAnchorMaker()._enumerate_shifted_anchor(hw)).to(DEV)
+    torch.manual_seed(7)
+    cls_t, reg_t = modules.RPNTargetMaker()(dev(gt), anchor)
+    assert cls_t.shape == (20646,) and cls_t.dtype == torch.int64 and reg_t.shape == (20646, 4)
+    assert np.array_equal(cls_t.cpu().numpy(), g["kat6_rpn_cls"].astype(np.int64))
+    rois, _ = synth.random_boxes(7 + 50, 2000)
+    torch.manual_seed(8)
+    fc, fr, fs = modules.FastRcnnTargetMaker()([dev(gt)], [dev(lab)], dev(rois))
+    assert fc.shape == (128,) and fr.shape == (128, 4) and fs.shape == (128, 4)
+    assert np.array_equal(fc.cpu().numpy(), g["kat6_frcnn_cls"].astype(np.int64))
+    assert np.array_equal(fs.cpu().numpy(), g["kat6_frcnn_rois"])
+    np.testing.assert_allclose(fr.cpu().numpy(), g["kat6_frcnn_reg"], rtol=RTOL, atol=2e-5)
+    # float labels are accepted like models/model.py:416 (cast at :166)
+    torch.manual_seed(8)
+    fc2, _, _ = modules.FastRcnnTargetMaker()([dev(gt)], [dev(lab.astype(np.float32))], dev(rois))
+    assert torch.equal(fc, fc2)
+
+
+def test_roi_pool_module_in_a_head_forward_backward(oracle):
+    """FastRCNNHead.forward (models/model.py:104-119): scale rois, RoIPool((7,7),1.0), view, Linear; backward
+    reaches the feature map through the custom autograd function."""
+    feat = dev(synth.features(800, 1, 32, 37, 62)).requires_grad_(True)
+    b, _ = synth.random_boxes(801, 128)
+    rois = dev(b) * torch.tensor([62, 37, 62, 37], dtype=torch.float32, device=DEV)
+    pool = modules.RoIPool(output_size=(7, 7), spatial_scale=1.)
+    x = pool(feat, [rois])
+    assert x.shape == (128, 32, 7, 7) and x.is_contiguous()
+    lin = torch.nn.Linear(32 * 49, 5).to(DEV)
+    lin(x.view(x.size(0), -1)).sum().backward()
+    wo, wa = oracle.roi_pool_forward(feat.detach().cpu().numpy(), oracle.scale_rois(b, 37, 62))
+    assert np.array_equal(x.detach().cpu().numpy(), wo)
+    go = lin.weight.detach().sum(0).reshape(1, 32, 7, 7).expand(128, -1, -1, -1).contiguous().cpu().numpy()
+    want = oracle.roi_pool_backward(go, wa, oracle.scale_rois(b, 37, 62), (1, 32, 37, 62))
+    scale = np.abs(want).max()
+    assert np.abs(feat.grad.cpu().numpy() - want).max() <= 1e-5 * scale
