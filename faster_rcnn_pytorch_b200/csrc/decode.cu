@@ -29,15 +29,33 @@ __global__ void __launch_bounds__(256) anchors_kernel(float4* __restrict__ out, 
     out[i] = make_anchor(tab, cell, a, fw, stride, W, H);
 }
 
-// one thread per (image, anchor); grid.y = image
-template <bool kLogits, bool kGenAnchors>
+// One thread per anchor and kImgs images (grid.y = image group): the anchor (4 IEEE divisions) and its
+// centre form are built once and reused for every image of the group; the 2*kImgs loads of a thread are
+// issued back to back (memory-level parallelism) before any arithmetic.
+//   score = 1 / (1 + exp(l0 - l1))           (== softmax(l)[1]; one ex2 + one reciprocal)
+//   box   = sat(c -/+ exp(t_wh) * a_wh / 2)  (add.sat == clamp(0,1) of the rounded sum)
+// exp() is ex2.approx(x * log2 e): <= 2 ulp + |x| * 2^-23 relative, inside the 1e-5 contract for decoded boxes
+// and scores; every index-valued stage downstream is evaluated on the fp32 values written here.
+template <bool kLogits, bool kGenAnchors, int kImgs>
 __global__ void __launch_bounds__(256)
     rpn_decode_kernel(const float4* __restrict__ reg, const float* __restrict__ cls, const float4* __restrict__ anchors,
-                      AnchorTable tab, int N, int fw, float stride, float W, float H, float min_size,
+                      AnchorTable tab, int B, int N, int fw, float stride, float W, float H, float min_size,
                       float4* __restrict__ boxes, float* __restrict__ scores, uint8_t* __restrict__ valid) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    const size_t g = (size_t)blockIdx.y * N + i;
+    const int b0 = blockIdx.y * kImgs;
+
+    float4 t[kImgs];
+    float2 l[kImgs];
+#pragma unroll
+    for (int j = 0; j < kImgs; ++j) {
+        if (b0 + j < B) {
+            const size_t g = (size_t)(b0 + j) * N + i;
+            t[j] = ld_stream(reg + g);
+            if (kLogits) l[j] = __ldg(reinterpret_cast<const float2*>(cls) + g);
+            else l[j].y = __ldg(cls + g);
+        }
+    }
 
     float4 an;
     if (kGenAnchors) {
@@ -46,36 +64,31 @@ __global__ void __launch_bounds__(256)
     } else {
         an = anchors[i];
     }
-    const float4 t = ld_stream(reg + g);
-
-    float s;
-    if (kLogits) {
-        const float2 l = *reinterpret_cast<const float2*>(cls + 2 * g);
-        const float m = fmaxf(l.x, l.y);
-        const float e0 = expf(__fsub_rn(l.x, m)), e1 = expf(__fsub_rn(l.y, m));
-        s = __fdiv_rn(e1, __fadd_rn(e0, e1));
-    } else {
-        s = cls[g];
-    }
-
     // xy_to_cxcy(anchor): c = (hi + lo)/2, wh = hi - lo
     const float acx = __fmul_rn(__fadd_rn(an.z, an.x), 0.5f), acy = __fmul_rn(__fadd_rn(an.w, an.y), 0.5f);
     const float aw = __fsub_rn(an.z, an.x), ah = __fsub_rn(an.w, an.y);
-    // decode: c = t_xy * a_wh + a_c ; wh = exp(t_wh) * a_wh
-    const float cx = __fadd_rn(__fmul_rn(t.x, aw), acx), cy = __fadd_rn(__fmul_rn(t.y, ah), acy);
-    const float w = __fmul_rn(expf(t.z), aw), h = __fmul_rn(expf(t.w), ah);
-    // cxcy_to_xy + clamp(0,1)
-    const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
-    float4 b;
-    b.x = fminf(fmaxf(__fsub_rn(cx, hw), 0.f), 1.f);
-    b.y = fminf(fmaxf(__fsub_rn(cy, hh), 0.f), 1.f);
-    b.z = fminf(fmaxf(__fadd_rn(cx, hw), 0.f), 1.f);
-    b.w = fminf(fmaxf(__fadd_rn(cy, hh), 0.f), 1.f);
-    const bool ok = (__fsub_rn(b.w, b.y) >= min_size) && (__fsub_rn(b.z, b.x) >= min_size);
 
-    st_stream(boxes + g, b);
-    scores[g] = s;
-    valid[g] = ok ? 1 : 0;
+#pragma unroll
+    for (int j = 0; j < kImgs; ++j) {
+        if (b0 + j < B) {
+            const size_t g = (size_t)(b0 + j) * N + i;
+            float s = l[j].y;
+            if (kLogits) s = __frcp_rn(__fadd_rn(1.0f, __expf(__fsub_rn(l[j].x, l[j].y))));
+            // decode: c = t_xy * a_wh + a_c ; wh/2 = exp(t_wh) * a_wh / 2 ; cxcy_to_xy ; clamp(0,1)
+            const float cx = __fadd_rn(__fmul_rn(t[j].x, aw), acx), cy = __fadd_rn(__fmul_rn(t[j].y, ah), acy);
+            const float hw = __fmul_rn(__fmul_rn(__expf(t[j].z), aw), 0.5f);
+            const float hh = __fmul_rn(__fmul_rn(__expf(t[j].w), ah), 0.5f);
+            float4 bx;
+            bx.x = __saturatef(__fsub_rn(cx, hw));
+            bx.y = __saturatef(__fsub_rn(cy, hh));
+            bx.z = __saturatef(__fadd_rn(cx, hw));
+            bx.w = __saturatef(__fadd_rn(cy, hh));
+            const bool ok = (__fsub_rn(bx.w, bx.y) >= min_size) && (__fsub_rn(bx.z, bx.x) >= min_size);
+            st_stream(boxes + g, bx);
+            scores[g] = s;
+            valid[g] = ok ? 1 : 0;
+        }
+    }
 }
 
 }  // namespace frr
@@ -121,17 +134,22 @@ int frr_rpn_decode(const float* reg, const float* cls, int cls_is_logits, const 
                       img_h, img_w, stride, tab.A);
     }
     if (B == 0 || N == 0) return FRR_OK;
-    dim3 grid((N + 255) / 256, B);
     cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH(L, G)                                                                                              \
-    rpn_decode_kernel<L, G><<<grid, 256, 0, st>>>((const float4*)reg, cls, (const float4*)anchors, tab, N, fw,   \
-                                                  (float)stride, (float)img_w, (float)img_h, min_size,           \
-                                                  (float4*)boxes, scores, valid)
+#define LAUNCH(L, G, I)                                                                                               \
+    rpn_decode_kernel<L, G, I><<<dim3((N + 255) / 256, (B + I - 1) / I), 256, 0, st>>>(                              \
+        (const float4*)reg, cls, (const float4*)anchors, tab, B, N, fw, (float)stride, (float)img_w, (float)img_h,   \
+        min_size, (float4*)boxes, scores, valid)
+#define LAUNCH_I(L, G)                        \
+    do {                                      \
+        if (B >= 4) LAUNCH(L, G, 4);          \
+        else LAUNCH(L, G, 1);                 \
+    } while (0)
     if (cls_is_logits) {
-        if (anchors) LAUNCH(true, false); else LAUNCH(true, true);
+        if (anchors) LAUNCH_I(true, false); else LAUNCH_I(true, true);
     } else {
-        if (anchors) LAUNCH(false, false); else LAUNCH(false, true);
+        if (anchors) LAUNCH_I(false, false); else LAUNCH_I(false, true);
     }
+#undef LAUNCH_I
 #undef LAUNCH
     count_launch();
     FRR_CHECK_LAUNCH("rpn_decode_kernel");

@@ -1,0 +1,75 @@
+// RegionProposal.forward for a batch in ONE C-ABI call (models/model.py:17-58): decode + clip + min-size
+// -> top-k -> NMS -> first post_nms_top_k boxes.  Three kernel launches on the caller's stream, every
+// intermediate lives in the caller-provided workspace; no allocation, no synchronisation, graph-capturable.
+#include "frr_common.cuh"
+
+namespace frr {
+
+struct ProposalWs {
+    size_t boxes, scores, valid, top_boxes, top_idx, top_count, keep, total;
+};
+
+static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static ProposalWs proposal_ws(int B, int N, int k, int post) {
+    ProposalWs w;
+    size_t o = 0;
+    w.boxes = o;     o += al256((size_t)B * N * 16);
+    w.scores = o;    o += al256((size_t)B * N * 4);
+    w.valid = o;     o += al256((size_t)B * N);
+    w.top_boxes = o; o += al256((size_t)B * k * 16);
+    w.top_idx = o;   o += al256((size_t)B * k * 4);
+    w.top_count = o; o += al256((size_t)B * 4);
+    w.keep = o;      o += al256((size_t)B * post * 4);
+    w.total = o;
+    return w;
+}
+
+}  // namespace frr
+
+extern "C" {
+
+size_t frr_rpn_proposals_workspace_bytes(int B, int N, int pre_nms_top_k, int post_nms_top_k) {
+    if (B < 0 || N < 0 || pre_nms_top_k < 0 || post_nms_top_k < 0) return 0;
+    const int k = pre_nms_top_k < N ? pre_nms_top_k : N;
+    return frr::proposal_ws(B, N, k, post_nms_top_k).total;
+}
+
+int frr_rpn_proposals(const float* reg, const float* cls, int cls_is_logits, const float* anchors,
+                      const float* base_table_host, int A, int img_h, int img_w, int stride, float min_size, int B, int N,
+                      int pre_nms_top_k, int post_nms_top_k, double iou_thr, float* rois, int32_t* roi_count,
+                      void* workspace, size_t workspace_bytes, frr_stream_t stream) {
+    using namespace frr;
+    FRR_CHECK_ARG(B >= 0 && N >= 0 && pre_nms_top_k >= 1 && post_nms_top_k >= 1, "frr_rpn_proposals: bad sizes");
+    FRR_CHECK_ARG(rois && roi_count && aligned16(rois), "frr_rpn_proposals: rois must be non-null and 16-byte aligned");
+    if (B == 0) return FRR_OK;
+    const int k = pre_nms_top_k < N ? pre_nms_top_k : N;  // models/model.py:46-47
+    const ProposalWs w = proposal_ws(B, N, k, post_nms_top_k);
+    FRR_CHECK_ARG(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0,
+                  "frr_rpn_proposals: workspace must be non-null and 256-byte aligned");
+    if (workspace_bytes < w.total) {
+        set_error("frr_rpn_proposals: workspace too small (%zu < %zu)", workspace_bytes, w.total);
+        return FRR_E_WORKSPACE;
+    }
+    char* p = static_cast<char*>(workspace);
+    float* boxes = reinterpret_cast<float*>(p + w.boxes);
+    float* scores = reinterpret_cast<float*>(p + w.scores);
+    uint8_t* valid = reinterpret_cast<uint8_t*>(p + w.valid);
+    float* top_boxes = reinterpret_cast<float*>(p + w.top_boxes);
+    int32_t* top_idx = reinterpret_cast<int32_t*>(p + w.top_idx);
+    int32_t* top_count = reinterpret_cast<int32_t*>(p + w.top_count);
+    int32_t* keep = reinterpret_cast<int32_t*>(p + w.keep);
+    int rc = frr_rpn_decode(reg, cls, cls_is_logits, anchors, base_table_host, A, img_h, img_w, stride, min_size, boxes,
+                            scores, valid, B, N, stream);
+    if (rc) return rc;
+    if (k == 0) {
+        FRR_CUDA(cudaMemsetAsync(roi_count, 0, (size_t)B * 4, (cudaStream_t)stream));
+        FRR_CUDA(cudaMemsetAsync(rois, 0, (size_t)B * post_nms_top_k * 16, (cudaStream_t)stream));
+        return FRR_OK;
+    }
+    rc = frr_topk_desc(scores, valid, boxes, B, N, k, nullptr, top_idx, nullptr, top_boxes, top_count, stream);
+    if (rc) return rc;
+    return frr_nms_sorted(top_boxes, top_count, B, k, iou_thr, post_nms_top_k, keep, roi_count, rois, 0, stream);
+}
+
+}  // extern "C"

@@ -1,4 +1,5 @@
-// P4: pre-NMS top-k of the RPN objectness scores, sorted descending (models/model.py:44-49).
+// P4 (general path): pre-NMS top-k of the RPN objectness scores, sorted descending (models/model.py:44-49).
+// The fast path for N <= 65536 is the shared-memory radix sort of topk_radix.cu; this kernel covers larger N.
 //
 // One CTA (1024 threads) per image:
 //   1. MSB-first radix select (4 x 8-bit digits) over order-preserving uint32 keys finds the
@@ -29,7 +30,7 @@ struct TopkSmemHeader {
 };
 
 __global__ void __launch_bounds__(kTopkThreads, 1)
-    topk_desc_kernel(const float* __restrict__ scores, const uint8_t* __restrict__ valid,
+    topk_bitonic_kernel(const float* __restrict__ scores, const uint8_t* __restrict__ valid,
                      const float4* __restrict__ boxes, int N, int k, int P /* pow2 >= k */, int nchunks /* ceil(N/32) */,
                      float* __restrict__ out_scores, int32_t* __restrict__ out_idx, int32_t* __restrict__ out_cidx,
                      float4* __restrict__ out_boxes, int32_t* __restrict__ out_count) {
@@ -220,6 +221,10 @@ static size_t topk_smem_bytes(int nchunks, int P) {
     return s + sizeof(unsigned long long) * (size_t)P;
 }
 
+int topk_radix_launch(const float* scores, const uint8_t* valid, const float* boxes, int B, int N, int k,
+                      float* out_scores, int32_t* out_idx, int32_t* out_cidx, float* out_boxes, int32_t* out_count,
+                      frr_stream_t stream);
+
 }  // namespace frr
 
 extern "C" int frr_topk_desc(const float* scores, const uint8_t* valid, const float* boxes, int B, int N, int k,
@@ -232,6 +237,11 @@ extern "C" int frr_topk_desc(const float* scores, const uint8_t* valid, const fl
                   "frr_topk_desc: boxes must be given and 16-byte aligned when out_boxes is requested");
     if (B == 0 || k == 0) return FRR_OK;
     FRR_CHECK_ARG(k <= 16384, "frr_topk_desc: k=%d exceeds the in-smem sort capacity 16384", k);
+    {   // fast path: shared-memory radix sort (topk_radix.cu); shapes outside it take the bitonic kernel below
+        const int rc = topk_radix_launch(scores, valid, boxes, B, N, k, out_scores, out_idx, out_cidx, out_boxes, out_count,
+                                         stream);
+        if (rc <= 0) return rc;
+    }
     int P = 32;
     while (P < k) P <<= 1;
     const int nchunks = (N + 31) / 32;
@@ -239,13 +249,13 @@ extern "C" int frr_topk_desc(const float* scores, const uint8_t* valid, const fl
     FRR_CHECK_ARG(smem <= 227 * 1024, "frr_topk_desc: N=%d k=%d needs %zu B shared memory (> 227 KB)", N, k, smem);
     static std::atomic<size_t> configured{0};
     if (configured.load() < smem) {
-        FRR_CUDA(cudaFuncSetAttribute(topk_desc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        FRR_CUDA(cudaFuncSetAttribute(topk_bitonic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured.store(227 * 1024);
     }
-    topk_desc_kernel<<<B, kTopkThreads, smem, (cudaStream_t)stream>>>(scores, valid, (const float4*)boxes, N, k, P,
+    topk_bitonic_kernel<<<B, kTopkThreads, smem, (cudaStream_t)stream>>>(scores, valid, (const float4*)boxes, N, k, P,
                                                                        nchunks, out_scores, out_idx, out_cidx,
                                                                        (float4*)out_boxes, out_count);
     count_launch();
-    FRR_CHECK_LAUNCH("topk_desc_kernel");
+    FRR_CHECK_LAUNCH("topk_bitonic_kernel");
     return FRR_OK;
 }

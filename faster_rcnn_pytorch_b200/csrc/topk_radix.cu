@@ -1,0 +1,296 @@
+// P4 (fast path): pre-NMS top-k, sorted descending, ties lower-index-first (models/model.py:44-49).
+//
+// One CTA (1024 threads) per image, everything after the first read of the scores stays in shared memory:
+//   0. validity words (ballot) + the order-preserving uint32 keys of all N scores staged in shared memory;
+//   1. MSB-first radix select (4 x 8-bit digits, warp-aggregated histogram atomics) -> T = k-th largest key
+//      and how many keys == T to take;
+//   2. ORDER-PRESERVING compaction of the selected (key, index) pairs (two block scans: #greater and #equal
+//      before every 32-anchor chunk), so that a STABLE sort by key alone yields "ties: lower index first";
+//   3. stable LSD radix sort of the <= 16384 selected pairs, 4 passes of 8 bits: every warp owns a contiguous
+//      run of rows, ranks its keys with match.any, keeps a private 256-bin histogram (u16), the digit-major /
+//      warp-minor exclusive scan turns the 32 x 256 counts into scatter offsets;
+//   4. scores / indices / compacted indices / gathered boxes are written out (padded past count).
+// Compared with the bitonic version (105 compare-exchange stages with a barrier each, contended histogram
+// atomics) this is ~10x fewer shared-memory wavefronts and barriers.  HBM bytes: 5N in, 40k out per image.
+#include "frr_common.cuh"
+
+namespace frr {
+
+constexpr int kRsThreads = 1024;
+constexpr int kRsWarps = kRsThreads / 32;
+
+struct RsHdr {
+    unsigned int hist[256];
+    unsigned int warp_tmp[kRsWarps];
+    unsigned int prefix_key;
+    unsigned int remaining;
+    unsigned int nvalid;
+    unsigned int pad;
+};
+
+struct RsLayout {
+    size_t vbits, gpre, epre, vpre, whist, keyA, idxA, area2, total;
+    int staged;
+};
+
+static inline size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+static RsLayout rs_layout(int N, int kcap, int nchunks, bool want_stage) {
+    RsLayout L;
+    size_t o = up16(sizeof(RsHdr));
+    L.vbits = o; o += 4 * (size_t)nchunks;
+    L.gpre = o;  o += 4 * (size_t)nchunks;
+    L.epre = o;  o += 4 * (size_t)nchunks;
+    L.vpre = o;  o += 4 * (size_t)nchunks;
+    o = up16(o);
+    L.whist = o; o += (size_t)kRsWarps * 256 * 2;
+    L.keyA = o;  o += 4 * (size_t)kcap;
+    L.idxA = o;  o += 2 * (size_t)kcap;
+    o = up16(o);
+    L.area2 = o;
+    const size_t sortB = 6 * (size_t)kcap;
+    const size_t stage = 4 * (size_t)N;
+    L.staged = want_stage ? 1 : 0;
+    L.total = o + up16(want_stage && stage > sortB ? stage : sortB);
+    return L;
+}
+
+template <bool kStaged>
+__global__ void __launch_bounds__(kRsThreads, 1)
+    topk_radix_kernel(const float* __restrict__ scores, const uint8_t* __restrict__ valid,
+                      const float4* __restrict__ boxes, int N, int k, int kcap, int nchunks, RsLayout L,
+                      float* __restrict__ out_scores, int32_t* __restrict__ out_idx, int32_t* __restrict__ out_cidx,
+                      float4* __restrict__ out_boxes, int32_t* __restrict__ out_count) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    RsHdr* hd = reinterpret_cast<RsHdr*>(smem);
+    unsigned int* vbits = reinterpret_cast<unsigned int*>(smem + L.vbits);
+    unsigned int* gpre = reinterpret_cast<unsigned int*>(smem + L.gpre);
+    unsigned int* epre = reinterpret_cast<unsigned int*>(smem + L.epre);
+    unsigned int* vpre = reinterpret_cast<unsigned int*>(smem + L.vpre);
+    unsigned short* whist = reinterpret_cast<unsigned short*>(smem + L.whist);  // [warp][256]
+    unsigned int* keyA = reinterpret_cast<unsigned int*>(smem + L.keyA);
+    unsigned short* idxA = reinterpret_cast<unsigned short*>(smem + L.idxA);
+    unsigned int* keyB = reinterpret_cast<unsigned int*>(smem + L.area2);
+    unsigned short* idxB = reinterpret_cast<unsigned short*>(smem + L.area2 + 4 * (size_t)kcap);
+    unsigned int* skey = reinterpret_cast<unsigned int*>(smem + L.area2);  // [N] staged keys (dead before the sort)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned int lt = (1u << lane) - 1u;
+    const int b = blockIdx.x;
+    const float* sc = scores + (size_t)b * N;
+    const uint8_t* va = valid ? valid + (size_t)b * N : nullptr;
+
+    // ---- 0. validity words, staged keys ---------------------------------------------------------------
+    for (int c = warp; c < nchunks; c += kRsWarps) {
+        const int i = c * 32 + lane;
+        const bool ok = (i < N) && (va ? (va[i] != 0) : true);
+        const unsigned int w = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) vbits[c] = w;
+        if (kStaged && i < N) skey[i] = float_to_ordered(sc[i]);
+    }
+    if (tid < 256) hd->hist[tid] = 0;
+    if (tid == 0) hd->prefix_key = 0;
+    __syncthreads();
+    auto key_at = [&](int i) -> unsigned int { return kStaged ? skey[i] : float_to_ordered(sc[i]); };
+    {
+        unsigned int run = 0;
+        for (int base = 0; base < nchunks; base += kRsThreads) {
+            const int c = base + tid;
+            const unsigned int v = (c < nchunks) ? __popc(vbits[c]) : 0u;
+            unsigned int tot;
+            const unsigned int ex = block_exclusive_scan(v, hd->warp_tmp, &tot);
+            if (c < nchunks) vpre[c] = run + ex;
+            run += tot;
+        }
+        if (tid == 0) hd->nvalid = run;
+    }
+    __syncthreads();
+    const int keff = min(k, (int)hd->nvalid);
+    if (tid == 0) {
+        out_count[b] = keff;
+        hd->remaining = (unsigned int)keff;
+    }
+    __syncthreads();
+
+    if (keff > 0) {
+        // ---- 1. radix select ----------------------------------------------------------------------------
+        unsigned int prefix = 0, pmask = 0;
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            for (int c = warp; c < nchunks; c += kRsWarps) {
+                const bool ok = (vbits[c] >> lane) & 1u;
+                const unsigned int key = ok ? key_at(c * 32 + lane) : 0u;
+                const bool in = ok && ((key & pmask) == prefix);
+                const unsigned int d = in ? ((key >> shift) & 255u) : (256u + lane);
+                const unsigned int m = __match_any_sync(0xffffffffu, d);
+                if (in && lane == __ffs(m) - 1) atomicAdd(&hd->hist[d], (unsigned int)__popc(m));
+            }
+            __syncthreads();
+            if (warp == 0) {  // walk digits from 255 down: the bucket where the cumulative count reaches `remaining`
+                const unsigned int need = hd->remaining;
+                unsigned int cnt[8], s = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { cnt[j] = hd->hist[255 - (lane * 8 + j)]; s += cnt[j]; }
+                unsigned int inc = s;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                unsigned int before = inc - s;
+                if (before < need && inc >= need) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (before < need && before + cnt[j] >= need) {
+                            hd->prefix_key = prefix | ((unsigned int)(255 - (lane * 8 + j)) << shift);
+                            hd->remaining = need - before;
+                            before = need;
+                        } else {
+                            before += cnt[j];
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            prefix = hd->prefix_key;
+            pmask |= (255u << shift);
+            if (tid < 256) hd->hist[tid] = 0;
+            __syncthreads();
+        }
+        const unsigned int T = prefix;
+        const unsigned int take_ties = hd->remaining;
+
+        // ---- 2. order-preserving compaction ---------------------------------------------------------------
+        for (int c = warp; c < nchunks; c += kRsWarps) {
+            const bool ok = (vbits[c] >> lane) & 1u;
+            const unsigned int key = ok ? key_at(c * 32 + lane) : 0u;
+            const unsigned int mg = __ballot_sync(0xffffffffu, ok && key > T);
+            const unsigned int me = __ballot_sync(0xffffffffu, ok && key == T);
+            if (lane == 0) { gpre[c] = __popc(mg); epre[c] = __popc(me); }
+        }
+        __syncthreads();
+        {
+            unsigned int run_g = 0, run_e = 0;
+            for (int base = 0; base < nchunks; base += kRsThreads) {
+                const int c = base + tid;
+                const unsigned int vg = (c < nchunks) ? gpre[c] : 0u, ve = (c < nchunks) ? epre[c] : 0u;
+                unsigned int tg, te;
+                const unsigned int eg = block_exclusive_scan(vg, hd->warp_tmp, &tg);
+                const unsigned int ee = block_exclusive_scan(ve, hd->warp_tmp, &te);
+                if (c < nchunks) { gpre[c] = run_g + eg; epre[c] = run_e + ee; }
+                run_g += tg;
+                run_e += te;
+            }
+        }
+        __syncthreads();
+        for (int c = warp; c < nchunks; c += kRsWarps) {
+            const int i = c * 32 + lane;
+            const bool ok = (vbits[c] >> lane) & 1u;
+            const unsigned int key = ok ? key_at(i) : 0u;
+            const bool gt = ok && key > T, eq = ok && key == T;
+            const unsigned int mg = __ballot_sync(0xffffffffu, gt), me = __ballot_sync(0xffffffffu, eq);
+            const unsigned int gb = gpre[c] + __popc(mg & lt), eb = epre[c] + __popc(me & lt);
+            if (gt || (eq && eb < take_ties)) {
+                const unsigned int pos = gb + min(eb, take_ties);
+                keyA[pos] = ~key;  // ascending ~key == descending score
+                idxA[pos] = (unsigned short)i;
+            }
+        }
+        __syncthreads();
+
+        // ---- 3. stable LSD radix sort of keyA/idxA[0..keff) --------------------------------------------------
+        const int rows = (keff + 31) >> 5;
+        const int rpw = (rows + kRsWarps - 1) / kRsWarps;
+        const int r0 = min(warp * rpw, rows), r1 = min(r0 + rpw, rows);
+        unsigned short* wh = whist + warp * 256;
+        unsigned int* srcK = keyA;
+        unsigned short* srcI = idxA;
+        unsigned int* dstK = keyB;
+        unsigned short* dstI = idxB;
+        for (int shift = 0; shift < 32; shift += 8) {
+            for (int i = tid; i < kRsWarps * 256 / 2; i += kRsThreads) reinterpret_cast<unsigned int*>(whist)[i] = 0u;
+            __syncthreads();
+            for (int r = r0; r < r1; ++r) {
+                const int i = r * 32 + lane;
+                const bool act = i < keff;
+                const unsigned int d = act ? ((srcK[i] >> shift) & 255u) : (256u + lane);
+                const unsigned int m = __match_any_sync(0xffffffffu, d);
+                if (act && lane == __ffs(m) - 1) wh[d] = (unsigned short)(wh[d] + __popc(m));
+                __syncwarp();
+            }
+            __syncthreads();
+            {   // exclusive scan in (digit, warp) order: thread t owns digit t>>2, warps (t&3)*8 .. +8
+                const int d = tid >> 2, w0 = (tid & 3) * 8;
+                unsigned int c8[8], s = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { c8[j] = whist[(w0 + j) * 256 + d]; s += c8[j]; }
+                unsigned int tot;
+                unsigned int run = block_exclusive_scan(s, hd->warp_tmp, &tot);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { whist[(w0 + j) * 256 + d] = (unsigned short)run; run += c8[j]; }
+            }
+            __syncthreads();
+            for (int r = r0; r < r1; ++r) {
+                const int i = r * 32 + lane;
+                const bool act = i < keff;
+                const unsigned int key = act ? srcK[i] : 0u;
+                const unsigned short id = act ? srcI[i] : (unsigned short)0;
+                const unsigned int d = act ? ((key >> shift) & 255u) : (256u + lane);
+                const unsigned int m = __match_any_sync(0xffffffffu, d);
+                unsigned int base = 0;
+                if (act) base = wh[d];
+                __syncwarp();
+                if (act) {
+                    if (lane == __ffs(m) - 1) wh[d] = (unsigned short)(base + __popc(m));
+                    const unsigned int pos = base + __popc(m & lt);
+                    dstK[pos] = key;
+                    dstI[pos] = id;
+                }
+                __syncwarp();
+            }
+            __syncthreads();
+            unsigned int* tk = srcK; srcK = dstK; dstK = tk;
+            unsigned short* ti = srcI; srcI = dstI; dstI = ti;
+        }
+        // 4 passes: the sorted pairs are back in keyA / idxA
+    }
+
+    // ---- 4. write-out ---------------------------------------------------------------------------------------
+    for (int j = tid; j < k; j += kRsThreads) {
+        const size_t o = (size_t)b * k + j;
+        if (j < keff) {
+            const unsigned int key = ~keyA[j];
+            const int i = (int)idxA[j];
+            if (out_scores) out_scores[o] = ordered_to_float(key);
+            out_idx[o] = i;
+            if (out_cidx) out_cidx[o] = (int)(vpre[i >> 5] + __popc(vbits[i >> 5] & ((1u << (i & 31)) - 1u)));
+            if (out_boxes) out_boxes[o] = boxes[(size_t)b * N + i];
+        } else {
+            if (out_scores) out_scores[o] = __uint_as_float(0xff800000u);  // -inf
+            out_idx[o] = -1;
+            if (out_cidx) out_cidx[o] = -1;
+            if (out_boxes) out_boxes[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+
+// Returns FRR_OK when the launch was done, 1 when the shape is outside the fast path (caller falls back).
+int topk_radix_launch(const float* scores, const uint8_t* valid, const float* boxes, int B, int N, int k,
+                      float* out_scores, int32_t* out_idx, int32_t* out_cidx, float* out_boxes, int32_t* out_count,
+                      frr_stream_t stream) {
+    if (N > 65536 || k > 16384) return 1;
+    const size_t limit = 227 * 1024;
+    const int kcap = (k + 31) & ~31;
+    const int nchunks = (N + 31) / 32;
+    RsLayout L = rs_layout(N, kcap, nchunks, true);
+    if (L.total > limit) L = rs_layout(N, kcap, nchunks, false);
+    if (L.total > limit) return 1;
+    auto kern = L.staged ? topk_radix_kernel<true> : topk_radix_kernel<false>;
+    FRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+    kern<<<B, kRsThreads, L.total, (cudaStream_t)stream>>>(scores, valid, (const float4*)boxes, N, k, kcap, nchunks, L,
+                                                            out_scores, out_idx, out_cidx, (float4*)out_boxes, out_count);
+    count_launch();
+    FRR_CHECK_LAUNCH("topk_radix_kernel");
+    return FRR_OK;
+}
+
+}  // namespace frr

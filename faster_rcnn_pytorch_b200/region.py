@@ -3,12 +3,19 @@
 ``rpn_proposals`` is the batched equivalent of the reference's ``RegionProposal.forward``
 (models/model.py:17-58): decode+clip+min-size -> top-k -> NMS -> first post_nms boxes, for B images
 at once, with no host synchronisation (ragged sizes come back as counts on the device).
+
+``ProposalPlan`` is the same computation with every buffer allocated once and the three kernels
+issued by ONE C-ABI call (``frr_rpn_proposals``), so a step costs one ctypes call on the host and is
+CUDA-graph capturable.  ``HostProposalPipeline`` wraps a plan for callers whose RPN head outputs live in
+host memory: pinned staging, H2D on a copy stream, kernels, D2H of rois + counts, double buffered so the
+copies of step i+1 overlap the kernels of step i.
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 
 PROPOSAL_MODES = {"train": (12000, 2000), "test": (6000, 300)}   # models/model.py:24-28
 RPN_NMS_THRESH = 0.7                                              # models/model.py:53
@@ -29,3 +36,118 @@ def rpn_proposals(cls, reg, image_hw=None, mode: str = "train", anchors=None, st
     if return_all:
         return dict(rois=rois, count=count, keep=keep, topk=top, boxes=boxes, scores=scores, valid=valid)
     return rois, count
+
+
+class ProposalPlan:
+    """Pre-planned proposal layer for a fixed (B, N) shape: workspace and outputs are allocated once;
+    ``run(cls, reg)`` is one ``frr_rpn_proposals`` call on the current stream (no allocation, no sync)."""
+
+    def __init__(self, B: int, N: int, device, image_hw=None, anchors=None, mode: str = "train", stride: int = 16,
+                 table=None, logits: bool = True, pre_nms_top_k=None, post_nms_top_k=None,
+                 nms_thresh: float = RPN_NMS_THRESH, min_size: float = ops._MIN_SIZE):
+        self.lib = _lib.load()
+        pre_k, post_k = PROPOSAL_MODES[mode]
+        self.pre_k = pre_k if pre_nms_top_k is None else int(pre_nms_top_k)
+        self.post_k = post_k if post_nms_top_k is None else int(post_nms_top_k)
+        self.B, self.N, self.device = int(B), int(N), torch.device(device)
+        self.logits, self.stride, self.thr, self.min_size = bool(logits), int(stride), float(nms_thresh), float(min_size)
+        self._table, self._tptr, self.A = ops._table_arg(table)
+        if anchors is not None:
+            self.anchors = ops._req(anchors, "anchors")
+            if tuple(self.anchors.shape) != (self.N, 4):
+                raise ValueError("anchors must be [N,4]")
+            self.H = self.W = 0
+        else:
+            if image_hw is None:
+                raise ValueError("image_hw is required when anchors are generated in-kernel")
+            self.anchors = None
+            self.H, self.W = int(image_hw[0]), int(image_hw[1])
+        with torch.cuda.device(self.device):
+            self.ws_bytes = int(self.lib.frr_rpn_proposals_workspace_bytes(self.B, self.N, self.pre_k, self.post_k))
+            self._ws = torch.empty((self.ws_bytes + 256,), dtype=torch.uint8, device=self.device)
+            self._ws_ptr = self._ws.data_ptr() + ((-self._ws.data_ptr()) % 256)
+            self.rois = torch.empty((self.B, self.post_k, 4), dtype=torch.float32, device=self.device)
+            self.count = torch.empty((self.B,), dtype=torch.int32, device=self.device)
+
+    def run(self, cls, reg, rois=None, count=None):
+        """cls [B,N,2] logits / [B,N] scores and reg [B,N,4]: CUDA fp32 contiguous.  Returns (rois, count) --
+        the plan's own output buffers unless ``rois`` / ``count`` are given (overwritten by the next run)."""
+        if not (cls.is_cuda and reg.is_cuda and cls.dtype == torch.float32 and reg.dtype == torch.float32):
+            raise ValueError("ProposalPlan.run: cls / reg must be CUDA fp32 tensors: the region stage has no CPU path")
+        if tuple(reg.shape) != (self.B, self.N, 4) or not reg.is_contiguous() or not cls.is_contiguous() or \
+                tuple(cls.shape) != ((self.B, self.N, 2) if self.logits else (self.B, self.N)):
+            raise ValueError("ProposalPlan.run: shape mismatch with the plan")
+        rois = self.rois if rois is None else rois
+        count = self.count if count is None else count
+        _lib.check(self.lib.frr_rpn_proposals(reg.data_ptr(), cls.data_ptr(), int(self.logits), ops._ptr(self.anchors),
+                                              self._tptr, self.A, self.H, self.W, self.stride, self.min_size, self.B,
+                                              self.N, self.pre_k, self.post_k, self.thr, rois.data_ptr(),
+                                              count.data_ptr(), self._ws_ptr, self.ws_bytes,
+                                              torch.cuda.current_stream().cuda_stream), "frr_rpn_proposals")
+        return rois, count
+
+
+class HostProposalPipeline:
+    """Proposal layer for HOST inputs (numpy / CPU tensors), double buffered.
+
+    ``submit(cls_host, reg_host)`` stages the inputs in pinned memory, copies them to the device on a copy
+    stream, runs the plan on the compute stream and copies rois + counts back into pinned memory; it returns a
+    ticket.  ``result(ticket)`` waits for that step only and returns ``(rois_host [B,post,4], count_host [B])``
+    views (valid until the slot is reused two submits later).  With ``depth`` = 2 the H2D copy of step i+1
+    overlaps the kernels of step i."""
+
+    def __init__(self, plan: ProposalPlan, depth: int = 2):
+        self.plan = plan
+        dev = plan.device
+        B, N = plan.B, plan.N
+        cshape = (B, N, 2) if plan.logits else (B, N)
+        self.depth = int(depth)
+        with torch.cuda.device(dev):
+            self.copy_stream = torch.cuda.Stream(device=dev)
+            self.compute_stream = torch.cuda.Stream(device=dev)
+            self.slots = []
+            for _ in range(self.depth):
+                self.slots.append(dict(
+                    h_cls=torch.empty(cshape, dtype=torch.float32).pin_memory(),
+                    h_reg=torch.empty((B, N, 4), dtype=torch.float32).pin_memory(),
+                    d_cls=torch.empty(cshape, dtype=torch.float32, device=dev),
+                    d_reg=torch.empty((B, N, 4), dtype=torch.float32, device=dev),
+                    d_rois=torch.empty((B, plan.post_k, 4), dtype=torch.float32, device=dev),
+                    d_count=torch.empty((B,), dtype=torch.int32, device=dev),
+                    h_rois=torch.empty((B, plan.post_k, 4), dtype=torch.float32).pin_memory(),
+                    h_count=torch.empty((B,), dtype=torch.int32).pin_memory(),
+                    copied=torch.cuda.Event(), done=torch.cuda.Event(), busy=False))
+        self._n = 0
+        self.h2d_bytes = int(np.prod(cshape) * 4 + B * N * 16)
+        self.d2h_bytes = int(B * plan.post_k * 16 + B * 4)
+
+    def submit(self, cls_host, reg_host, stage: bool = True) -> int:
+        """``stage=False``: cls_host / reg_host are already pinned CPU tensors and are copied from directly."""
+        t = self._n
+        s = self.slots[t % self.depth]
+        if s["busy"]:
+            s["done"].synchronize()      # slot reuse: its previous step must have left the device
+        if stage:
+            s["h_cls"].copy_(torch.as_tensor(cls_host))
+            s["h_reg"].copy_(torch.as_tensor(reg_host))
+            src_cls, src_reg = s["h_cls"], s["h_reg"]
+        else:
+            src_cls, src_reg = cls_host, reg_host
+        with torch.cuda.stream(self.copy_stream):
+            s["d_cls"].copy_(src_cls, non_blocking=True)
+            s["d_reg"].copy_(src_reg, non_blocking=True)
+            s["copied"].record(self.copy_stream)
+        with torch.cuda.stream(self.compute_stream):
+            self.compute_stream.wait_event(s["copied"])
+            self.plan.run(s["d_cls"], s["d_reg"], rois=s["d_rois"], count=s["d_count"])
+            s["h_rois"].copy_(s["d_rois"], non_blocking=True)
+            s["h_count"].copy_(s["d_count"], non_blocking=True)
+            s["done"].record(self.compute_stream)
+        s["busy"] = True
+        self._n += 1
+        return t
+
+    def result(self, ticket: int):
+        s = self.slots[ticket % self.depth]
+        s["done"].synchronize()
+        return s["h_rois"], s["h_count"]

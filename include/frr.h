@@ -98,6 +98,20 @@ int frr_nms_sorted_tuned(const float* boxes, const int32_t* counts, int B, int n
                          int64_t* dbg_cycles, frr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * RegionProposal.forward for a batch in one call -- models/model.py:17-58 (P1-P4 + N1 chained: the three
+ * kernels above on `stream`, intermediates in `workspace`).  k = min(pre_nms_top_k, N) (:46-47).
+ * rois [B,post_nms_top_k,4] zero padded, roi_count [B].  Reference constants: 12000/2000 (train),
+ * 6000/300 (test), iou_thr 0.7, min_size 0.001f.  workspace: 256-byte aligned, size from
+ * frr_rpn_proposals_workspace_bytes.
+ * ------------------------------------------------------------------------------------- */
+size_t frr_rpn_proposals_workspace_bytes(int B, int N, int pre_nms_top_k, int post_nms_top_k);
+int frr_rpn_proposals(const float* reg /* [B,N,4] */, const float* cls /* [B,N,2] logits or [B,N] scores */,
+                      int cls_is_logits, const float* anchors /* [N,4] or NULL */, const float* base_table_host, int A,
+                      int img_h, int img_w, int stride, float min_size, int B, int N, int pre_nms_top_k,
+                      int post_nms_top_k, double iou_thr, float* rois, int32_t* roi_count, void* workspace,
+                      size_t workspace_bytes, frr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * R1-R3  RoIPool -- torchvision.ops.RoIPool((7,7), 1.0) at models/model.py:97,113 and its autograd
  *        backward (train.py:36).  Schemas replaced: torchvision::roi_pool(input, rois, spatial_scale,
  *        ph, pw) -> (out, argmax); torchvision::_roi_pool_backward(grad, rois, argmax, ...).

@@ -247,3 +247,29 @@ def test_full_gpu_proposal_pipeline_stagewise(oracle, hw, seed, mode, B):
         got = keep[i, :int(cnt[i])].cpu().numpy()
         assert np.array_equal(got, want)
         assert np.array_equal(rois[i, :len(got)].cpu().numpy(), tb[got])
+
+
+# ------------------------------------------------------------------------------------ fused call / host pipeline
+def test_proposal_plan_and_host_pipeline_match_stagewise_ops(oracle):
+    """frr_rpn_proposals (one C-ABI call, caller workspace) and the double-buffered host pipeline return
+    exactly what the three separate ops return."""
+    from faster_rcnn_pytorch_b200 import region
+    hw, B = (320, 480), 3
+    ins = [synth.rpn_head_outputs(900 + i, hw) for i in range(2 * B)]
+    n = synth.num_anchors(hw)
+    for mode in ("train", "test"):
+        plan = region.ProposalPlan(B, n, DEV, image_hw=hw, mode=mode, logits=True)
+        pipe = region.HostProposalPipeline(plan)
+        tickets, wants = [], []
+        for s in range(2):
+            lg = np.stack([x[0] for x in ins[s * B:(s + 1) * B]]); rg = np.stack([x[1] for x in ins[s * B:(s + 1) * B]])
+            want_rois, want_cnt = region.rpn_proposals(dev(lg), dev(rg), image_hw=hw, mode=mode)
+            rois, cnt = plan.run(dev(lg), dev(rg))
+            assert torch.equal(rois, want_rois) and torch.equal(cnt, want_cnt)
+            tickets.append(pipe.submit(lg, rg))
+            wants.append((want_rois.cpu(), want_cnt.cpu()))
+        for t, (wr, wc) in zip(tickets, wants):
+            hr, hc = pipe.result(t)
+            assert torch.equal(hr, wr) and torch.equal(hc, wc)
+    with pytest.raises(ValueError):
+        plan.run(torch.zeros(B, n, 2), torch.zeros(B, n, 4))
