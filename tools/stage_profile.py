@@ -1,0 +1,135 @@
+"""Developer tool (GPU box): per-kernel timings of the training / inference region-stage kernels at the
+BASELINE config-3 / config-4 shapes, with algorithmic bytes and the fraction of the measured HBM
+peak; torchvision's own sm_100 CUDA kernels are timed beside them on the same inputs.
+
+    python tools/stage_profile.py [--quick]
+"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from faster_rcnn_pytorch_b200 import ops, synth, targets, region
+
+dev = torch.device("cuda:0")
+PEAK = 6538.3
+try:
+    PEAK = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def timeit(fn, reps=30, warm=5, flush=None):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()            # > L2: evict
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / reps * 1e3  # us
+
+
+def report(name, us, nbytes=None, **kw):
+    d = {"kernel": name, "us": round(us, 2)}
+    if nbytes:
+        d["MB"] = round(nbytes / 1e6, 2)
+        d["GBps"] = round(nbytes / us / 1e3, 1)
+        d["hbm_frac"] = round(nbytes / us / 1e3 / PEAK, 3)
+    d.update(kw)
+    print(json.dumps(d), flush=True)
+
+
+def main():
+    quick = "--quick" in sys.argv
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    import torchvision
+    for tag, B, C, fh, fw, per_img in [("cfg3_train", 16, 512, 37, 62, 128), ("cfg4_infer", 8, 512, 50, 83, 300)]:
+        K = B * per_img
+        feat = torch.from_numpy(synth.features(1, B, C, fh, fw)).to(dev)
+        rois_np = np.concatenate([np.concatenate([np.full((per_img, 1), b, np.float32),
+                                                  synth.random_boxes(10 + b, per_img)[0] * np.array([fw, fh, fw, fh], np.float32)], 1)
+                                  for b in range(B)])
+        rois = torch.from_numpy(rois_np).to(dev)
+        go = torch.randn((K, C, 7, 7), device=dev)
+        fbytes = feat.numel() * 4
+        obytes = K * C * 49 * 4
+        for cl in (False, True):
+            f = feat.contiguous(memory_format=torch.channels_last) if cl else feat
+            lay = "nhwc" if cl else "nchw"
+            out, arg = ops.roi_pool_forward(f, rois)
+            us = timeit(lambda: ops.roi_pool_forward(f, rois), flush=flush)
+            report(f"{tag}/roi_pool_fwd/{lay}", us, fbytes + 2 * obytes, K=K)
+            us = timeit(lambda: ops.roi_pool_forward(f, rois, want_argmax=False), flush=flush)
+            report(f"{tag}/roi_pool_fwd_noargmax/{lay}", us, fbytes + obytes, K=K)
+            us = timeit(lambda: ops.roi_pool_backward(go, arg, rois, feat.shape, channels_last=cl), flush=flush)
+            report(f"{tag}/roi_pool_bwd/{lay}", us, 2 * obytes + fbytes, K=K)
+            us = timeit(lambda: ops.roi_align_forward(f, rois, sampling_ratio=2), flush=flush)
+            report(f"{tag}/roi_align_fwd/{lay}", us, fbytes + obytes, K=K)
+            us = timeit(lambda: ops.roi_align_backward(go, rois, feat.shape, sampling_ratio=2, channels_last=cl), flush=flush)
+            report(f"{tag}/roi_align_bwd/{lay}", us, obytes + fbytes, K=K)
+        # torchvision's CUDA kernels (generic sm_100 recompiles) on the same inputs
+        us = timeit(lambda: torch.ops.torchvision.roi_pool(feat, rois, 1.0, 7, 7), flush=flush)
+        report(f"{tag}/torchvision_roi_pool_fwd", us, fbytes + 2 * obytes)
+        o_tv, a_tv = torch.ops.torchvision.roi_pool(feat, rois, 1.0, 7, 7)
+        us = timeit(lambda: torch.ops.torchvision._roi_pool_backward(go, rois, a_tv, 1.0, 7, 7, B, C, fh, fw), flush=flush)
+        report(f"{tag}/torchvision_roi_pool_bwd", us, 2 * obytes + fbytes)
+        us = timeit(lambda: torch.ops.torchvision.roi_align(feat, rois, 1.0, 7, 7, 2, False), flush=flush)
+        report(f"{tag}/torchvision_roi_align_fwd", us, fbytes + obytes)
+        us = timeit(lambda: torch.ops.torchvision._roi_align_backward(go, rois, 1.0, 7, 7, B, C, fh, fw, 2, False), flush=flush)
+        report(f"{tag}/torchvision_roi_align_bwd", us, obytes + fbytes)
+        if quick:
+            break
+
+    # ---- target makers (config 3: B=16, G=8, 600x1000, 2000 proposals)
+    hw, B, G, R = (600, 1000), 16, 8, 2000
+    N = synth.num_anchors(hw)
+    gt = torch.from_numpy(np.stack([synth.gt_boxes(3000 + i, G)[0] for i in range(B)])).to(dev)
+    lab = torch.from_numpy(np.stack([synth.gt_boxes(3000 + i, G)[1] for i in range(B)])).to(dev)
+    props = torch.from_numpy(np.stack([synth.random_boxes(3100 + i, R)[0] for i in range(B)])).to(dev)
+    us = timeit(lambda: ops.rpn_targets_assign(gt, None, N, image_hw=hw), flush=flush)
+    report("cfg3/rpn_targets_assign", us, B * N * (4 + 4 + 1 + 8), B=B, N=N)
+    ws = ops.rpn_targets_assign(gt, None, N, image_hw=hw)
+    us = timeit(lambda: ops.rpn_targets_finalize(ws, None, None), flush=flush)
+    report("cfg3/rpn_targets_finalize", us, B * N * (4 + 1 + 8 + 16), B=B, N=N)
+    us = timeit(lambda: ops.frcnn_targets_assign(props, None, gt, None), flush=flush)
+    report("cfg3/frcnn_targets_assign", us, B * (R + G) * (16 + 17), B=B)
+    torch.manual_seed(0)
+    us = timeit(lambda: targets.make_targets(gt, None, lab, props, None, image_hw=hw), reps=10)
+    report("cfg3/make_targets_host_roundtrip(4 kernels + 1 D2H + randperm + H2D)", us, B=B)
+
+    # ---- detection post-processing (config 4: B=8, R=300, C=81)
+    B, R, C = 8, 300, 81
+    cls = torch.from_numpy(np.stack([synth.head_outputs(600 + i, R, C)[0] for i in range(B)])).to(dev)
+    reg = torch.from_numpy(np.stack([synth.head_outputs(600 + i, R, C)[1] for i in range(B)])).to(dev)
+    rr = torch.from_numpy(np.stack([synth.random_boxes(700 + i, R)[0] for i in range(B)])).to(dev)
+    us = timeit(lambda: ops.decode_classwise(cls.reshape(B * R, C), reg.reshape(B * R, 4 * C), rr.reshape(B * R, 4), C), flush=flush)
+    report("cfg4/decode_classwise", us, B * R * C * (4 + 16 + 4 + 16), B=B)
+    prob, boxes = ops.decode_classwise(cls.reshape(B * R, C), reg.reshape(B * R, 4 * C), rr.reshape(B * R, 4), C)
+    for thres in (0.05, 0.005):
+        us = timeit(lambda: ops.class_nms(prob.reshape(B, R, C), boxes.reshape(B, R, 4 * C), C, score_thres=thres), flush=flush)
+        dc = ops.class_nms(prob.reshape(B, R, C), boxes.reshape(B, R, 4 * C), C, score_thres=thres)[3]
+        report(f"cfg4/class_nms(thres={thres})", us, B * R * C * 20, B=B, dets=int(dc.sum()))
+
+    # ---- inference proposals (config 4: 800x1333, 6000 -> 300) and config 1 (600x1000, B=1)
+    for tag, hw, B in [("cfg4", (800, 1333), 8), ("cfg1", (600, 1000), 1)]:
+        n = synth.num_anchors(hw)
+        rs = np.random.RandomState(1)
+        lg = torch.from_numpy(rs.standard_normal((B, n, 2)).astype(np.float32)).to(dev)
+        rg = torch.from_numpy((rs.standard_normal((B, n, 4)) * 0.2).astype(np.float32)).to(dev)
+        plan = region.ProposalPlan(B, n, dev, image_hw=hw, mode="test")
+        us = timeit(lambda: plan.run(lg, rg), flush=flush)
+        report(f"{tag}/rpn_proposals_test_mode", us, B=B, N=n)
+
+
+if __name__ == "__main__":
+    main()
