@@ -1,0 +1,553 @@
+// R1-R4 fast paths: RoIPool / RoIAlign 7x7 on feature planes that fit shared memory (the VGG16 stride-16 map of
+// models/model.py:97,113 and the coarse FPN levels of models/new_model.py:127,143).
+//
+// A CTA owns CB channel planes of ONE image; every feature element is read from HBM once and every output
+// element written once (HBM traffic = the algorithmic bytes), for NCHW and channels_last inputs alike.
+//
+// Forward (CB = 16, 8 or 4): the features are staged in shared memory PIXEL-MAJOR ([pixel][CB], chunk-swizzled): a
+//   thread owns one bin and ALL CB channels, so CB/4 LDS.128 feed CB running maxima and every loop / bounds / index
+//   instruction is shared by CB channels (one channel per thread cost 131 warp instructions per bin and channel,
+//   this layout ~25).  The lanes of a warp take the 49 bins of the SAME roi (same window size +-1 -> no
+//   divergence in the window loops).  The per-roi geometry (bin boundaries for RoIPool, 1-D bilinear sample
+//   records for RoIAlign) is computed once per roi into shared memory, not once per output element.  Results go
+//   to a shared-memory tile laid out exactly like the [K,C,7,7] output (the CB*49 values of one roi are
+//   contiguous there) and leave as coalesced 16-byte streaming stores.  (One cp.async.bulk store per roi was
+//   measured slower here: ~60 cycles of issue per 1.5 KB transfer on the critical path of warp 0.)
+// Backward (RoIPool, CB = 16 or 8): shared-memory float atomics are a CAS loop on sm_100 (LDS / FADD /
+//   ATOMS.CAST.SPIN) and global RED.ADD.F32 costs ~1.3 cycles per lane, so neither is used.  A WARP owns a plane
+//   exclusively (no inter-warp conflicts) and adds with plain LDS / FADD / STS.  Its lanes are 4 rois x 8
+//   bin-slices (lane j of a roi takes bins q = j (mod 8), in a per-lane rotated order so that the lanes of one roi
+//   work on far-apart bins); grad_out / argmax are read straight into registers (8 consecutive floats per roi and
+//   load -> full sectors), software-pipelined one roi-group ahead.  The only possible collisions -- two lanes
+//   hitting the same pixel in the same step -- are resolved by a one-byte ticket per pixel.  (Putting all 224
+//   items of a group into one ticket round was measured 1.6x slower: neighbouring bins then compete.)  Every
+//   plane is written once (TMA store): no memset pass, no global atomics.
+//
+// Numerics: RoIPool max/argmax bit-exact vs torchvision CPU (same scan order, strict >); RoIAlign keeps
+// torchvision's operation order (w1*v1+w2*v2+w3*v3+w4*v4, samples iy-major, / count), no FMA contraction.
+#include "roi_common.cuh"
+
+namespace frr {
+
+constexpr int kFastFwdThreads = 448;
+constexpr int kIdCap = 512;  // rois scanned per tile (one per thread, blockDim <= 512)
+constexpr int kPoolGeoCap = 126;  // RoIPool bin boundaries are computed for up to 126 rois at once (14 passes of 9)
+
+// developer instrumentation: clock64() cycles of CTA (0,0) per phase, accumulated over launches
+__device__ long long g_roi_dbg[16];
+#define ROI_TICK(slot)                          \
+    if (prof) {                                 \
+        const long long t1_ = clock64();        \
+        g_roi_dbg[slot] += t1_ - t0_;           \
+        t0_ = t1_;                              \
+    }
+
+struct FastHdr {
+    int cnt[16];
+    int id[kIdCap];
+};
+constexpr int kHdrBytes = 2304;
+static_assert(sizeof(FastHdr) <= kHdrBytes, "header does not fit");
+
+struct AlignRec {  // 1-D half of torchvision's bilinear_interpolate for one sample coordinate
+    int lo, hi;    // lo < 0: the sample is outside [-1, size] and contributes nothing
+    float l, h;    // weights of hi / lo
+};
+
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Ordered list of the rois of image b inside rois[tile, tile + blockDim): ids ascending.  Called by all threads
+// (blockDim a multiple of 32, <= 512).  Returns the count.
+__device__ __forceinline__ int stage_ids(const float* __restrict__ rois, int K, int tile, int b, FastHdr* hd) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const int k = tile + tid;
+    const bool ok = (k < K) && ((int)__ldg(rois + 5 * (size_t)k) == b);
+    const unsigned int m = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) hd->cnt[warp] = __popc(m);
+    __syncthreads();
+    int pre = 0, tot = 0;
+    for (int w = 0; w < nwarps; ++w) {
+        const int c = hd->cnt[w];
+        if (w < warp) pre += c;
+        tot += c;
+    }
+    if (ok) hd->id[pre + __popc(m & ((1u << lane) - 1u))] = k;
+    __syncthreads();
+    return tot;
+}
+
+__device__ __forceinline__ AlignRec align_rec(float v, int size) {
+    AlignRec r;
+    if (v < -1.0f || v > (float)size) {
+        r.lo = -1; r.hi = -1; r.l = 0.f; r.h = 0.f;
+        return r;
+    }
+    if (v <= 0.f) v = 0.f;
+    int lo = (int)v, hi;
+    if (lo >= size - 1) { hi = lo = size - 1; v = (float)lo; } else { hi = lo + 1; }
+    r.lo = lo; r.hi = hi;
+    r.l = __fsub_rn(v, (float)lo);
+    r.h = __fsub_rn(1.f, r.l);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+// Shared-memory feature layout: px[p][CB] -- the CB channels of pixel p are contiguous (CB/4 float4 chunks); chunk k of
+// pixel p is stored at chunk slot (k + p) % NCH so that lanes reading neighbouring pixels hit different bank groups.
+template <int CB>
+__device__ __forceinline__ int chunk_slot(int p, int k) {
+    return (k + p) & (CB / 4 - 1);
+}
+
+// NCHW: consecutive threads read consecutive pixels of 4 planes (coalesced), 2 trips (8 loads) in flight; channels_last:
+// consecutive threads read consecutive 16-byte channel chunks of a pixel, 4 trips in flight.  No runtime divisions.
+template <int CB>
+__device__ __forceinline__ void load_pixels(float4* px, const float* __restrict__ feat, int b, int c0, int C, int HW,
+                                            bool nhwc) {
+    constexpr int NCH = CB / 4;
+    const int nt = blockDim.x;
+    if (!nhwc) {
+#pragma unroll 1
+        for (int k = 0; k < NCH; ++k) {
+            const int c = c0 + 4 * k;
+            const float* src = feat + ((size_t)b * C + c) * HW;
+            const bool h0 = c + 0 < C, h1 = c + 1 < C, h2 = c + 2 < C, h3 = c + 3 < C;
+            for (int p0 = threadIdx.x; p0 < HW; p0 += 2 * nt) {
+                float4 v[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int p = p0 + u * nt;
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p < HW) {
+                        if (h0) v[u].x = __ldg(src + p);
+                        if (h1) v[u].y = __ldg(src + HW + p);
+                        if (h2) v[u].z = __ldg(src + 2 * (size_t)HW + p);
+                        if (h3) v[u].w = __ldg(src + 3 * (size_t)HW + p);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int p = p0 + u * nt;
+                    if (p < HW) px[(size_t)p * NCH + chunk_slot<CB>(p, k)] = v[u];
+                }
+            }
+        }
+    } else {
+        const int n = NCH * HW;
+        const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat) & 15u) == 0);
+        for (int i0 = threadIdx.x; i0 < n; i0 += 4 * nt) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * nt;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < n) {
+                    const int p = i / NCH, k = i - p * NCH;  // NCH is a compile-time power of two
+                    const int c = c0 + 4 * k;
+                    const float* src = feat + ((size_t)b * HW + p) * C + c;
+                    if (vec && c + 3 < C) {
+                        v[u] = __ldg(reinterpret_cast<const float4*>(src));
+                    } else {
+                        if (c + 0 < C) v[u].x = __ldg(src);
+                        if (c + 1 < C) v[u].y = __ldg(src + 1);
+                        if (c + 2 < C) v[u].z = __ldg(src + 2);
+                        if (c + 3 < C) v[u].w = __ldg(src + 3);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * nt;
+                if (i < n) {
+                    const int p = i / NCH, k = i - p * NCH;
+                    px[(size_t)p * NCH + chunk_slot<CB>(p, k)] = v[u];
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+template <int CB, bool kAlign, bool kArg>
+__global__ void __launch_bounds__(kFastFwdThreads, (CB <= 8) ? 2 : 1)
+    roi_fwd_fast_kernel(const float* __restrict__ feat, const float* __restrict__ rois, int K, int C, int H, int W, int RP,
+                        float scale, int aligned, int nhwc, float* __restrict__ out, int32_t* __restrict__ argmax) {
+    constexpr int NCH = CB / 4;                      // float4 chunks per pixel
+    constexpr int RS = kFastFwdThreads / 49;         // rois worked on at the same time (9)
+    constexpr int kGeoPer = kAlign ? 28 * 16 : 28 * 2;  // geometry bytes per roi
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FastHdr* hd = reinterpret_cast<FastHdr*>(smem_raw);
+    unsigned char* geo = smem_raw + kHdrBytes;  // [GC] rois
+    const int GC = kAlign ? RP : kPoolGeoCap;    // rois whose geometry is computed together
+    const int stage = RP * CB * 49;              // values in the staging tile: [roi][channel][49]
+    float* s_out = reinterpret_cast<float*>(geo + ((GC * kGeoPer + 127) & ~127));
+    int32_t* s_arg = reinterpret_cast<int32_t*>(s_out + stage);  // (kArg only)
+    float4* px = reinterpret_cast<float4*>(kArg ? reinterpret_cast<unsigned char*>(s_arg + stage)
+                                                : reinterpret_cast<unsigned char*>(s_arg));
+
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y, c0 = blockIdx.x * CB;
+    const int HW = H * W;
+    const int cb = min(CB, C - c0);
+    const bool prof = (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0);
+    long long t0_ = clock64();
+    load_pixels<CB>(px, feat, b, c0, C, HW, nhwc != 0);
+    ROI_TICK(0);
+
+    // thread -> (roi slot rs, bin): the 49 bins of a roi sit in consecutive lanes (same window size +-1)
+    const int rs = tid / 49;
+    const int bin = tid - rs * 49;
+    const int ph = bin / 7, pw = bin - ph * 7;
+    const bool worker = rs < RS;
+    // vector copy-out needs 16-byte aligned runs of cb*49 values
+    const bool vec_ok = ((cb * 196) % 16 == 0) && (((size_t)C * 196) % 16 == 0) && (((size_t)c0 * 196) % 16 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) &&
+                        (!kArg || (reinterpret_cast<uintptr_t>(argmax) & 15u) == 0);
+
+    for (int tile = 0; tile < K; tile += kFastFwdThreads) {
+        const int ns = stage_ids(rois, K, tile, b, hd);
+        ROI_TICK(1);
+        for (int g0 = 0; g0 < ns; g0 += GC) {
+          // ---- geometry of rois g0 .. g0+GC, once per roi ------------------------------------------------
+          const int ng = min(GC, ns - g0);
+          for (int t = tid; t < ng * 28; t += kFastFwdThreads) {
+              const int s = t / 28, j = t - s * 28;
+              const float* r = rois + 5 * (size_t)hd->id[g0 + s];
+              if (!kAlign) {
+                  const int kind = j / 7, p = j - kind * 7;  // hs[7] he[7] ws[7] we[7]
+                  const PoolGeom gm = pool_geom(r, scale);
+                  int v;
+                  if (kind < 2) {
+                      const float bsz = __fdiv_rn((float)gm.rh, 7.0f);
+                      v = (kind == 0 ? (int)floorf(__fmul_rn((float)p, bsz)) : (int)ceilf(__fmul_rn((float)(p + 1), bsz))) + gm.sh;
+                      v = min(max(v, 0), H);
+                  } else {
+                      const float bsz = __fdiv_rn((float)gm.rw, 7.0f);
+                      v = (kind == 2 ? (int)floorf(__fmul_rn((float)p, bsz)) : (int)ceilf(__fmul_rn((float)(p + 1), bsz))) + gm.sw;
+                      v = min(max(v, 0), W);
+                  }
+                  reinterpret_cast<short*>(geo)[t] = (short)v;
+              } else {  // y samples 0..13, x samples 0..13
+                  const AlignGeom gm = align_geom(r, scale, 7, 7, 2, aligned != 0);
+                  reinterpret_cast<AlignRec*>(geo)[t] = (j < 14) ? align_rec(sample_y(gm, j >> 1, j & 1), H)
+                                                                 : align_rec(sample_x(gm, (j - 14) >> 1, (j - 14) & 1), W);
+              }
+          }
+          __syncthreads();
+          ROI_TICK(2);
+          for (int p0 = g0; p0 < g0 + ng; p0 += RP) {
+            const int nr = min(RP, g0 + ng - p0);
+            const int gs = p0 - g0;  // geometry slot of the pass's first roi
+            if (worker) {
+#pragma unroll 1
+                for (int s = rs; s < nr; s += RS) {
+                    float* so = s_out + s * CB * 49 + bin;
+                    if (!kAlign) {
+                        const short* bnd = reinterpret_cast<const short*>(geo) + (gs + s) * 28;
+                        const int hs = bnd[ph], he = bnd[7 + ph], ws = bnd[14 + pw], we = bnd[21 + pw];
+                        const float init = ((he <= hs) || (we <= ws)) ? 0.f : -FLT_MAX;
+                        float best[CB];
+                        int bidx[CB];
+#pragma unroll
+                        for (int c = 0; c < CB; ++c) { best[c] = init; bidx[c] = -1; }
+#pragma unroll 1
+                        for (int h = hs; h < he; ++h) {
+#pragma unroll 1
+                            for (int idx = h * W + ws; idx < h * W + we; ++idx) {
+                                const float4* pp = px + (size_t)idx * NCH;
+#pragma unroll
+                                for (int k = 0; k < NCH; ++k) {
+                                    const float4 v = pp[chunk_slot<CB>(idx, k)];
+                                    if (kArg) {
+                                        if (v.x > best[4 * k + 0]) { best[4 * k + 0] = v.x; bidx[4 * k + 0] = idx; }
+                                        if (v.y > best[4 * k + 1]) { best[4 * k + 1] = v.y; bidx[4 * k + 1] = idx; }
+                                        if (v.z > best[4 * k + 2]) { best[4 * k + 2] = v.z; bidx[4 * k + 2] = idx; }
+                                        if (v.w > best[4 * k + 3]) { best[4 * k + 3] = v.w; bidx[4 * k + 3] = idx; }
+                                    } else {
+                                        best[4 * k + 0] = fmaxf(best[4 * k + 0], v.x);
+                                        best[4 * k + 1] = fmaxf(best[4 * k + 1], v.y);
+                                        best[4 * k + 2] = fmaxf(best[4 * k + 2], v.z);
+                                        best[4 * k + 3] = fmaxf(best[4 * k + 3], v.w);
+                                    }
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int c = 0; c < CB; ++c) so[c * 49] = best[c];
+                        if (kArg) {
+                            int32_t* sa = s_arg + s * CB * 49 + bin;
+#pragma unroll
+                            for (int c = 0; c < CB; ++c) sa[c * 49] = bidx[c];
+                        }
+                    } else {
+                        const AlignRec* rec = reinterpret_cast<const AlignRec*>(geo) + (gs + s) * 28;
+                        float acc[CB];
+#pragma unroll
+                        for (int c = 0; c < CB; ++c) acc[c] = 0.f;
+#pragma unroll 1
+                        for (int s4 = 0; s4 < 4; ++s4) {
+                            const AlignRec yy = rec[2 * ph + (s4 >> 1)];
+                            const AlignRec xx = rec[14 + 2 * pw + (s4 & 1)];
+                            if (yy.lo >= 0 && xx.lo >= 0) {
+                                const float w1 = __fmul_rn(yy.h, xx.h), w2 = __fmul_rn(yy.h, xx.l);
+                                const float w3 = __fmul_rn(yy.l, xx.h), w4 = __fmul_rn(yy.l, xx.l);
+                                const int i1 = yy.lo * W + xx.lo, i2 = yy.lo * W + xx.hi;
+                                const int i3 = yy.hi * W + xx.lo, i4 = yy.hi * W + xx.hi;
+#pragma unroll
+                                for (int k = 0; k < NCH; ++k) {
+                                    const float4 v1 = px[(size_t)i1 * NCH + chunk_slot<CB>(i1, k)];
+                                    const float4 v2 = px[(size_t)i2 * NCH + chunk_slot<CB>(i2, k)];
+                                    const float4 v3 = px[(size_t)i3 * NCH + chunk_slot<CB>(i3, k)];
+                                    const float4 v4 = px[(size_t)i4 * NCH + chunk_slot<CB>(i4, k)];
+#define FRR_BIL(e, c)                                                                                                   \
+    acc[4 * k + e] = __fadd_rn(acc[4 * k + e],                                                                          \
+                               __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, v1.c), __fmul_rn(w2, v2.c)), __fmul_rn(w3, v3.c)), \
+                                         __fmul_rn(w4, v4.c)))
+                                    FRR_BIL(0, x); FRR_BIL(1, y); FRR_BIL(2, z); FRR_BIL(3, w);
+#undef FRR_BIL
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int c = 0; c < CB; ++c) so[c * 49] = __fdiv_rn(acc[c], 4.0f);
+                    }
+                }
+            }
+            __syncthreads();
+            ROI_TICK(3);
+            // ---- copy-out: the cb*49 values of a roi are contiguous in the output -> coalesced 16-byte stores;
+            //      warp w takes rois w, w + 14, ...: no index divisions
+            {
+                const int warp = tid >> 5, lane = tid & 31;
+                for (int s = warp; s < nr; s += kFastFwdThreads / 32) {
+                    const size_t o = ((size_t)hd->id[p0 + s] * C + c0) * 49;
+                    if (vec_ok) {
+                        const float4* so4 = reinterpret_cast<const float4*>(s_out + s * CB * 49);
+                        const int4* sa4 = reinterpret_cast<const int4*>(s_arg + s * CB * 49);
+                        for (int e = lane; e < cb * 49 / 4; e += 32) {
+                            st_stream(reinterpret_cast<float4*>(out + o) + e, so4[e]);
+                            if (kArg) reinterpret_cast<int4*>(argmax + o)[e] = sa4[e];
+                        }
+                    } else {
+                        for (int e = lane; e < cb * 49; e += 32) {
+                            out[o + e] = s_out[s * CB * 49 + e];
+                            if (kArg) argmax[o + e] = s_arg[s * CB * 49 + e];
+                        }
+                    }
+                }
+            }
+            __syncthreads();  // the staging tile (and, after the last pass, the geometry) is rewritten next
+            ROI_TICK(4);
+          }
+        }
+    }
+    ROI_TICK(5);
+}
+
+// ---------------------------------------------------------------------------------------------
+// RoIPool backward
+// ---------------------------------------------------------------------------------------------
+template <int CB>
+__global__ void __launch_bounds__(CB * 32, 1)
+    roi_pool_bwd_fast_kernel(const float* __restrict__ grad_out, const int32_t* __restrict__ argmax,
+                             const float* __restrict__ rois, int K, int C, int H, int W, int nhwc,
+                             float* __restrict__ grad_in) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FastHdr* hd = reinterpret_cast<FastHdr*>(smem_raw);
+    float* planes = reinterpret_cast<float*>(smem_raw + kHdrBytes);
+    const int HW = H * W;
+    const int HWp = (HW + 15) & ~15;
+    unsigned char* tags = reinterpret_cast<unsigned char*>(planes + (size_t)CB * HW);  // [CB][HWp]
+    float* itm_g = reinterpret_cast<float*>(tags + (size_t)CB * HWp);                   // [CB][7][32]
+    int* itm_a = reinterpret_cast<int*>(itm_g + CB * 7 * 32);                           // [CB][7][32]
+
+    const int tid = threadIdx.x, lane = tid & 31, c = tid >> 5;  // warp c owns plane c
+    const int b = blockIdx.y, c0 = blockIdx.x * CB;
+    const int cb = min(CB, C - c0);
+    const bool prof = (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0);
+    long long t0_ = clock64();
+    for (int i = tid; i < CB * HW; i += CB * 32) planes[i] = 0.f;
+    float* pl = planes + (size_t)c * HW;
+    unsigned char* tg = tags + (size_t)c * HWp;
+    float* ig = itm_g + c * 7 * 32 + lane;
+    int* ia = itm_a + c * 7 * 32 + lane;
+    __syncthreads();
+    ROI_TICK(8);
+
+    const int rl = lane >> 3, j = lane & 7;  // lane = (roi of the group, bin slice): bins q = j + 8k, k rotated per lane
+    const int rot = (j == 7) ? 1 : (3 * j) % 7;
+    const size_t chan = (size_t)(c0 + c) * 49;
+    for (int tile = 0; tile < K; tile += CB * 32) {
+        const int ns = stage_ids(rois, K, tile, b, hd);
+        ROI_TICK(9);
+        if (c < cb) {
+            float g[7], gn[7];
+            int a[7], an[7];
+            auto fetch = [&](int r0, float* gg, int* aa) {
+                const int r = r0 + rl;
+                const bool have = r < ns;
+                const size_t base = have ? (size_t)hd->id[r] * C * 49 + chan : 0;
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                    const int q = j + 8 * k;
+                    gg[k] = 0.f;
+                    aa[k] = -1;
+                    if (have && q < 49) {
+                        gg[k] = __ldg(grad_out + base + q);
+                        aa[k] = __ldg(argmax + base + q);
+                    }
+                }
+            };
+            fetch(0, g, a);
+            for (int r0 = 0; r0 < ns; r0 += 4) {
+                fetch(r0 + 4, gn, an);  // next group in flight while this one is accumulated
+                // the lane's 7 items go through shared memory ([k][lane], conflict free) so that the rotated order
+                // below is a dynamic address, not a 7-way select chain
+#pragma unroll
+                for (int k = 0; k < 7; ++k) { ig[k * 32] = g[k]; ia[k * 32] = a[k]; }
+                int kk = rot;
+#pragma unroll 1
+                for (int st = 0; st < 7; ++st) {
+                    // rotated order: at step st lane j works on k = (st + rot_j) % 7, rot = {0,3,6,2,5,1,4,1}: the lanes
+                    // of one roi are then >= 2 bins apart in both directions
+                    const int av = ia[kk * 32];
+                    const float gv = ig[kk * 32];
+                    kk = (kk == 6) ? 0 : kk + 1;
+                    bool act = av >= 0;
+                    unsigned int pending = __ballot_sync(0xffffffffu, act);
+                    while (pending) {  // one trip unless two lanes hit the same pixel in this step
+                        if (act) tg[av] = (unsigned char)lane;
+                        __syncwarp();
+                        const bool won = act && tg[av] == (unsigned char)lane;
+                        __syncwarp();
+                        if (won) {
+                            pl[av] = __fadd_rn(pl[av], gv);
+                            act = false;
+                        }
+                        pending = __ballot_sync(0xffffffffu, act);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 7; ++k) { g[k] = gn[k]; a[k] = an[k]; }
+            }
+        }
+        ROI_TICK(10);
+        __syncthreads();  // ids are rewritten by the next tile
+    }
+    ROI_TICK(11);
+    store_planes(planes, grad_in, b, c0, cb, C, HW, nhwc != 0);
+    ROI_TICK(12);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: 0 = launched, 1 = shape outside the fast path (caller falls back), < 0 = error
+// ---------------------------------------------------------------------------------------------
+static const size_t kSmemLimit = 227 * 1024;
+
+// rois per pass for a shared-memory budget: as many as fit beside the pixels, a multiple of 9 (9 rois are worked on
+// at the same time: 448 threads / 49 bins), capped; 0 = no fit
+static int fwd_fast_rp(int CB, int HW, bool align, bool arg, size_t budget) {
+    const size_t fixed = kHdrBytes + 128 + (size_t)CB * HW * 4 + (align ? 0 : (size_t)kPoolGeoCap * 56);
+    if (fixed >= budget) return 0;
+    const size_t per_roi = (size_t)CB * 49 * 4 * (arg ? 2 : 1) + (align ? 28 * 16 : 0);
+    int rp = (int)((budget - fixed) / per_roi);
+    if (rp > 36) rp = 36;
+    return rp / 9 * 9;
+}
+static size_t fwd_fast_smem(int CB, int HW, bool align, bool arg, int rp) {
+    const size_t geo = ((align ? (size_t)rp * 28 * 16 : (size_t)kPoolGeoCap * 56) + 127) & ~(size_t)127;
+    return kHdrBytes + geo + (size_t)rp * CB * 49 * 4 * (arg ? 2 : 1) + (size_t)CB * HW * 4;
+}
+// CB <= 8 kernels are built for two CTAs per SM (28 warps hide the shared-memory latency of the window loops)
+static size_t fwd_budget(int CB) { return CB <= 8 ? (kSmemLimit - 2048) / 2 : kSmemLimit; }
+static size_t bwd_fast_smem(int CB, int HW) {
+    return kHdrBytes + (size_t)CB * HW * 4 + (size_t)CB * ((HW + 15) & ~15) + (size_t)CB * 7 * 32 * 8;
+}
+
+template <bool kAlign, bool kArg, int CB>
+static int launch_fwd(const float* feat, const float* rois, int K, int B, int C, int H, int W, float scale, int aligned,
+                      int nhwc, float* out, int32_t* argmax, cudaStream_t st) {
+    auto kern = roi_fwd_fast_kernel<CB, kAlign, kArg>;
+    int rp = fwd_fast_rp(CB, H * W, kAlign, kArg, fwd_budget(CB));
+    if (rp == 0) rp = fwd_fast_rp(CB, H * W, kAlign, kArg, kSmemLimit);
+    const size_t smem = fwd_fast_smem(CB, H * W, kAlign, kArg, rp);
+    FRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    kern<<<dim3((C + CB - 1) / CB, B), kFastFwdThreads, smem, st>>>(feat, rois, K, C, H, W, rp, scale, aligned, nhwc, out,
+                                                                     argmax);
+    return FRR_OK;
+}
+
+int roi_fwd_fast(bool align, const float* feat, const float* rois, int K, int B, int C, int H, int W, int PH, int PW,
+                 float scale, int sampling, int aligned, int nhwc, float* out, int32_t* argmax, frr_stream_t stream) {
+    if (PH != 7 || PW != 7 || (align && sampling != 2) || H > 32767 || W > 32767) return 1;
+    const bool arg = !align && argmax != nullptr;
+    const int HW = H * W;
+    // CB = 8 when two CTAs fit an SM, else 4 when two fit, else the largest of {16, 8, 4} that fits at all
+    int cbk = 0;
+    for (int t = 8; t >= 4 && cbk == 0; t >>= 1)
+        if (fwd_fast_rp(t, HW, align, arg, fwd_budget(t)) > 0) cbk = t;
+    for (int t = 16; t >= 4 && cbk == 0; t >>= 1)
+        if (fwd_fast_rp(t, HW, align, arg, kSmemLimit) > 0) cbk = t;
+    if (cbk == 0) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+#define FRR_FWD(CBK)                                                                                                 \
+    (align ? launch_fwd<true, false, CBK>(feat, rois, K, B, C, H, W, scale, aligned, nhwc, out, argmax, st)          \
+     : arg ? launch_fwd<false, true, CBK>(feat, rois, K, B, C, H, W, scale, aligned, nhwc, out, argmax, st)          \
+           : launch_fwd<false, false, CBK>(feat, rois, K, B, C, H, W, scale, aligned, nhwc, out, argmax, st))
+    rc = cbk == 16 ? FRR_FWD(16) : cbk == 8 ? FRR_FWD(8) : FRR_FWD(4);
+#undef FRR_FWD
+    if (rc) return rc;
+    count_launch();
+    FRR_CHECK_LAUNCH("roi_fwd_fast_kernel");
+    return FRR_OK;
+}
+
+template <int CB>
+static int launch_pool_bwd(const float* go, const int32_t* argmax, const float* rois, int K, int B, int C, int H, int W,
+                           int nhwc, float* gin, cudaStream_t st) {
+    auto kern = roi_pool_bwd_fast_kernel<CB>;
+    const size_t smem = bwd_fast_smem(CB, H * W);
+    FRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    kern<<<dim3((C + CB - 1) / CB, B), CB * 32, smem, st>>>(go, argmax, rois, K, C, H, W, nhwc, gin);
+    return FRR_OK;
+}
+
+int roi_pool_bwd_fast(const float* grad_out, const int32_t* argmax, const float* rois, int K, int B, int C, int H, int W,
+                      int PH, int PW, int nhwc, float* grad_in, frr_stream_t stream) {
+    if (PH != 7 || PW != 7) return 1;
+    const int HW = H * W;
+    int cbk = 0;
+    for (int t = 16; t >= 4; t >>= 1) {
+        if (bwd_fast_smem(t, HW) > kSmemLimit) continue;
+        cbk = t;
+        if ((long)B * ((C + t - 1) / t) >= (long)num_sms()) break;
+    }
+    if (cbk == 0) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rc = cbk == 16 ? launch_pool_bwd<16>(grad_out, argmax, rois, K, B, C, H, W, nhwc, grad_in, st)
+                 : cbk == 8  ? launch_pool_bwd<8>(grad_out, argmax, rois, K, B, C, H, W, nhwc, grad_in, st)
+                             : launch_pool_bwd<4>(grad_out, argmax, rois, K, B, C, H, W, nhwc, grad_in, st);
+    if (rc) return rc;
+    count_launch();
+    FRR_CHECK_LAUNCH("roi_pool_bwd_fast_kernel");
+    return FRR_OK;
+}
+
+}  // namespace frr
+
+// Developer hook: copies the 16 phase counters (cycles of CTA (0,0): forward 0 plane load, 1 roi scan, 2 geometry +
+// buffer wait, 3 compute, 4 store issue, 5 drain; backward 8 zero, 9 roi scan, 10 accumulate, 11 tile syncs,
+// 12 plane store) to the host and clears them.  Synchronises the device.
+extern "C" int frr_roi_debug_cycles(int64_t* host_out16) {
+    FRR_CHECK_ARG(host_out16 != nullptr, "frr_roi_debug_cycles: null pointer");
+    long long z[16] = {0};
+    FRR_CUDA(cudaMemcpyFromSymbol(host_out16, frr::g_roi_dbg, sizeof(z)));
+    FRR_CUDA(cudaMemcpyToSymbol(frr::g_roi_dbg, z, sizeof(z)));
+    return FRR_OK;
+}

@@ -143,6 +143,10 @@ int frr_roi_align_bwd(const float* grad_out, const float* rois, int K, int B, in
                       float spatial_scale, int sampling_ratio, int aligned, int channels_last, float* grad_in,
                       frr_stream_t stream);
 
+/* Developer hook: per-phase clock64() cycles of CTA (0,0) of the 7x7 fast kernels, accumulated since the last call
+ * (16 slots, see roi_fast.cu); copies to host_out16 and clears.  Synchronises the device. */
+int frr_roi_debug_cycles(int64_t* host_out16);
+
 /* ---------------------------------------------------------------------------------------
  * T1  RPN target maker -- RPNTargetMaker.forward, models/model.py:186-266 (IoU: utils/util.py:66-102).
  *     Two kernels around one small D2H copy, because the reference samples with torch.randperm on

@@ -53,13 +53,25 @@ def main():
     quick = "--quick" in sys.argv
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     import torchvision
-    for tag, B, C, fh, fw, per_img in [("cfg3_train", 16, 512, 37, 62, 128), ("cfg4_infer", 8, 512, 50, 83, 300)]:
+    for tag, B, C, fh, fw, per_img, real in [("cfg3_train", 16, 512, 37, 62, 128, False), ("cfg3_train_rpnrois", 16, 512, 37, 62, 128, True),
+                                              ("cfg4_infer", 8, 512, 50, 83, 300, False), ("cfg4_infer_rpnrois", 8, 512, 50, 83, 300, True)]:
         K = B * per_img
         feat = torch.from_numpy(synth.features(1, B, C, fh, fw)).to(dev)
-        rois_np = np.concatenate([np.concatenate([np.full((per_img, 1), b, np.float32),
-                                                  synth.random_boxes(10 + b, per_img)[0] * np.array([fw, fh, fw, fh], np.float32)], 1)
-                                  for b in range(B)])
-        rois = torch.from_numpy(rois_np).to(dev)
+        if real:   # proposals of the RPN pipeline on synthetic head outputs: first per_img per image
+            hw = (fh * 16, fw * 16)
+            n = synth.num_anchors(hw)
+            rs = np.random.RandomState(77)
+            lg = torch.from_numpy(rs.standard_normal((B, n, 2)).astype(np.float32)).to(dev)
+            rg = torch.from_numpy((rs.standard_normal((B, n, 4)) * 0.2).astype(np.float32)).to(dev)
+            pr, pc = region.rpn_proposals(lg, rg, image_hw=hw, mode="train")
+            assert int(pc.min()) >= per_img
+            boxes = pr[:, :per_img].cpu().numpy() * np.array([fw, fh, fw, fh], np.float32)
+            rois_np = np.concatenate([np.concatenate([np.full((per_img, 1), b, np.float32), boxes[b]], 1) for b in range(B)])
+        else:
+            rois_np = np.concatenate([np.concatenate([np.full((per_img, 1), b, np.float32),
+                                                      synth.random_boxes(10 + b, per_img)[0] * np.array([fw, fh, fw, fh], np.float32)], 1)
+                                      for b in range(B)])
+        rois = torch.from_numpy(rois_np.astype(np.float32)).to(dev)
         go = torch.randn((K, C, 7, 7), device=dev)
         fbytes = feat.numel() * 4
         obytes = K * C * 49 * 4
@@ -87,7 +99,7 @@ def main():
         report(f"{tag}/torchvision_roi_align_fwd", us, fbytes + obytes)
         us = timeit(lambda: torch.ops.torchvision._roi_align_backward(go, rois, 1.0, 7, 7, B, C, fh, fw, 2, False), flush=flush)
         report(f"{tag}/torchvision_roi_align_bwd", us, obytes + fbytes)
-        if quick:
+        if quick and real:
             break
 
     # ---- target makers (config 3: B=16, G=8, 600x1000, 2000 proposals)
