@@ -261,6 +261,8 @@ int roi_fwd_fast(bool align, const float* feat, const float* rois, int K, int B,
                  float scale, int sampling, int aligned, int nhwc, float* out, int32_t* argmax, frr_stream_t stream);
 int roi_pool_bwd_fast(const float* grad_out, const int32_t* argmax, const float* rois, int K, int B, int C, int H, int W,
                       int PH, int PW, int nhwc, float* grad_in, frr_stream_t stream);
+int roi_align_bwd_fast(const float* grad_out, const float* rois, int K, int B, int C, int H, int W, int PH, int PW,
+                       float scale, int sampling, int aligned, int nhwc, float* grad_in, frr_stream_t stream);
 
 static size_t roi_smem_bytes(int CB, int HW) {
     return ((sizeof(RoiSmemHdr) + 127) & ~(size_t)127) + (size_t)CB * HW * sizeof(float);
@@ -318,8 +320,9 @@ static int roi_backward(const float* grad_out, const int32_t* argmax, const floa
     FRR_CHECK_ARG(grad_in && (K == 0 || (grad_out && rois)), "roi backward: null pointer");
     FRR_CHECK_ARG(kAlign || K == 0 || argmax, "roi_pool backward: argmax is required");
     FRR_CHECK_ARG(K >= 0 && B > 0 && C > 0 && H > 0 && W > 0 && PH > 0 && PW > 0 && B <= 65535, "roi backward: bad sizes");
-    if (!kAlign && K > 0) {
-        const int rc = roi_pool_bwd_fast(grad_out, argmax, rois, K, B, C, H, W, PH, PW, nhwc, grad_in, stream);
+    if (K > 0) {
+        const int rc = kAlign ? roi_align_bwd_fast(grad_out, rois, K, B, C, H, W, PH, PW, scale, sampling, aligned, nhwc, grad_in, stream)
+                              : roi_pool_bwd_fast(grad_out, argmax, rois, K, B, C, H, W, PH, PW, nhwc, grad_in, stream);
         if (rc <= 0) return rc;
     }
     cudaStream_t st = (cudaStream_t)stream;

@@ -445,6 +445,142 @@ __global__ void __launch_bounds__(CB * 32, 1)
 }
 
 // ---------------------------------------------------------------------------------------------
+// RoIAlign backward (sampling_ratio = 2)
+// ---------------------------------------------------------------------------------------------
+// The bilinear weights are separable and channel independent.  Per roi the CTA builds, once, the 14 y-sample records
+// and the dense 7 x Wt matrix Ax[pw][w] = total x-weight of bin column pw on pixel column w; then every warp (= one
+// channel plane, owned exclusively) computes for ITS channel
+//     T[ph][w]      = sum_pw grad_out[ph][pw] * Ax[pw][w]              (lanes = pixel columns, <= 3 bins per column)
+//     plane[y][w]  += 0.25 * wy * T[ph(s)][w]   for the 2 taps (y, wy) of each of the 14 y samples
+// Lanes own distinct columns and the samples are walked in order, so the adds are plain LDS / FFMA / STS: no atomics,
+// no tickets.  torchvision scatters 16 atomicAdd per output element instead (822 M atomics at the config-3 shape).
+constexpr int kAbRois = 8;    // rois per geometry group
+constexpr int kAbCols = 128;  // widest feature map of the fast path (a roi touches at most W pixel columns)
+
+struct AlignBwdGeo {
+    AlignRec y[14];
+    AlignRec x[14];
+    float ax[7][kAbCols];
+    unsigned char pw_lo[kAbCols];
+    int x0, wt, span, pad;
+};
+
+template <int CB>
+__global__ void __launch_bounds__(CB * 32, 1)
+    roi_align_bwd_fast_kernel(const float* __restrict__ grad_out, const float* __restrict__ rois, int K, int C, int H,
+                              int W, float scale, int aligned, int nhwc, float* __restrict__ grad_in) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FastHdr* hd = reinterpret_cast<FastHdr*>(smem_raw);
+    AlignBwdGeo* geo = reinterpret_cast<AlignBwdGeo*>(smem_raw + kHdrBytes);                 // [kAbRois]
+    float* sgo = reinterpret_cast<float*>(geo + kAbRois);                                     // [CB][64]
+    float* planes = sgo + CB * 64;
+    const int HW = H * W;
+
+    const int tid = threadIdx.x, lane = tid & 31, c = tid >> 5;  // warp c owns plane c
+    const int b = blockIdx.y, c0 = blockIdx.x * CB;
+    const int cb = min(CB, C - c0);
+    for (int i = tid; i < CB * HW; i += CB * 32) planes[i] = 0.f;
+    float* pl = planes + (size_t)c * HW;
+    float* mygo = sgo + c * 64;
+    const size_t chan = (size_t)(c0 + c) * 49;
+    if (tid < kAbRois) geo[tid].span = 0;
+    __syncthreads();
+
+    for (int tile = 0; tile < K; tile += CB * 32) {
+        const int ns = stage_ids(rois, K, tile, b, hd);
+        for (int r0 = 0; r0 < ns; r0 += kAbRois) {
+            const int nr = min(kAbRois, ns - r0);
+            // ---- geometry of the group, built once for all channels -----------------------------------
+            // (a) sample records: thread (roi, j < 28)
+            for (int t = tid; t < nr * 28; t += CB * 32) {
+                const int s = t / 28, j = t - s * 28;
+                const AlignGeom gm = align_geom(rois + 5 * (size_t)hd->id[r0 + s], scale, 7, 7, 2, aligned != 0);
+                if (j < 14) geo[s].y[j] = align_rec(sample_y(gm, j >> 1, j & 1), H);
+                else geo[s].x[j - 14] = align_rec(sample_x(gm, (j - 14) >> 1, (j - 14) & 1), W);
+            }
+            __syncthreads();
+            // (b) column extent of every roi
+            if (tid < nr) {
+                int lo = W, hi = -1;
+                for (int j = 0; j < 14; ++j) {
+                    const AlignRec r = geo[tid].x[j];
+                    if (r.lo >= 0) { lo = min(lo, r.lo); hi = max(hi, r.hi); }
+                }
+                geo[tid].x0 = lo;
+                geo[tid].wt = hi >= lo ? hi - lo + 1 : 0;
+            }
+            __syncthreads();
+            // (c) Ax[pw][w] and the first bin column of every pixel column
+            for (int t = tid; t < nr * kAbCols; t += CB * 32) {
+                const int s = t / kAbCols, w = t - s * kAbCols;
+                const int col = geo[s].x0 + w;
+                int first = 7, last = -1;
+#pragma unroll
+                for (int pw = 0; pw < 7; ++pw) {
+                    float a = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const AlignRec r = geo[s].x[2 * pw + i];
+                        if (r.lo >= 0) {
+                            if (r.lo == col) a = __fadd_rn(a, r.h);
+                            if (r.hi == col) a = __fadd_rn(a, r.l);
+                        }
+                    }
+                    geo[s].ax[pw][w] = a;
+                    if (a != 0.f) { first = min(first, pw); last = pw; }
+                }
+                geo[s].pw_lo[w] = (unsigned char)(first == 7 ? 0 : first);
+                if (w < geo[s].wt && last >= first) atomicMax(&geo[s].span, last - first + 1);
+            }
+            __syncthreads();
+
+            if (c < cb) {
+                for (int s = 0; s < nr; ++s) {
+                    const AlignBwdGeo& gg = geo[s];
+                    // stage this channel's 49 output gradients (coalesced) for broadcast reads
+                    const size_t base = (size_t)hd->id[r0 + s] * C * 49 + chan;
+                    mygo[lane] = __ldg(grad_out + base + lane);
+                    if (lane + 32 < 49) mygo[lane + 32] = __ldg(grad_out + base + lane + 32);
+                    __syncwarp();
+                    const int span = gg.span;
+                    for (int w0 = 0; w0 < gg.wt; w0 += 32) {
+                        const int w = w0 + lane;
+                        const bool on = w < gg.wt;
+                        float T[7];
+#pragma unroll
+                        for (int ph = 0; ph < 7; ++ph) T[ph] = 0.f;
+                        const int plo = on ? (int)gg.pw_lo[w] : 0;
+                        for (int i = 0; i < span; ++i) {
+                            const int pw = min(plo + i, 6);
+                            const float a = (on && plo + i < 7) ? gg.ax[pw][w] : 0.f;
+#pragma unroll
+                            for (int ph = 0; ph < 7; ++ph) T[ph] = __fmaf_rn(a, mygo[ph * 7 + pw], T[ph]);
+                        }
+                        float* colp = pl + gg.x0 + w;
+#pragma unroll
+                        for (int sy = 0; sy < 14; ++sy) {
+                            const AlignRec yr = gg.y[sy];
+                            if (on && yr.lo >= 0) {
+                                const float t = __fmul_rn(0.25f, T[sy >> 1]);
+                                float* p0 = colp + yr.lo * W;
+                                *p0 = __fmaf_rn(yr.h, t, *p0);
+                                float* p1 = colp + yr.hi * W;
+                                *p1 = __fmaf_rn(yr.l, t, *p1);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            __syncthreads();  // geometry is rewritten by the next group
+            if (tid < kAbRois) geo[tid].span = 0;
+        }
+        __syncthreads();  // ids are rewritten by the next tile
+    }
+    store_planes(planes, grad_in, b, c0, cb, C, HW, nhwc != 0);
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side: 0 = launched, 1 = shape outside the fast path (caller falls back), < 0 = error
 // ---------------------------------------------------------------------------------------------
 static const size_t kSmemLimit = 227 * 1024;
@@ -536,6 +672,41 @@ int roi_pool_bwd_fast(const float* grad_out, const int32_t* argmax, const float*
     if (rc) return rc;
     count_launch();
     FRR_CHECK_LAUNCH("roi_pool_bwd_fast_kernel");
+    return FRR_OK;
+}
+
+static size_t align_bwd_smem(int CB, int HW) {
+    return kHdrBytes + sizeof(AlignBwdGeo) * kAbRois + (size_t)CB * 64 * 4 + (size_t)CB * HW * 4;
+}
+
+template <int CB>
+static int launch_align_bwd(const float* go, const float* rois, int K, int B, int C, int H, int W, float scale, int aligned,
+                            int nhwc, float* gin, cudaStream_t st) {
+    auto kern = roi_align_bwd_fast_kernel<CB>;
+    FRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    kern<<<dim3((C + CB - 1) / CB, B), CB * 32, align_bwd_smem(CB, H * W), st>>>(go, rois, K, C, H, W, scale, aligned, nhwc, gin);
+    return FRR_OK;
+}
+
+int roi_align_bwd_fast(const float* grad_out, const float* rois, int K, int B, int C, int H, int W, int PH, int PW,
+                       float scale, int sampling, int aligned, int nhwc, float* grad_in, frr_stream_t stream) {
+    // every roi may touch at most kAbCols pixel columns: guaranteed when the map is no wider than that
+    if (PH != 7 || PW != 7 || sampling != 2 || W > kAbCols) return 1;
+    const int HW = H * W;
+    int cbk = 0;
+    for (int t = 16; t >= 4; t >>= 1) {
+        if (align_bwd_smem(t, HW) > kSmemLimit) continue;
+        cbk = t;
+        if ((long)B * ((C + t - 1) / t) >= (long)num_sms()) break;
+    }
+    if (cbk == 0) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rc = cbk == 16 ? launch_align_bwd<16>(grad_out, rois, K, B, C, H, W, scale, aligned, nhwc, grad_in, st)
+                 : cbk == 8  ? launch_align_bwd<8>(grad_out, rois, K, B, C, H, W, scale, aligned, nhwc, grad_in, st)
+                             : launch_align_bwd<4>(grad_out, rois, K, B, C, H, W, scale, aligned, nhwc, grad_in, st);
+    if (rc) return rc;
+    count_launch();
+    FRR_CHECK_LAUNCH("roi_align_bwd_fast_kernel");
     return FRR_OK;
 }
 
