@@ -346,6 +346,157 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------ other workloads
+def _events_ms(torch, fn, steps, sync):
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
+
+
+def run_extra(args):
+    """configs[2] (--workload train): target makers + RoIPool 7x7 fwd/bwd, batch 16 @600x1000, 128 RoIs/image;
+    configs[3] (--workload infer): COCO-shaped 800x1333 inference, 8 images/GPU: proposals (6000 -> 300), RoIPool of
+    300 RoIs, per-class decode, 80-class NMS, detections all-gathered over NCCL when N > 1.
+    Prints one JSON line in the same format (these are not the driver's default line)."""
+    import torch
+    import torch.distributed as dist
+    from faster_rcnn_pytorch_b200 import _lib, ops, region, synth, targets, dist as fdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    peak, how = peaks()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def maxms(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    rs = np.random.RandomState(9000 + rank)
+    C = 512
+    if args.workload == "train":
+        hw, B, G, per = (600, 1000), 16, 8, 128
+        fh, fw = hw[0] // 16, hw[1] // 16
+        n = synth.num_anchors(hw)
+        NR = 3   # rotated input sets: 3 x (75 MB features + 206 MB grad_out) > L2
+        feats = [torch.from_numpy(rs.standard_normal((B, C, fh, fw)).astype(np.float32)).to(dev) for _ in range(NR)]
+        gouts = [torch.from_numpy(rs.standard_normal((B * per, C, 7, 7)).astype(np.float32)).to(dev) for _ in range(NR)]
+        lg = torch.from_numpy(rs.standard_normal((B, n, 2)).astype(np.float32)).to(dev)
+        rg = torch.from_numpy((rs.standard_normal((B, n, 4)) * 0.2).astype(np.float32)).to(dev)
+        gt = torch.from_numpy(np.stack([synth.gt_boxes(3000 + 100 * rank + i, G)[0] for i in range(B)])).to(dev)
+        lab = torch.from_numpy(np.stack([synth.gt_boxes(3000 + 100 * rank + i, G)[1] for i in range(B)])).to(dev)
+        props, pcnt = region.rpn_proposals(lg, rg, image_hw=hw, mode="train")     # config-2 pipeline proposals
+        scale = torch.tensor([fw, fh, fw, fh], dtype=torch.float32, device=dev)
+        bidx = torch.arange(B, device=dev, dtype=torch.float32).repeat_interleave(per)[:, None]
+        stats = {}
+
+        def step(i):
+            torch.manual_seed(3000 + i)
+            t = targets.make_targets(gt, None, lab, props, pcnt, image_hw=hw)    # 4 kernels + ONE D2H of counts
+            rois5 = torch.cat([bidx, (t["sample_rois"] * scale).reshape(-1, 4)], dim=1)
+            out, arg = ops.roi_pool_forward(feats[i % NR], rois5)
+            gin = ops.roi_pool_backward(gouts[i % NR], arg, rois5, feats[0].shape)
+            stats["last"] = (out, gin, rois5, arg)
+            return gin
+
+        for i in range(max(args.warmup, 3)):
+            step(i)
+        sampler = ClockSampler(local) if rank == 0 else None
+        l0 = _lib.launch_count()
+        ms = maxms(_events_ms(torch, step, args.steps, sync_all))
+        launches = _lib.launch_count() - l0
+        out, gin, rois5, arg = stats["last"]
+        obytes = B * per * C * 49 * 4
+        fbytes = B * C * fh * fw * 4
+        ms_f = _events_ms(torch, lambda i: ops.roi_pool_forward(feats[i % NR], rois5), 12, sync_all) / 12
+        ms_b = _events_ms(torch, lambda i: ops.roi_pool_backward(gouts[i % NR], arg, rois5, feats[0].shape), 12, sync_all) / 12
+        ms_t = _events_ms(torch, lambda i: targets.make_targets(gt, None, lab, props, pcnt, image_hw=hw), 12, sync_all) / 12
+        clocks = sampler.stop() if sampler else None
+        if rank == 0:
+            fb = fbytes + 2 * obytes
+            print(json.dumps({
+                "metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "configs[2]: training targets (256 anchor / 128 RoI sampling, G=8) + RoIPool 7x7 fwd/bwd on "
+                                       "512-ch stride-16 features (37x62), batch 16 images/GPU, RoIs sampled from the RPN proposals",
+                           "l2": f"features/grad_out rotated over {NR} resident sets (> 126 MB L2)"},
+                "kernels_ms_per_batch": {"roi_pool_fwd": ms_f, "roi_pool_bwd": ms_b, "make_targets(4 kernels + D2H + host randperm + H2D)": ms_t},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": {"kernel": "roi_fwd_fast_kernel", "bound": "hbm", "achieved": fb / (ms_f * 1e-3) / 1e9, "peak": peak,
+                             "unit": "GB/s", "frac": fb / (ms_f * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": how,
+                             "bytes_per_launch": fb},
+                "roofline_bwd": {"kernel": "roi_pool_bwd_fast_kernel", "bound": "hbm", "achieved": fb / (ms_b * 1e-3) / 1e9,
+                                 "peak": peak, "unit": "GB/s", "frac": fb / (ms_b * 1e-3) / 1e9 / peak, "bytes_per_launch": fb},
+            }))
+    else:
+        hw, B, R, NC = (800, 1333), 8, 300, 81
+        fh, fw = hw[0] // 16, hw[1] // 16
+        n = synth.num_anchors(hw)
+        NR = 4
+        feats = [torch.from_numpy(rs.standard_normal((B, C, fh, fw)).astype(np.float32)).to(dev) for _ in range(NR)]
+        lgs = [torch.from_numpy(rs.standard_normal((B, n, 2)).astype(np.float32)).to(dev) for _ in range(NR)]
+        rgs = [torch.from_numpy((rs.standard_normal((B, n, 4)) * 0.2).astype(np.float32)).to(dev) for _ in range(NR)]
+        hcls = torch.from_numpy(rs.standard_normal((B * R, NC)).astype(np.float32)).to(dev)       # head outputs (FC head is
+        hreg = torch.from_numpy(rs.standard_normal((B * R, 4 * NC)).astype(np.float32)).to(dev)   # cuBLAS, not the product)
+        plan = region.ProposalPlan(B, n, dev, image_hw=hw, mode="test")
+        scale = torch.tensor([fw, fh, fw, fh], dtype=torch.float32, device=dev)
+        bidx = torch.arange(B, device=dev, dtype=torch.float32).repeat_interleave(R)[:, None]
+        ids = torch.arange(rank * B, (rank + 1) * B, dtype=torch.int64, device=dev)
+        keepalive = {}
+
+        def step(i):
+            rois, cnt = plan.run(lgs[i % NR], rgs[i % NR])
+            rois5 = torch.cat([bidx, (rois * scale).reshape(-1, 4)], dim=1)
+            pooled, _ = ops.roi_pool_forward(feats[i % NR], rois5, want_argmax=False)
+            prob, boxes = ops.decode_classwise(hcls, hreg, rois.reshape(-1, 4), NC)
+            db, dl, ds, dc = ops.class_nms(prob.reshape(B, R, NC), boxes.reshape(B, R, 4 * NC), NC, score_thres=0.05,
+                                           roi_count=cnt)
+            packed, pc = fdist.pack_detections(db, dl, ds, dc, 100)
+            keepalive["d"] = fdist.gather_detections(packed, pc, ids)
+            return pooled
+
+        for i in range(max(args.warmup, 3)):
+            step(i)
+        sampler = ClockSampler(local) if rank == 0 else None
+        l0 = _lib.launch_count()
+        ms = maxms(_events_ms(torch, step, args.steps, sync_all))
+        launches = _lib.launch_count() - l0
+        clocks = sampler.stop() if sampler else None
+        if rank == 0:
+            print(json.dumps({
+                "metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "configs[3]: COCO-shaped 800x1333 inference, 81 classes, 6000 -> 300 proposals, RoIPool of 300 "
+                                       "RoIs x 512 ch, 80-class NMS @0.3 (thres 0.05), 8 images/GPU, detections [8,100,6] all-gathered",
+                           "l2": f"inputs rotated over {NR} resident sets"},
+                "gpu_launches": int(launches), "clocks": clocks, "detections_gathered": int(keepalive["d"][1].sum()),
+            }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -354,11 +505,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="rpn", choices=["rpn", "train", "infer"],
+                    help="rpn = BASELINE configs[1] (the driver's line); train = configs[2]; infer = configs[3]")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    else:
+    elif args.workload == "rpn":
         run_ours(args)
+    else:
+        run_extra(args)
 
 
 if __name__ == "__main__":
