@@ -273,8 +273,8 @@ def run_ours(args):
 
     def k_nms(i):
         r = i % N_ROTATE
-        _lib.check(lib.frr_nms_sorted(t_boxes[r].data_ptr(), t_cnt[r].data_ptr(), B, PRE_K, THR, POST_K, keep.data_ptr(),
-                                      kcnt.data_ptr(), rois.data_ptr(), 0, st), "frr_nms_sorted")
+        _lib.check(lib.frr_nms_sorted_tuned(t_boxes[r].data_ptr(), t_cnt[r].data_ptr(), B, PRE_K, THR, POST_K, keep.data_ptr(),
+                                            kcnt.data_ptr(), rois.data_ptr(), 0, 0, None, 1, st), "frr_nms_sorted")
 
     def time_kernel(fn, reps):
         for i in range(N_ROTATE):
@@ -298,8 +298,8 @@ def run_ours(args):
     ms_nms1 = {}
     for cs in (8, 16):
         def k_one(i, cs=cs):
-            _lib.check(lib.frr_nms_sorted(one.data_ptr(), one_c.data_ptr(), 1, PRE_K, THR, POST_K, keep.data_ptr(),
-                                          kcnt.data_ptr(), rois.data_ptr(), cs, st), "frr_nms_sorted")
+            _lib.check(lib.frr_nms_sorted_tuned(one.data_ptr(), one_c.data_ptr(), 1, PRE_K, THR, POST_K, keep.data_ptr(),
+                                                kcnt.data_ptr(), rois.data_ptr(), cs, 0, None, 1, st), "frr_nms_sorted")
         ms_nms1[cs] = time_kernel(k_one, 50)
     clocks = sampler.stop() if sampler else None
 

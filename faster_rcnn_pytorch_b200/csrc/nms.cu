@@ -19,7 +19,7 @@
 // the smallest fp32 strictly above thr.  Almost every pair is rejected without the division by
 // a conservative 10-instruction screen:  inter/union < up  <=  inter < c2*(area_a + area_b) with
 // c2 = up/(1+up)*(1 - 2^-19)  (the 2^-19 margin covers every fp32 rounding in the screen and in
-// the exact formula, see suppress_screen()); the ~0.3 % of pairs that pass the screen take the exact
+// the exact formula, see suppress_screen<kUnit>()); the ~0.3 % of pairs that pass the screen take the exact
 // division.  Degenerate / tiny boxes carry a NaN screening area, which always fails the screen.
 #include <cooperative_groups.h>
 #include <math.h>
@@ -68,9 +68,13 @@ __device__ __noinline__ bool suppress_exact(float4 a, float4 b, float up) {
 //   screen:  T = RN(RN(c2 Aa) + RN(c2 Ab)) <= c2 (Aa+Ab)(1+2^-22), and c2 (1+2^-22) < u'/(1+u').
 // Only one of w/h is clamped: if w < 0 then I <= 0 < T (the true intersection is 0: not suppressed).
 // sa/sb are the c2-scaled areas (NaN if degenerate -> T is NaN -> the screen reports "maybe").
+// kUnit: all coordinates lie in [0,1] (RPN / detection boxes are clamped there), so |h| <= 1 and the clamp of h at 0
+// is the free .sat modifier of the subtraction (FMA pipe) instead of an FMNMX on the half-rate ALU pipe.
+template <bool kUnit>
 __device__ __forceinline__ bool suppress_screen(const float4& a, float sa, const float4& b, float sb) {
     const float w = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
-    const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
+    const float hd = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
+    const float h = kUnit ? __saturatef(hd) : fmaxf(0.f, hd);
     return !(__fmul_rn(w, h) < __fadd_rn(sa, sb));
 }
 
@@ -101,7 +105,7 @@ __device__ __forceinline__ bool bar_or(int id, int n, bool pred) {
 
 enum { DBG_CHUNKS = 0, DBG_LOAD, DBG_P1, DBG_SYNC, DBG_P2, DBG_P3, DBG_P4, DBG_P5, DBG_SURV, DBG_ITERS, DBG_N };
 
-template <int kThreads, bool kFast>
+template <int kThreads, bool kFast, bool kUnit>
 __global__ void __launch_bounds__(kThreads)
     nms_keeplist_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ counts, int n, int max_keep,
                         int slice_cap, NmsThr thr, int32_t* __restrict__ keep, int32_t* __restrict__ keep_count,
@@ -169,23 +173,26 @@ __global__ void __launch_bounds__(kThreads)
                 // Screen every kept box of the slice; remember only the FIRST one that passes the screen and
                 // evaluate it exactly after the loop (all lanes together).  The screen is tight (2^-19), so a
                 // pass is almost always a true suppression; the rare lane whose exact test fails rescans.
+                // The slice part is walked from its END so that the plain conditional move below leaves the SMALLEST
+                // passing k (one ALU op less per pair than "first hit wins").
                 int pk[kTile];
 #pragma unroll
-                for (int j = 0; j < kTile; ++j) pk[j] = has[j] ? -1 : 0;
+                for (int j = 0; j < kTile; ++j) pk[j] = -1;
+                const int cntp = (ns > part) ? (ns - part + kParts - 1) / kParts : 0;
 #pragma unroll 2
-                for (int k = part; k < ns; k += kParts) {
+                for (int k = part + (cntp - 1) * kParts; k >= part; k -= kParts) {
                     const float4 kb = kbox[k];
                     const float ka = karea[k];
 #pragma unroll
                     for (int j = 0; j < kTile; ++j)
-                        if (suppress_screen(kb, ka, cb[j], ca[j]) && pk[j] < 0) pk[j] = k;
+                        if (suppress_screen<kUnit>(kb, ka, cb[j], ca[j])) pk[j] = k;
                 }
 #pragma unroll
                 for (int j = 0; j < kTile; ++j) {
                     if (has[j] && pk[j] >= 0) {
                         sup[j] = suppress_exact(kbox[pk[j]], cb[j], thr.up);
                         for (int k2 = pk[j] + kParts; k2 < ns && !sup[j]; k2 += kParts)
-                            if (suppress_screen(kbox[k2], karea[k2], cb[j], ca[j]))
+                            if (suppress_screen<kUnit>(kbox[k2], karea[k2], cb[j], ca[j]))
                                 sup[j] = suppress_exact(kbox[k2], cb[j], thr.up);
                     }
                 }
@@ -252,8 +259,9 @@ __global__ void __launch_bounds__(kThreads)
         FRR_TICK(DBG_P2);
         if (prof) dbg[DBG_SURV] += s;
 
-        // ---- phase 3: predecessor masks among survivors: warp item = (row, 32-column word), two words
-        //      per iteration for ILP ------------------------------------------------------------------------
+        // ---- phase 3: predecessor masks among survivors.  3a: warp item = (row, 32-column word), screen only (two
+        //      words per trip for ILP); 3b: the few set bits are refined with the exact test, one (row, word) entry
+        //      per thread, so the exact path never diverges a busy warp ----------------------------------------
         for (int row = warp; row < s; row += kWarps) {
             const float4 rb = sm->sbox[row];
             const float ra = sm->sarea[row];
@@ -261,10 +269,8 @@ __global__ void __launch_bounds__(kThreads)
                 const int j0 = q * 32 + lane, j1 = j0 + 32;  // j1 <= 255
                 bool h0 = false, h1 = false;
                 if (kFast) {
-                    const bool m0 = (j0 < row) && suppress_screen(sm->sbox[j0], sm->sarea[j0], rb, ra);
-                    const bool m1 = (j1 < row) && suppress_screen(sm->sbox[j1], sm->sarea[j1], rb, ra);
-                    if (m0) h0 = suppress_exact(sm->sbox[j0], rb, thr.up);
-                    if (m1) h1 = suppress_exact(sm->sbox[j1], rb, thr.up);
+                    h0 = (j0 < row) && suppress_screen<kUnit>(sm->sbox[j0], sm->sarea[j0], rb, ra);
+                    h1 = (j1 < row) && suppress_screen<kUnit>(sm->sbox[j1], sm->sarea[j1], rb, ra);
                 } else {
                     if (j0 < row) h0 = suppress_exact(sm->sbox[j0], rb, thr.up);
                     if (j1 < row) h1 = suppress_exact(sm->sbox[j1], rb, thr.up);
@@ -274,6 +280,21 @@ __global__ void __launch_bounds__(kThreads)
                 if (lane == 0) {
                     sm->pred[row][q] = b0;
                     sm->pred[row][q + 1] = b1;
+                }
+            }
+        }
+        if (kFast) {
+            __syncthreads();
+            for (int e = tid; e < s * kChunkWords; e += kThreads) {
+                const int row = e / kChunkWords, q = e - row * kChunkWords;
+                if (q * 32 < row) {
+                    unsigned int m = sm->pred[row][q], keepm = m;
+                    while (m) {
+                        const int bit = __ffs(m) - 1;
+                        m &= m - 1;
+                        if (!suppress_exact(sm->sbox[q * 32 + bit], sm->sbox[row], thr.up)) keepm &= ~(1u << bit);
+                    }
+                    sm->pred[row][q] = keepm;
                 }
             }
         }
@@ -381,7 +402,7 @@ static size_t nms_smem_bytes(int slice_cap) {
 
 int nms_launch(const float* boxes, const int32_t* counts, int B, int n, double iou_thr, int max_keep,
                       int32_t* keep, int32_t* keep_count, float* out_boxes, int cluster_size, int threads,
-                      long long* dbg, frr_stream_t stream) {
+                      long long* dbg, int unit_boxes, frr_stream_t stream) {
     FRR_CHECK_ARG(keep && keep_count, "frr_nms_sorted: null output");
     FRR_CHECK_ARG(B >= 0 && n >= 0 && max_keep >= 0, "frr_nms_sorted: bad sizes B=%d n=%d max_keep=%d", B, n, max_keep);
     FRR_CHECK_ARG(n == 0 || (boxes && aligned16(boxes)), "frr_nms_sorted: boxes must be non-null, 16-byte aligned");
@@ -409,12 +430,15 @@ int nms_launch(const float* boxes, const int32_t* counts, int B, int n, double i
     const NmsThr thr = make_thr(iou_thr);
     using kern_t = void (*)(const float4*, const int32_t*, int, int, int, NmsThr, int32_t*, int32_t*, float4*, long long*);
     kern_t kern = nullptr;
-    if (thr.fast)
-        kern = threads == 256 ? nms_keeplist_kernel<256, true>
-                              : threads == 512 ? nms_keeplist_kernel<512, true> : nms_keeplist_kernel<1024, true>;
+    if (thr.fast && unit_boxes)
+        kern = threads == 256 ? nms_keeplist_kernel<256, true, true>
+                              : threads == 512 ? nms_keeplist_kernel<512, true, true> : nms_keeplist_kernel<1024, true, true>;
+    else if (thr.fast)
+        kern = threads == 256 ? nms_keeplist_kernel<256, true, false>
+                              : threads == 512 ? nms_keeplist_kernel<512, true, false> : nms_keeplist_kernel<1024, true, false>;
     else
-        kern = threads == 256 ? nms_keeplist_kernel<256, false>
-                              : threads == 512 ? nms_keeplist_kernel<512, false> : nms_keeplist_kernel<1024, false>;
+        kern = threads == 256 ? nms_keeplist_kernel<256, false, false>
+                              : threads == 512 ? nms_keeplist_kernel<512, false, false> : nms_keeplist_kernel<1024, false, false>;
     FRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
     if (S > 8) FRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
 
@@ -443,12 +467,12 @@ extern "C" int frr_nms_sorted(const float* boxes, const int32_t* counts, int B, 
                               int32_t* keep, int32_t* keep_count, float* out_boxes, int cluster_size,
                               frr_stream_t stream) {
     return frr::nms_launch(boxes, counts, B, n, iou_thr, max_keep, keep, keep_count, out_boxes, cluster_size, 0, nullptr,
-                           stream);
+                           0, stream);
 }
 
 extern "C" int frr_nms_sorted_tuned(const float* boxes, const int32_t* counts, int B, int n, double iou_thr, int max_keep,
                                     int32_t* keep, int32_t* keep_count, float* out_boxes, int cluster_size, int threads,
-                                    int64_t* dbg_cycles, frr_stream_t stream) {
+                                    int64_t* dbg_cycles, int unit_boxes, frr_stream_t stream) {
     return frr::nms_launch(boxes, counts, B, n, iou_thr, max_keep, keep, keep_count, out_boxes, cluster_size, threads,
-                           (long long*)dbg_cycles, stream);
+                           (long long*)dbg_cycles, unit_boxes, stream);
 }

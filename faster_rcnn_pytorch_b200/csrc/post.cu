@@ -14,7 +14,8 @@
 namespace frr {
 
 int nms_launch(const float* boxes, const int32_t* counts, int B, int n, double iou_thr, int max_keep, int32_t* keep,
-               int32_t* keep_count, float* out_boxes, int cluster_size, int threads, long long* dbg, frr_stream_t stream);
+               int32_t* keep_count, float* out_boxes, int cluster_size, int threads, long long* dbg, int unit_boxes,
+               frr_stream_t stream);
 
 // ------------------------------------------------------------------------------------------------ D1
 // one warp per roi row
@@ -207,7 +208,7 @@ int frr_class_nms(const float* prob, const float* boxes, const int32_t* roi_coun
         count_launch();
         FRR_CHECK_LAUNCH("class_sort_kernel");
         int rc = nms_launch((const float*)sboxes, counts, (int)P, R, iou_thr, R, keep, keep_count, (float*)kboxes, 1, 256,
-                            nullptr, stream);
+                            nullptr, 0, stream);
         if (rc) return rc;
     } else {
         FRR_CUDA(cudaMemsetAsync(keep_count, 0, P * 4, st));

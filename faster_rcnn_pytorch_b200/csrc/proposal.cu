@@ -5,6 +5,10 @@
 
 namespace frr {
 
+int nms_launch(const float* boxes, const int32_t* counts, int B, int n, double iou_thr, int max_keep, int32_t* keep,
+               int32_t* keep_count, float* out_boxes, int cluster_size, int threads, long long* dbg, int unit_boxes,
+               frr_stream_t stream);
+
 struct ProposalWs {
     size_t boxes, scores, valid, top_boxes, top_idx, top_count, keep, total;
 };
@@ -69,7 +73,8 @@ int frr_rpn_proposals(const float* reg, const float* cls, int cls_is_logits, con
     }
     rc = frr_topk_desc(scores, valid, boxes, B, N, k, nullptr, top_idx, nullptr, top_boxes, top_count, stream);
     if (rc) return rc;
-    return frr_nms_sorted(top_boxes, top_count, B, k, iou_thr, post_nms_top_k, keep, roi_count, rois, 0, stream);
+    // the decoded boxes are clamped to [0,1] (models/model.py:34): unit-range screening
+    return nms_launch(top_boxes, top_count, B, k, iou_thr, post_nms_top_k, keep, roi_count, rois, 0, 0, nullptr, 1, stream);
 }
 
 }  // extern "C"

@@ -115,9 +115,10 @@ def topk_desc(scores, k: int, valid=None, boxes=None, want_cidx: bool = False):
 
 
 def nms_sorted(boxes, iou_threshold: float, max_keep: int | None = None, counts=None, gather: bool = True,
-               cluster_size: int = 0, threads: int = 0, dbg=None):
+               cluster_size: int = 0, threads: int = 0, dbg=None, unit_boxes: bool = False):
     """N1 on score-sorted boxes [B,n,4].  Returns keep int32 [B,max_keep] (-1 padded), count int32 [B],
-    rois [B,max_keep,4] (zero padded) or None."""
+    rois [B,max_keep,4] (zero padded) or None.  ``unit_boxes``: the caller guarantees coordinates in [0,1]
+    (enables a cheaper, result-identical screening test)."""
     lib = _lib.load()
     boxes = _req(boxes, "boxes")
     if boxes.dim() != 3 or boxes.shape[-1] != 4:
@@ -133,7 +134,7 @@ def nms_sorted(boxes, iou_threshold: float, max_keep: int | None = None, counts=
         rois = torch.empty((B, mk, 4), dtype=torch.float32, device=dev) if gather else None
         _lib.check(lib.frr_nms_sorted_tuned(boxes.data_ptr(), _ptr(counts), B, n, float(iou_threshold), mk,
                                             keep.data_ptr(), cnt.data_ptr(), _ptr(rois), int(cluster_size), int(threads),
-                                            _ptr(dbg), _stream()), "frr_nms_sorted")
+                                            _ptr(dbg), int(bool(unit_boxes)), _stream()), "frr_nms_sorted")
     return keep, cnt, rois
 
 

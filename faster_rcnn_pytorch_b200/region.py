@@ -32,7 +32,7 @@ def rpn_proposals(cls, reg, image_hw=None, mode: str = "train", anchors=None, st
     k = min(pre_k, boxes.shape[1])
     top = ops.topk_desc(scores, k, valid=valid, boxes=boxes, want_cidx=return_all)
     keep, count, rois = ops.nms_sorted(top["boxes"], nms_thresh, max_keep=post_k, counts=top["count"],
-                                       cluster_size=cluster_size)
+                                       cluster_size=cluster_size, unit_boxes=True)   # decode clamps to [0,1]
     if return_all:
         return dict(rois=rois, count=count, keep=keep, topk=top, boxes=boxes, scores=scores, valid=valid)
     return rois, count

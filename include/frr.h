@@ -97,10 +97,12 @@ int frr_nms_sorted(const float* boxes /* [B,n,4] */, const int32_t* counts /* [B
                    int cluster_size, frr_stream_t stream);
 /* Same, with tuning / profiling knobs: threads per CTA (0 = auto, 256, 512 or 1024); dbg_cycles = NULL
  * or int64[16] accumulating per-phase clock64() cycles of CTA 0 (slots: chunks, load, phase1, cluster
- * sync, phase2..5, survivors, fix-point rounds).                                                  */
+ * sync, phase2..5, survivors, fix-point rounds); unit_boxes != 0 = the caller guarantees every coordinate
+ * lies in [0,1] (true for the clamped RPN / detection boxes of models/model.py:34,378), which enables a
+ * cheaper screening test; results are identical.                                                    */
 int frr_nms_sorted_tuned(const float* boxes, const int32_t* counts, int B, int n, double iou_thr, int max_keep,
                          int32_t* keep, int32_t* keep_count, float* out_boxes, int cluster_size, int threads,
-                         int64_t* dbg_cycles, frr_stream_t stream);
+                         int64_t* dbg_cycles, int unit_boxes, frr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * RegionProposal.forward for a batch in one call -- models/model.py:17-58 (P1-P4 + N1 chained: the three

@@ -273,3 +273,16 @@ def test_proposal_plan_and_host_pipeline_match_stagewise_ops(oracle):
             assert torch.equal(hr, wr) and torch.equal(hc, wc)
     with pytest.raises(ValueError):
         plan.run(torch.zeros(B, n, 2), torch.zeros(B, n, 4))
+
+
+def test_nms_unit_range_screen_gives_identical_keep_lists(oracle):
+    """unit_boxes=True (coordinates in [0,1]: cheaper screening test) must not change any result."""
+    for seed, n, thr in [(104, 12000, 0.7), (103, 3000, 0.3), (400, 1500, 0.5)]:
+        b, _, _ = _sorted_boxes(seed, n)
+        if seed == 400:
+            b[::7, 2] = b[::7, 0]; b[::11, [0, 2]] = b[::11, [2, 0]]; b[5] = b[4]
+        k0, c0, r0 = ops.nms_sorted(dev(b[None]), thr, max_keep=2000)
+        k1, c1, r1 = ops.nms_sorted(dev(b[None]), thr, max_keep=2000, unit_boxes=True)
+        assert torch.equal(k0, k1) and torch.equal(c0, c1) and torch.equal(r0, r1)
+        want = oracle.nms(b, -np.arange(n, dtype=np.float32), thr)[:2000]
+        assert np.array_equal(k1[0, :int(c1[0])].cpu().numpy(), want)

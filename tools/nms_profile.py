@@ -19,18 +19,18 @@ names = ["chunks", "load", "p1", "sync", "p2", "p3", "p4", "p5", "surv", "iters"
 def run(bx, cnt, S, threads, reps=20, dbg=False):
     d = torch.zeros(16, dtype=torch.int64, device=dev) if dbg else None
     for _ in range(3):
-        ops.nms_sorted(bx, 0.7, max_keep=2000, counts=cnt, cluster_size=S, threads=threads)
+        ops.nms_sorted(bx, 0.7, max_keep=2000, counts=cnt, cluster_size=S, threads=threads, unit_boxes=True)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        ops.nms_sorted(bx, 0.7, max_keep=2000, counts=cnt, cluster_size=S, threads=threads)
+        ops.nms_sorted(bx, 0.7, max_keep=2000, counts=cnt, cluster_size=S, threads=threads, unit_boxes=True)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     out = {"B": bx.shape[0], "S": S, "threads": threads, "us": round(ms * 1e3, 1)}
     if dbg:
-        keep, c, _ = ops.nms_sorted(bx, 0.7, max_keep=2000, counts=cnt, cluster_size=S, threads=threads, dbg=d)
+        keep, c, _ = ops.nms_sorted(bx, 0.7, max_keep=2000, counts=cnt, cluster_size=S, threads=threads, dbg=d, unit_boxes=True)
         torch.cuda.synchronize()
         out.update({k: int(v) for k, v in zip(names, d.cpu().tolist())})
         out["kept"] = int(c[0])
