@@ -39,8 +39,12 @@ constexpr int kGroup = kChunk / kTile;  // threads that together cover one chunk
 struct NmsThr {
     float up;  // smallest fp32 with (double)up > thr
     float c2;  // up/(1+up) * (1 - 2^-19): screening constant
+    float fy;  // a box of height h can only be suppressed by boxes whose y-centre is within fy * h of its own
     int fast;  // screening usable (1e-6 <= thr, finite)
 };
+
+constexpr int kStrips = 64;         // y-strips of the sorted kept slice; strip kStrips = boxes that must always be tested
+constexpr int kGroupCands = 4;      // candidates per warp pass in the sorted phase 1
 
 __device__ __forceinline__ float box_area(const float4& b) {
     return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
@@ -90,7 +94,22 @@ struct NmsSmem {
     float4 sbox[kChunk];  // survivor boxes (compacted)
     float sarea[kChunk];
     short ssrc[kChunk];  // survivor -> position inside the chunk
+    // sorted phase 1 (kUnit): kept slice bucketed by y-strip, chunk candidates ordered by y-strip
+    unsigned int shist[kStrips + 2];
+    unsigned int scursor[kStrips + 2];
+    unsigned int chist[kStrips + 2];
+    unsigned int ccursor[kStrips + 2];
+    unsigned short sstart[kStrips + 2];  // sstart[s] = first sorted position of strip s; [kStrips+1] = total
+    unsigned char cord[kChunk];          // chunk positions ordered by y-strip
 };
+
+// y-strip of a box: monotone in the y-centre; boxes without a usable screening area (degenerate / malformed, NaN sa)
+// go to the extra strip kStrips and are tested against everything
+__device__ __forceinline__ int strip_of_y(float y) { return min(kStrips - 1, max(0, (int)(y * (float)kStrips))); }
+// (strips run along x: detection images are usually landscape, so boxes are narrower relative to the x-extent)
+__device__ __forceinline__ int strip_of(const float4& b, float sa) {
+    return (sa != sa) ? kStrips : strip_of_y(0.5f * (b.x + b.z));
+}
 
 // barrier over the first `n` threads of the CTA with an OR reduction of `pred`
 __device__ __forceinline__ bool bar_or(int id, int n, bool pred) {
@@ -105,7 +124,7 @@ __device__ __forceinline__ bool bar_or(int id, int n, bool pred) {
 
 enum { DBG_CHUNKS = 0, DBG_LOAD, DBG_P1, DBG_SYNC, DBG_P2, DBG_P3, DBG_P4, DBG_P5, DBG_SURV, DBG_ITERS, DBG_N };
 
-template <int kThreads, bool kFast, bool kUnit>
+template <int kThreads, bool kFast, bool kUnit, bool kSort>
 __global__ void __launch_bounds__(kThreads)
     nms_keeplist_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ counts, int n, int max_keep,
                         int slice_cap, NmsThr thr, int32_t* __restrict__ keep, int32_t* __restrict__ keep_count,
@@ -125,6 +144,12 @@ __global__ void __launch_bounds__(kThreads)
     NmsSmem* sm = reinterpret_cast<NmsSmem*>(smem_raw);
     float4* kbox = reinterpret_cast<float4*>(smem_raw + ((sizeof(NmsSmem) + 15) & ~(size_t)15));  // [slice_cap]
     float* karea = reinterpret_cast<float*>(kbox + slice_cap);                                      // [slice_cap]
+    // kUnit: second buffer for the per-chunk re-bucketing of the slice (layout: boxA | boxB | areaA | areaB)
+    constexpr bool kSorted = kFast && kUnit && kSort;
+    float4* kbox_alt = kbox + slice_cap;
+    if (kSorted) karea = reinterpret_cast<float*>(kbox + 2 * slice_cap);
+    float* karea_alt = karea + slice_cap;
+    int ns_sorted = 0;  // slice entries already bucketed in the current buffer
 
     const int cnt = counts ? min(counts[img], n) : n;
     const float4* ib = boxes + (size_t)img * n;
@@ -144,6 +169,7 @@ __global__ void __launch_bounds__(kThreads)
     float4 nbx = make_float4(0.f, 0.f, 0.f, 0.f);  // prefetched candidate of the next chunk (first kChunk threads)
     if (tid < kChunk && tid < cnt) nbx = ib[tid];
     if (tid < 2 * kChunkWords) (&sm->acc[0][0])[tid] = 0u;
+    if (kSorted && tid < kStrips + 2) sm->sstart[tid] = 0;
     for (int base = 0; base < cnt && nk < max_keep; base += kChunk, par ^= 1) {
         if (prof) { t0 = clock64(); dbg[DBG_CHUNKS] += 1; }
         // ---- phase 0: stage the chunk's candidates in shared memory, prefetch the next chunk ----------
@@ -156,8 +182,142 @@ __global__ void __launch_bounds__(kThreads)
         __syncthreads();
         FRR_TICK(DBG_LOAD);
 
-        // ---- phase 1: 4 candidates per thread vs this CTA's slice of the kept list ----------------------
         const int ns = (nk - rank + S - 1) / S;  // kept ordinals o with o % S == rank
+        if (kSorted) {
+            // ---- phase 1 (sorted): the slice is bucketed by x-strip, the chunk's candidates are ordered by x-strip;
+            //      a warp takes 4 x-adjacent candidates (warp-uniform registers) and its LANES walk only the kept
+            //      boxes whose strip can reach them: |cx_K - cx_c| <= fy * w_c is necessary for IoU >= thr (the
+            //      bound is the same in x and y), so everything outside that x-range is skipped exactly.
+            // (a) re-bucket the slice when boxes were appended by the previous chunk (counting sort into the other
+            //     buffer) and (b) order the chunk's candidates by y-strip (counting sort of <= 256 positions; positions
+            //     past the end of the list are marked suppressed right away) -- the two sorts share their barriers
+            const bool resort = ns > ns_sorted;
+            if (tid < kStrips + 2) { sm->shist[tid] = 0u; sm->chist[tid] = 0u; }
+            __syncthreads();
+            if (resort)
+                for (int i = tid; i < ns; i += kThreads) atomicAdd(&sm->shist[strip_of(kbox[i], karea[i])], 1u);
+            int cst = kStrips + 1;
+            if (tid < kChunk) {
+                if (base + tid < cnt) cst = strip_of(sm->cbox[tid], sm->carea[tid]);
+                else atomicOr(&sm->acc[par][tid >> 5], 1u << (tid & 31));
+                atomicAdd(&sm->chist[cst], 1u);
+            }
+            __syncthreads();
+            if (warp < 2 && (warp == 1 || resort)) {  // warp 0: slice strips, warp 1: candidate strips (3 counts per lane)
+                unsigned int* hist = warp == 0 ? sm->shist : sm->chist;
+                unsigned int* cursor = warp == 0 ? sm->scursor : sm->ccursor;
+                unsigned int c3[3], t3 = 0;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const int e = lane * 3 + q;
+                    c3[q] = (e <= kStrips + 1) ? hist[e] : 0u;
+                    t3 += c3[q];
+                }
+                unsigned int inc = t3;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                unsigned int run = inc - t3;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const int e = lane * 3 + q;
+                    if (e <= kStrips + 1) {
+                        cursor[e] = run;
+                        if (warp == 0) sm->sstart[e] = (unsigned short)run;
+                    }
+                    run += c3[q];
+                }
+            }
+            __syncthreads();
+            if (resort) {
+                for (int i = tid; i < ns; i += kThreads) {
+                    const float4 b = kbox[i];
+                    const float a = karea[i];
+                    const unsigned int pos = atomicAdd(&sm->scursor[strip_of(b, a)], 1u);
+                    kbox_alt[pos] = b;
+                    karea_alt[pos] = a;
+                }
+                float4* tb = kbox; kbox = kbox_alt; kbox_alt = tb;
+                float* ta = karea; karea = karea_alt; karea_alt = ta;
+                ns_sorted = ns;
+            }
+            if (tid < kChunk) sm->cord[atomicAdd(&sm->ccursor[cst], 1u)] = (unsigned char)tid;
+            __syncthreads();
+            FRR_TICK(10);  // bucketing time (reported separately, not part of the phase-1 slot)
+            // (c) groups of 4 y-adjacent candidates
+            const int sp_lo = sm->sstart[kStrips], sp_hi = sm->sstart[kStrips + 1];  // always-tested boxes
+            for (int g = warp; g < kChunk / kGroupCands; g += kWarps) {
+                float4 cb[kGroupCands];
+                float ca[kGroupCands];
+                int cpos[kGroupCands];
+                bool has[kGroupCands];
+                bool all_range = false;
+                float ylo = 3.0e38f, yhi = -3.0e38f;
+                bool any = false;
+#pragma unroll
+                for (int j = 0; j < kGroupCands; ++j) {
+                    cpos[j] = sm->cord[g * kGroupCands + j];
+                    cb[j] = sm->cbox[cpos[j]];
+                    ca[j] = sm->carea[cpos[j]];
+                    has[j] = base + cpos[j] < cnt;
+                    if (has[j]) {
+                        any = true;
+                        if (ca[j] != ca[j]) {
+                            all_range = true;  // no usable screening area: test against the whole slice
+                        } else {
+                            const float cy = 0.5f * (cb[j].x + cb[j].z);
+                            const float r = thr.fy * (cb[j].z - cb[j].x) * 1.0001f + 2.0e-6f;
+                            ylo = fminf(ylo, cy - r);
+                            yhi = fmaxf(yhi, cy + r);
+                        }
+                    }
+                }
+                if (!any) continue;  // warp-uniform
+                int lo = 0, hi = ns;
+                if (!all_range) {
+                    lo = sm->sstart[strip_of_y(ylo)];
+                    hi = sm->sstart[strip_of_y(yhi) + 1];
+                }
+                // two segments: the y-range and (unless already covered) the always-tested strip
+                int pk[kGroupCands];
+#pragma unroll
+                for (int j = 0; j < kGroupCands; ++j) pk[j] = -1;
+#pragma unroll 1
+                for (int seg = 0; seg < 2; ++seg) {
+                    const int a0 = seg == 0 ? lo : (all_range ? 0 : sp_lo);
+                    const int a1 = seg == 0 ? hi : (all_range ? 0 : sp_hi);
+                    const int trips = (a1 - a0 + 31) >> 5;
+                    // walked from the end: the plain conditional move leaves the smallest passing k
+                    for (int k = a0 + lane + (trips - 1) * 32; k >= a0; k -= 32) {
+                        if (k < a1) {
+                            const float4 kb = kbox[k];
+                            const float ka = karea[k];
+#pragma unroll
+                            for (int j = 0; j < kGroupCands; ++j)
+                                if (suppress_screen<true>(kb, ka, cb[j], ca[j])) pk[j] = k;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < kGroupCands; ++j) {
+                    if (!has[j]) continue;  // warp-uniform
+                    bool r = false;
+                    if (pk[j] >= 0) r = suppress_exact(kbox[pk[j]], cb[j], thr.up);
+                    bool sup = __any_sync(0xffffffffu, r);
+                    if (!sup && __any_sync(0xffffffffu, pk[j] >= 0)) {
+                        // a screen hit was not confirmed by the exact test (rare): exact walk of both segments
+                        for (int k = lo + lane; k < hi; k += 32) r = r || suppress_exact(kbox[k], cb[j], thr.up);
+                        if (!all_range)
+                            for (int k = sp_lo + lane; k < sp_hi; k += 32) r = r || suppress_exact(kbox[k], cb[j], thr.up);
+                        sup = __any_sync(0xffffffffu, r);
+                    }
+                    if (sup && lane == 0) atomicOr(&sm->acc[par][cpos[j] >> 5], 1u << (cpos[j] & 31));
+                }
+            }
+        } else {
+        // ---- phase 1: 4 candidates per thread vs this CTA's slice of the kept list ----------------------
         {
             float4 cb[kTile];
             float ca[kTile];
@@ -207,6 +367,7 @@ __global__ void __launch_bounds__(kThreads)
                 const unsigned int wj = __ballot_sync(0xffffffffu, sup[j]);
                 if (lane == 0 && wj != 0u) atomicOr(&sm->acc[par][(warp & 1) + 2 * j], wj);
             }
+        }
         }
         __syncthreads();
         // publish this CTA's 8 words to every CTA of the cluster (distributed shared memory)
@@ -393,11 +554,15 @@ static NmsThr make_thr(double thr) {
     t.fast = (thr >= 1.0e-6) && isfinite(thr) && (t.up < 1.0e30f) ? 1 : 0;
     const double u = (double)t.up;
     t.c2 = t.fast ? (float)(u / (1.0 + u) * (1.0 - 1.9073486328125e-06)) : 0.f;
+    // IoU >= thr needs |cy_a - cy_b| <= max(1 - thr, (1 - thr) / (2 thr)) * h of EITHER box; thr is
+    // lowered by 2^-18 relative to cover the fp32 rounding of the exact IoU
+    const double tl = thr * (1.0 - 3.814697265625e-06);
+    t.fy = t.fast ? (float)(fmax(1.0 - tl, (1.0 - tl) / (2.0 * tl)) * (1.0 + 1.0e-6)) : 0.f;
     return t;
 }
 
-static size_t nms_smem_bytes(int slice_cap) {
-    return ((sizeof(NmsSmem) + 15) & ~(size_t)15) + (size_t)slice_cap * (sizeof(float4) + sizeof(float));
+static size_t nms_smem_bytes(int slice_cap, bool sorted) {
+    return ((sizeof(NmsSmem) + 15) & ~(size_t)15) + (size_t)slice_cap * (sizeof(float4) + sizeof(float)) * (sorted ? 2 : 1);
 }
 
 int nms_launch(const float* boxes, const int32_t* counts, int B, int n, double iou_thr, int max_keep,
@@ -413,32 +578,34 @@ int nms_launch(const float* boxes, const int32_t* counts, int B, int n, double i
     const int kcap = max_keep < n ? max_keep : n;  // most boxes that can ever be kept
     int S = cluster_size;
     if (S == 0) {
-        // auto: fill the machine.  148 SMs / B images, rounded down to a power of two, capped at 8 (portable).
+        // auto: fill the machine.  148 SMs / B images, rounded down to a power of two, capped at 16.
         int per = num_sms() / (B > 0 ? B : 1);
         S = 1;
-        while (S * 2 <= per && S < 8) S *= 2;
+        while (S * 2 <= per && S < 16) S *= 2;
     }
     FRR_CHECK_ARG(S == 1 || S == 2 || S == 4 || S == 8 || S == 16, "frr_nms_sorted: cluster_size %d not in {1,2,4,8,16}", S);
     if (threads == 0) threads = 1024;
     // grow the cluster until a slice of the kept list fits in shared memory
+    const NmsThr thr = make_thr(iou_thr);
+    // The y-strip sorted phase 1 pays ~10 k cycles of bucketing per chunk: it wins once a CTA's slice of the kept
+    // list is large (batched launches with 1-2 CTAs per image), not for a single image spread over 16 CTAs.
+    const bool sorted = thr.fast && unit_boxes && (kcap / S >= 384);
     const size_t limit = 227 * 1024;
-    while (nms_smem_bytes((kcap + S - 1) / S + 1) > limit && S < 16) S *= 2;
+    while (nms_smem_bytes((kcap + S - 1) / S + 1, sorted) > limit && S < 16) S *= 2;
     const int slice_cap = (kcap + S - 1) / S + 1;
-    const size_t smem = nms_smem_bytes(slice_cap);
+    const size_t smem = nms_smem_bytes(slice_cap, sorted);
     FRR_CHECK_ARG(smem <= limit, "frr_nms_sorted: max_keep=%d does not fit the kept list in shared memory", max_keep);
 
-    const NmsThr thr = make_thr(iou_thr);
     using kern_t = void (*)(const float4*, const int32_t*, int, int, int, NmsThr, int32_t*, int32_t*, float4*, long long*);
     kern_t kern = nullptr;
-    if (thr.fast && unit_boxes)
-        kern = threads == 256 ? nms_keeplist_kernel<256, true, true>
-                              : threads == 512 ? nms_keeplist_kernel<512, true, true> : nms_keeplist_kernel<1024, true, true>;
-    else if (thr.fast)
-        kern = threads == 256 ? nms_keeplist_kernel<256, true, false>
-                              : threads == 512 ? nms_keeplist_kernel<512, true, false> : nms_keeplist_kernel<1024, true, false>;
-    else
-        kern = threads == 256 ? nms_keeplist_kernel<256, false, false>
-                              : threads == 512 ? nms_keeplist_kernel<512, false, false> : nms_keeplist_kernel<1024, false, false>;
+#define FRR_NMS_PICK(F, U, SO)                                                                      \
+    (threads == 256 ? nms_keeplist_kernel<256, F, U, SO>                                               \
+                    : threads == 512 ? nms_keeplist_kernel<512, F, U, SO> : nms_keeplist_kernel<1024, F, U, SO>)
+    if (sorted) kern = FRR_NMS_PICK(true, true, true);
+    else if (thr.fast && unit_boxes) kern = FRR_NMS_PICK(true, true, false);
+    else if (thr.fast) kern = FRR_NMS_PICK(true, false, false);
+    else kern = FRR_NMS_PICK(false, false, false);
+#undef FRR_NMS_PICK
     FRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
     if (S > 8) FRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
 

@@ -13,7 +13,7 @@ sc = torch.from_numpy(np.stack([x[2] for x in ins])).to(dev)
 boxes, scores, valid = ops.rpn_decode(reg, sc, image_hw=HW)
 top = ops.topk_desc(scores, 12000, valid=valid, boxes=boxes)
 tb, tc = top["boxes"], top["count"]
-names = ["chunks", "load", "p1", "sync", "p2", "p3", "p4", "p5", "surv", "iters"]
+names = ["chunks", "load", "p1", "sync", "p2", "p3", "p4", "p5", "surv", "iters", "bucket"]
 
 
 def run(bx, cnt, S, threads, reps=20, dbg=False):
@@ -38,10 +38,10 @@ def run(bx, cnt, S, threads, reps=20, dbg=False):
     print(json.dumps(out), flush=True)
 
 
-for threads in (256, 512, 1024):
+for threads in (512, 1024):
     for S in (1, 2):
         run(tb, tc, S, threads, dbg=True)
 one, onec = tb[:1].contiguous(), tc[:1].contiguous()
-for threads in (256, 512, 1024):
+for threads in (512, 1024):
     for S in (4, 8, 16):
         run(one, onec, S, threads, reps=50, dbg=True)
