@@ -25,17 +25,20 @@ struct RsHdr {
     unsigned int prefix_key;
     unsigned int remaining;
     unsigned int nvalid;
-    unsigned int pad;
+    unsigned int bsize;    // keys in the bucket chosen by the last select pass
+    unsigned int lcount;   // candidate list fill
+    unsigned int pad[3];
 };
 
 struct RsLayout {
     size_t vbits, gpre, epre, vpre, whist, keyA, idxA, area2, total;
     int staged;
+    int db;  // digit bits of the sort passes (5 when the 2^db x 1024 u16 counters fit, else 4)
 };
 
 static inline size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-static RsLayout rs_layout(int N, int kcap, int nchunks, bool want_stage) {
+static RsLayout rs_layout(int N, int kcap, int nchunks, bool want_stage, int db) {
     RsLayout L;
     size_t o = up16(sizeof(RsHdr));
     L.vbits = o; o += 4 * (size_t)nchunks;
@@ -43,7 +46,8 @@ static RsLayout rs_layout(int N, int kcap, int nchunks, bool want_stage) {
     L.epre = o;  o += 4 * (size_t)nchunks;
     L.vpre = o;  o += 4 * (size_t)nchunks;
     o = up16(o);
-    L.whist = o; o += (size_t)kRsWarps * 256 * 2;
+    L.whist = o; o += ((size_t)1 << db) * kRsThreads * 2;  // counters [digit][thread] u16
+    L.db = db;
     L.keyA = o;  o += 4 * (size_t)kcap;
     L.idxA = o;  o += 2 * (size_t)kcap;
     o = up16(o);
@@ -149,15 +153,30 @@ __global__ void __launch_bounds__(kRsThreads, 1)
 
     if (keff > 0) {
         // ---- 1. radix select ----------------------------------------------------------------------------
+        // After the first pass only the keys of the threshold bucket matter: they are collected once into a
+        // candidate list (scratch in keyA, unordered) and the remaining passes walk the list instead of all N keys.
         unsigned int prefix = 0, pmask = 0;
+        unsigned int* lst = keyA;
+        int ln = -1;  // < 0: walk all keys
         for (int shift = 24; shift >= 0; shift -= 8) {
-            for (int c = warp; c < nchunks; c += kRsWarps) {
-                const bool ok = (vbits[c] >> lane) & 1u;
-                const unsigned int key = ok ? key_at(c * 32 + lane) : 0u;
-                const bool in = ok && ((key & pmask) == prefix);
-                const unsigned int d = (key >> shift) & 255u;
-                const unsigned int m = match_digit8(d, in);
-                if (in && lane == __ffs(m) - 1) atomicAdd(&hd->hist[d], (unsigned int)__popc(m));
+            if (ln < 0) {
+                for (int c = warp; c < nchunks; c += kRsWarps) {
+                    const bool ok = (vbits[c] >> lane) & 1u;
+                    const unsigned int key = ok ? key_at(c * 32 + lane) : 0u;
+                    const bool in = ok && ((key & pmask) == prefix);
+                    const unsigned int d = (key >> shift) & 255u;
+                    const unsigned int m = match_digit8(d, in);
+                    if (in && lane == __ffs(m) - 1) atomicAdd(&hd->hist[d], (unsigned int)__popc(m));
+                }
+            } else {
+                for (int i0 = warp * 32; i0 < ln; i0 += kRsThreads) {
+                    const int i = i0 + lane;
+                    const unsigned int key = (i < ln) ? lst[i] : 0u;
+                    const bool in = (i < ln) && ((key & pmask) == prefix);
+                    const unsigned int d = (key >> shift) & 255u;
+                    const unsigned int m = match_digit8(d, in);
+                    if (in && lane == __ffs(m) - 1) atomicAdd(&hd->hist[d], (unsigned int)__popc(m));
+                }
             }
             __syncthreads();
             if (warp == 0) {  // walk digits from 255 down: the bucket where the cumulative count reaches `remaining`
@@ -178,6 +197,7 @@ __global__ void __launch_bounds__(kRsThreads, 1)
                         if (before < need && before + cnt[j] >= need) {
                             hd->prefix_key = prefix | ((unsigned int)(255 - (lane * 8 + j)) << shift);
                             hd->remaining = need - before;
+                            hd->bsize = cnt[j];
                             before = need;
                         } else {
                             before += cnt[j];
@@ -189,8 +209,24 @@ __global__ void __launch_bounds__(kRsThreads, 1)
             prefix = hd->prefix_key;
             pmask |= (255u << shift);
             if (tid < 256) hd->hist[tid] = 0;
+            if (tid == 0) hd->lcount = 0u;
             __syncthreads();
+            if (ln < 0 && shift > 0 && (int)hd->bsize <= kcap) {  // collect the threshold bucket (uniform branch)
+                for (int c = warp; c < nchunks; c += kRsWarps) {
+                    const bool ok = (vbits[c] >> lane) & 1u;
+                    const unsigned int key = ok ? key_at(c * 32 + lane) : 0u;
+                    const bool in = ok && ((key & pmask) == prefix);
+                    const unsigned int m = __ballot_sync(0xffffffffu, in);
+                    unsigned int basepos = 0;
+                    if (lane == 0 && m) basepos = atomicAdd(&hd->lcount, (unsigned int)__popc(m));
+                    basepos = __shfl_sync(0xffffffffu, basepos, 0);
+                    if (in) lst[basepos + __popc(m & lt)] = key;
+                }
+                __syncthreads();
+                ln = (int)hd->lcount;
+            }
         }
+        __syncthreads();  // the list (keyA) is dead from here on
         const unsigned int T = prefix;
         const unsigned int take_ties = hd->remaining;
         RS_TICK(1);
@@ -235,60 +271,90 @@ __global__ void __launch_bounds__(kRsThreads, 1)
 
         RS_TICK(2);
         // ---- 3. stable LSD radix sort of keyA/idxA[0..keff) --------------------------------------------------
-        const int rows = (keff + 31) >> 5;
-        const int rpw = (rows + kRsWarps - 1) / kRsWarps;
-        const int r0 = min(warp * rpw, rows), r1 = min(r0 + rpw, rows);
-        unsigned short* wh = whist + warp * 256;
+        // Thread t owns the `ipt` consecutive pairs [t*ipt, (t+1)*ipt) (ipt odd: conflict-free strided LDS) and a PRIVATE
+        // u16 counter per digit, cnt[d][t]: counting and ranking are plain LDS / STS (no ballots, no atomics; the
+        // ballot-ranked version spent 60 ALU-pipe instructions per 32 keys and pass).  The exclusive scan over
+        // cnt in (digit, thread) order gives every thread its scatter cursor per digit; walking the pairs in order
+        // keeps the sort stable.  Only the bits that differ between the selected keys are sorted.
+        unsigned int* cnt32 = reinterpret_cast<unsigned int*>(whist);
+        const int DB = L.db, ND = 1 << DB;
+        const int ipt = ((keff + kRsThreads - 1) / kRsThreads) | 1;
+        const int i0 = tid * ipt, i1 = min(i0 + ipt, keff);
+        unsigned int orv = 0u, andv = 0xffffffffu;
+        for (int i = i0; i < i1; ++i) { const unsigned int kk = keyA[i]; orv |= kk; andv &= kk; }
+        orv = __reduce_or_sync(0xffffffffu, orv);
+        andv = __reduce_and_sync(0xffffffffu, andv);
+        if (lane == 0) { hd->warp_tmp[warp] = orv; hd->hist[warp] = andv; }
+        __syncthreads();
+        orv = hd->warp_tmp[lane]; andv = hd->hist[lane];
+        orv = __reduce_or_sync(0xffffffffu, orv);
+        andv = __reduce_and_sync(0xffffffffu, andv);
+        __syncthreads();
+        const unsigned int vary = orv ^ andv;
+        const int lowbit = vary ? (__ffs(vary) - 1) : 0;
+        const int nbits = vary ? (32 - __clz(vary) - lowbit) : 0;
+        const int npass = (nbits + DB - 1) / DB;
         unsigned int* srcK = keyA;
         unsigned short* srcI = idxA;
         unsigned int* dstK = keyB;
         unsigned short* dstI = idxB;
-        for (int shift = 0; shift < 32; shift += 8) {
-            for (int i = tid; i < kRsWarps * 256 / 2; i += kRsThreads) reinterpret_cast<unsigned int*>(whist)[i] = 0u;
+        unsigned short* mycnt = whist + tid;  // cnt[d][tid] = mycnt[d * kRsThreads]
+        for (int pass = 0; pass < npass; ++pass) {
+            const int shift = lowbit + pass * DB;
+            for (int i = tid; i < ND * kRsThreads / 2; i += kRsThreads) cnt32[i] = 0u;
             __syncthreads();
-            for (int r = r0; r < r1; ++r) {
-                const int i = r * 32 + lane;
-                const bool act = i < keff;
-                const unsigned int d = act ? ((srcK[i] >> shift) & 255u) : 0u;
-                const unsigned int m = match_digit8(d, act);
-                if (act && lane == __ffs(m) - 1) wh[d] = (unsigned short)(wh[d] + __popc(m));
-                __syncwarp();
+            for (int i = i0; i < i1; ++i) {
+                const unsigned int d = (srcK[i] >> shift) & (unsigned int)(ND - 1);
+                mycnt[d * kRsThreads] = (unsigned short)(mycnt[d * kRsThreads] + 1);
             }
             __syncthreads();
-            {   // exclusive scan in (digit, warp) order: thread t owns digit t>>2, warps (t&3)*8 .. +8
-                const int d = tid >> 2, w0 = (tid & 3) * 8;
-                unsigned int c8[8], s = 0;
+            // scan in (digit, thread) order: warp d walks row d of cnt (1024 threads) in 32 coalesced steps with a
+            // running warp scan (conflict-free, unlike a per-thread walk of 2^DB strided counters); then the digit bases
+            if (warp < ND) {
+                unsigned short* row = whist + warp * kRsThreads;
+                unsigned int run = 0;
+                for (int st = 0; st < kRsThreads / 32; ++st) {
+                    const unsigned int v = row[st * 32 + lane];
+                    unsigned int inc = v;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { c8[j] = whist[(w0 + j) * 256 + d]; s += c8[j]; }
-                unsigned int tot;
-                unsigned int run = block_exclusive_scan(s, hd->warp_tmp, &tot);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { whist[(w0 + j) * 256 + d] = (unsigned short)run; run += c8[j]; }
-            }
-            __syncthreads();
-            for (int r = r0; r < r1; ++r) {
-                const int i = r * 32 + lane;
-                const bool act = i < keff;
-                const unsigned int key = act ? srcK[i] : 0u;
-                const unsigned short id = act ? srcI[i] : (unsigned short)0;
-                const unsigned int d = (key >> shift) & 255u;
-                const unsigned int m = match_digit8(d, act);
-                unsigned int base = 0;
-                if (act) base = wh[d];
-                __syncwarp();
-                if (act) {
-                    if (lane == __ffs(m) - 1) wh[d] = (unsigned short)(base + __popc(m));
-                    const unsigned int pos = base + __popc(m & lt);
-                    dstK[pos] = key;
-                    dstI[pos] = id;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= o) inc += t;
+                    }
+                    row[st * 32 + lane] = (unsigned short)(run + inc - v);
+                    run += __shfl_sync(0xffffffffu, inc, 31);
                 }
-                __syncwarp();
+                if (lane == 0) hd->hist[warp] = run;  // digit total
+            }
+            __syncthreads();
+            if (warp == 0) {  // exclusive scan of the ND digit totals -> hist[64 + d]
+                const unsigned int v = (lane < ND) ? hd->hist[lane] : 0u;
+                unsigned int inc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                hd->hist[64 + lane] = inc - v;
+            }
+            __syncthreads();
+            for (int i = i0; i < i1; ++i) {
+                const unsigned int key = srcK[i];
+                const unsigned int d = (key >> shift) & (unsigned int)(ND - 1);
+                const unsigned int within = mycnt[d * kRsThreads];
+                mycnt[d * kRsThreads] = (unsigned short)(within + 1);
+                const unsigned int pos = hd->hist[64 + d] + within;
+                dstK[pos] = key;
+                dstI[pos] = srcI[i];
             }
             __syncthreads();
             unsigned int* tk = srcK; srcK = dstK; dstK = tk;
             unsigned short* ti = srcI; srcI = dstI; dstI = ti;
         }
-        // 4 passes: the sorted pairs are back in keyA / idxA
+        if (srcK != keyA) {  // odd number of passes: bring the result back to keyA / idxA
+            for (int i = tid; i < keff; i += kRsThreads) { keyA[i] = srcK[i]; idxA[i] = srcI[i]; }
+            __syncthreads();
+        }
         RS_TICK(3);
     }
 
@@ -334,8 +400,10 @@ int topk_radix_launch(const float* scores, const uint8_t* valid, const float* bo
     const size_t limit = 227 * 1024;
     const int kcap = (k + 31) & ~31;
     const int nchunks = (N + 31) / 32;
-    RsLayout L = rs_layout(N, kcap, nchunks, true);
-    if (L.total > limit) L = rs_layout(N, kcap, nchunks, false);
+    RsLayout L = rs_layout(N, kcap, nchunks, true, 5);
+    if (L.total > limit) L = rs_layout(N, kcap, nchunks, true, 4);
+    if (L.total > limit) L = rs_layout(N, kcap, nchunks, false, 5);
+    if (L.total > limit) L = rs_layout(N, kcap, nchunks, false, 4);
     if (L.total > limit) return 1;
     auto kern = L.staged ? topk_radix_kernel<true> : topk_radix_kernel<false>;
     FRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
