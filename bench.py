@@ -76,7 +76,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = max(threads, 8)
+    sample = max(threads, 8) * 4
     vals = []
     for _ in range(args.warmup):
         cpu_images_per_s(min(sample, threads), threads)
@@ -473,7 +473,7 @@ def run_extra(args):
             db, dl, ds, dc = ops.class_nms(prob.reshape(B, R, NC), boxes.reshape(B, R, 4 * NC), NC, score_thres=0.05,
                                            roi_count=cnt)
             packed, pc = fdist.pack_detections(db, dl, ds, dc, 100)
-            keepalive["d"] = fdist.gather_detections(packed, pc, ids)
+            keepalive["d"] = fdist.gather_detections(packed, pc, ids, equal_batch=True)
             return pooled
 
         for i in range(max(args.warmup, 3)):

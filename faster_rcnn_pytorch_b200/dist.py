@@ -42,8 +42,10 @@ def pack_detections(det_boxes, det_labels, det_scores, det_count, max_det: int):
     return out, cnt
 
 
-def gather_detections(packed, counts, image_ids, group=None):
+def gather_detections(packed, counts, image_ids, group=None, equal_batch: bool = False):
     """All-gather fixed-shape detections from every rank (one collective per tensor, no pickling, no host copy).
+    ``equal_batch=True``: the caller guarantees the same B_local on every rank (the usual sharded-eval case); the size
+    exchange and its host synchronisation are skipped and the call is fully asynchronous.
 
     packed [B_local,max_det,6] fp32, counts [B_local] int32, image_ids [B_local] int64.  Ranks may hold different
     B_local (the last shard can be short): tensors are padded to the largest local batch, padding rows carry
@@ -53,6 +55,15 @@ def gather_detections(packed, counts, image_ids, group=None):
     if ws == 1:
         return packed, counts, image_ids
     dev = packed.device
+    if equal_batch:
+        B = packed.shape[0]
+        P = torch.empty((ws * B,) + tuple(packed.shape[1:]), dtype=packed.dtype, device=dev)
+        Cn = torch.empty((ws * B,), dtype=torch.int32, device=dev)
+        I = torch.empty((ws * B,), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(P, packed.contiguous(), group=group)
+        dist.all_gather_into_tensor(Cn, counts.to(torch.int32).contiguous(), group=group)
+        dist.all_gather_into_tensor(I, image_ids.to(torch.int64).contiguous(), group=group)
+        return P, Cn, I
     b_local = torch.tensor([packed.shape[0]], dtype=torch.int64, device=dev)
     sizes = [torch.zeros_like(b_local) for _ in range(ws)]
     dist.all_gather(sizes, b_local, group=group)
