@@ -251,8 +251,7 @@ def run_ours(args):
     d_boxes = [torch.empty((B, n, 4), dtype=torch.float32, device=dev) for _ in range(N_ROTATE)]
     d_scores = [torch.empty((B, n), dtype=torch.float32, device=dev) for _ in range(N_ROTATE)]
     d_valid = [torch.empty((B, n), dtype=torch.uint8, device=dev) for _ in range(N_ROTATE)]
-    t_boxes = [torch.empty((B, PRE_K, 4), dtype=torch.float32, device=dev) for _ in range(N_ROTATE)]
-    t_idx = torch.empty((B, PRE_K), dtype=torch.int32, device=dev)
+    t_idx = [torch.empty((B, PRE_K), dtype=torch.int32, device=dev) for _ in range(N_ROTATE)]
     t_cnt = [torch.empty((B,), dtype=torch.int32, device=dev) for _ in range(N_ROTATE)]
     keep = torch.empty((B, POST_K), dtype=torch.int32, device=dev)
     kcnt = torch.empty((B,), dtype=torch.int32, device=dev)
@@ -267,14 +266,15 @@ def run_ours(args):
 
     def k_topk(i):
         r = i % N_ROTATE
-        _lib.check(lib.frr_topk_desc(d_scores[r].data_ptr(), d_valid[r].data_ptr(), d_boxes[r].data_ptr(), B, n, PRE_K,
-                                     None, t_idx.data_ptr(), None, t_boxes[r].data_ptr(), t_cnt[r].data_ptr(), st),
+        _lib.check(lib.frr_topk_desc(d_scores[r].data_ptr(), d_valid[r].data_ptr(), None, B, n, PRE_K,
+                                     None, t_idx[r].data_ptr(), None, None, t_cnt[r].data_ptr(), st),
                    "frr_topk_desc")
 
     def k_nms(i):
         r = i % N_ROTATE
-        _lib.check(lib.frr_nms_sorted_tuned(t_boxes[r].data_ptr(), t_cnt[r].data_ptr(), B, PRE_K, THR, POST_K, keep.data_ptr(),
-                                            kcnt.data_ptr(), rois.data_ptr(), 0, 0, None, 1, st), "frr_nms_sorted")
+        _lib.check(lib.frr_nms_sorted_indirect(d_boxes[r].data_ptr(), n, t_idx[r].data_ptr(), t_cnt[r].data_ptr(), B, PRE_K,
+                                               THR, POST_K, keep.data_ptr(), kcnt.data_ptr(), rois.data_ptr(), 0, 1, st),
+                   "frr_nms_sorted_indirect")
 
     def time_kernel(fn, reps):
         for i in range(N_ROTATE):
@@ -293,13 +293,15 @@ def run_ours(args):
     ms_topk = time_kernel(k_topk, reps)
     ms_nms = time_kernel(k_nms, reps)
     # single-image NMS latency (whole GPU available to one image: clusters of 8 / 16 CTAs)
-    one = t_boxes[0][:1].contiguous()
+    one_src = d_boxes[0][:1].contiguous()
+    one_idx = t_idx[0][:1].contiguous()
     one_c = t_cnt[0][:1].contiguous()
     ms_nms1 = {}
     for cs in (8, 16):
         def k_one(i, cs=cs):
-            _lib.check(lib.frr_nms_sorted_tuned(one.data_ptr(), one_c.data_ptr(), 1, PRE_K, THR, POST_K, keep.data_ptr(),
-                                                kcnt.data_ptr(), rois.data_ptr(), cs, 0, None, 1, st), "frr_nms_sorted")
+            _lib.check(lib.frr_nms_sorted_indirect(one_src.data_ptr(), n, one_idx.data_ptr(), one_c.data_ptr(), 1, PRE_K, THR,
+                                                   POST_K, keep.data_ptr(), kcnt.data_ptr(), rois.data_ptr(), cs, 1, st),
+                       "frr_nms_sorted_indirect")
         ms_nms1[cs] = time_kernel(k_one, 50)
     clocks = sampler.stop() if sampler else None
 
@@ -316,7 +318,7 @@ def run_ours(args):
     if rank == 0:
         peak, how = peaks()
         dec_bytes = B * n * 44.0                      # reg 16 + logits 8 + box 16 + score 4 per anchor
-        topk_bytes = B * (n * 5.0 + PRE_K * 40.0)     # scores 4 + valid 1 per anchor; idx 4 + box gather 16+16 per pick
+        topk_bytes = B * (n * 5.0 + PRE_K * 4.0)      # scores 4 + valid 1 per anchor; sorted index 4 per pick (NMS gathers)
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -128,7 +128,8 @@ template <int kThreads, bool kFast, bool kUnit, bool kSort>
 __global__ void __launch_bounds__(kThreads)
     nms_keeplist_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ counts, int n, int max_keep,
                         int slice_cap, NmsThr thr, int32_t* __restrict__ keep, int32_t* __restrict__ keep_count,
-                        float4* __restrict__ out_boxes, long long* __restrict__ dbg) {
+                        float4* __restrict__ out_boxes, long long* __restrict__ dbg,
+                        const int32_t* __restrict__ gather_idx, int src_n) {
     static_assert(kThreads >= kChunk && kThreads % kGroup == 0, "bad thread count");
     constexpr int kWarps = kThreads / 32;
     constexpr int kParts = kThreads / kGroup;  // interleaved parts of the kept slice
@@ -152,7 +153,12 @@ __global__ void __launch_bounds__(kThreads)
     int ns_sorted = 0;  // slice entries already bucketed in the current buffer
 
     const int cnt = counts ? min(counts[img], n) : n;
-    const float4* ib = boxes + (size_t)img * n;
+    // candidate i of the image: boxes[img][i], or boxes[img][gather_idx[img][i]] when the sorted order is given as
+    // indices into an unsorted [B, src_n, 4] array (the top-k kernel then never writes the 12 000 gathered boxes, and
+    // only the ~5 000 candidates NMS really visits are ever gathered)
+    const float4* ib = boxes + (size_t)img * (gather_idx ? src_n : n);
+    const int32_t* gi = gather_idx ? gather_idx + (size_t)img * n : nullptr;
+    auto cand = [&](int i) -> float4 { return gi ? ib[gi[i]] : ib[i]; };
     int32_t* ikeep = keep + (size_t)img * max_keep;
     float4* iout = out_boxes ? out_boxes + (size_t)img * max_keep : nullptr;
     const bool prof = (dbg != nullptr) && blockIdx.x == 0 && tid == 0;
@@ -167,7 +173,7 @@ __global__ void __launch_bounds__(kThreads)
     int nk = 0;  // kept so far (identical in every CTA of the cluster)
     int par = 0;
     float4 nbx = make_float4(0.f, 0.f, 0.f, 0.f);  // prefetched candidate of the next chunk (first kChunk threads)
-    if (tid < kChunk && tid < cnt) nbx = ib[tid];
+    if (tid < kChunk && tid < cnt) nbx = cand(tid);
     if (tid < 2 * kChunkWords) (&sm->acc[0][0])[tid] = 0u;
     if (kSorted && tid < kStrips + 2) sm->sstart[tid] = 0;
     for (int base = 0; base < cnt && nk < max_keep; base += kChunk, par ^= 1) {
@@ -177,7 +183,7 @@ __global__ void __launch_bounds__(kThreads)
             sm->cbox[tid] = nbx;
             sm->carea[tid] = screen_area(nbx, thr.c2);
             const int nx = base + kChunk + tid;
-            if (nx < cnt) nbx = ib[nx];
+            if (nx < cnt) nbx = cand(nx);
         }
         __syncthreads();
         FRR_TICK(DBG_LOAD);
@@ -567,7 +573,7 @@ static size_t nms_smem_bytes(int slice_cap, bool sorted) {
 
 int nms_launch(const float* boxes, const int32_t* counts, int B, int n, double iou_thr, int max_keep,
                       int32_t* keep, int32_t* keep_count, float* out_boxes, int cluster_size, int threads,
-                      long long* dbg, int unit_boxes, frr_stream_t stream) {
+                      long long* dbg, int unit_boxes, frr_stream_t stream, const int32_t* gather_idx, int src_n) {
     FRR_CHECK_ARG(keep && keep_count, "frr_nms_sorted: null output");
     FRR_CHECK_ARG(B >= 0 && n >= 0 && max_keep >= 0, "frr_nms_sorted: bad sizes B=%d n=%d max_keep=%d", B, n, max_keep);
     FRR_CHECK_ARG(n == 0 || (boxes && aligned16(boxes)), "frr_nms_sorted: boxes must be non-null, 16-byte aligned");
@@ -596,7 +602,8 @@ int nms_launch(const float* boxes, const int32_t* counts, int B, int n, double i
     const size_t smem = nms_smem_bytes(slice_cap, sorted);
     FRR_CHECK_ARG(smem <= limit, "frr_nms_sorted: max_keep=%d does not fit the kept list in shared memory", max_keep);
 
-    using kern_t = void (*)(const float4*, const int32_t*, int, int, int, NmsThr, int32_t*, int32_t*, float4*, long long*);
+    using kern_t = void (*)(const float4*, const int32_t*, int, int, int, NmsThr, int32_t*, int32_t*, float4*, long long*,
+                            const int32_t*, int);
     kern_t kern = nullptr;
 #define FRR_NMS_PICK(F, U, SO)                                                                      \
     (threads == 256 ? nms_keeplist_kernel<256, F, U, SO>                                               \
@@ -622,7 +629,7 @@ int nms_launch(const float* boxes, const int32_t* counts, int B, int n, double i
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     FRR_CUDA(cudaLaunchKernelEx(&cfg, kern, (const float4*)boxes, counts, n, max_keep, slice_cap, thr, keep, keep_count,
-                                (float4*)out_boxes, dbg));
+                                (float4*)out_boxes, dbg, gather_idx, src_n));
     count_launch();
     FRR_CHECK_LAUNCH("nms_keeplist_kernel");
     return FRR_OK;
@@ -634,12 +641,22 @@ extern "C" int frr_nms_sorted(const float* boxes, const int32_t* counts, int B, 
                               int32_t* keep, int32_t* keep_count, float* out_boxes, int cluster_size,
                               frr_stream_t stream) {
     return frr::nms_launch(boxes, counts, B, n, iou_thr, max_keep, keep, keep_count, out_boxes, cluster_size, 0, nullptr,
-                           0, stream);
+                           0, stream, nullptr, 0);
 }
 
 extern "C" int frr_nms_sorted_tuned(const float* boxes, const int32_t* counts, int B, int n, double iou_thr, int max_keep,
                                     int32_t* keep, int32_t* keep_count, float* out_boxes, int cluster_size, int threads,
                                     int64_t* dbg_cycles, int unit_boxes, frr_stream_t stream) {
     return frr::nms_launch(boxes, counts, B, n, iou_thr, max_keep, keep, keep_count, out_boxes, cluster_size, threads,
-                           (long long*)dbg_cycles, unit_boxes, stream);
+                           (long long*)dbg_cycles, unit_boxes, stream, nullptr, 0);
+}
+
+// Same as frr_nms_sorted_tuned, but the score order is given as indices: candidate i of image b is
+// boxes_src[b][order[b][i]] (boxes_src [B,src_n,4], order int32 [B,n], e.g. the out_idx of frr_topk_desc).
+extern "C" int frr_nms_sorted_indirect(const float* boxes_src, int src_n, const int32_t* order, const int32_t* counts, int B,
+                                       int n, double iou_thr, int max_keep, int32_t* keep, int32_t* keep_count,
+                                       float* out_boxes, int cluster_size, int unit_boxes, frr_stream_t stream) {
+    FRR_CHECK_ARG(order != nullptr && src_n >= 0, "frr_nms_sorted_indirect: order must be given");
+    return frr::nms_launch(boxes_src, counts, B, n, iou_thr, max_keep, keep, keep_count, out_boxes, cluster_size, 0, nullptr,
+                           unit_boxes, stream, order, src_n);
 }

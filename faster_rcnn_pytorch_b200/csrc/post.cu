@@ -15,7 +15,7 @@ namespace frr {
 
 int nms_launch(const float* boxes, const int32_t* counts, int B, int n, double iou_thr, int max_keep, int32_t* keep,
                int32_t* keep_count, float* out_boxes, int cluster_size, int threads, long long* dbg, int unit_boxes,
-               frr_stream_t stream);
+               frr_stream_t stream, const int32_t* gather_idx = nullptr, int src_n = 0);
 
 // ------------------------------------------------------------------------------------------------ D1
 // one warp per roi row

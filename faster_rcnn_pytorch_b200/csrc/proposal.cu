@@ -7,7 +7,7 @@ namespace frr {
 
 int nms_launch(const float* boxes, const int32_t* counts, int B, int n, double iou_thr, int max_keep, int32_t* keep,
                int32_t* keep_count, float* out_boxes, int cluster_size, int threads, long long* dbg, int unit_boxes,
-               frr_stream_t stream);
+               frr_stream_t stream, const int32_t* gather_idx = nullptr, int src_n = 0);
 
 struct ProposalWs {
     size_t boxes, scores, valid, top_boxes, top_idx, top_count, keep, total;
@@ -59,7 +59,6 @@ int frr_rpn_proposals(const float* reg, const float* cls, int cls_is_logits, con
     float* boxes = reinterpret_cast<float*>(p + w.boxes);
     float* scores = reinterpret_cast<float*>(p + w.scores);
     uint8_t* valid = reinterpret_cast<uint8_t*>(p + w.valid);
-    float* top_boxes = reinterpret_cast<float*>(p + w.top_boxes);
     int32_t* top_idx = reinterpret_cast<int32_t*>(p + w.top_idx);
     int32_t* top_count = reinterpret_cast<int32_t*>(p + w.top_count);
     int32_t* keep = reinterpret_cast<int32_t*>(p + w.keep);
@@ -71,10 +70,12 @@ int frr_rpn_proposals(const float* reg, const float* cls, int cls_is_logits, con
         FRR_CUDA(cudaMemsetAsync(rois, 0, (size_t)B * post_nms_top_k * 16, (cudaStream_t)stream));
         return FRR_OK;
     }
-    rc = frr_topk_desc(scores, valid, boxes, B, N, k, nullptr, top_idx, nullptr, top_boxes, top_count, stream);
+    // top-k writes only the sorted indices; NMS gathers the candidates it visits straight from the decoded boxes
+    rc = frr_topk_desc(scores, valid, nullptr, B, N, k, nullptr, top_idx, nullptr, nullptr, top_count, stream);
     if (rc) return rc;
     // the decoded boxes are clamped to [0,1] (models/model.py:34): unit-range screening
-    return nms_launch(top_boxes, top_count, B, k, iou_thr, post_nms_top_k, keep, roi_count, rois, 0, 0, nullptr, 1, stream);
+    return nms_launch(boxes, top_count, B, k, iou_thr, post_nms_top_k, keep, roi_count, rois, 0, 0, nullptr, 1, stream,
+                      top_idx, N);
 }
 
 }  // extern "C"

@@ -104,6 +104,13 @@ int frr_nms_sorted_tuned(const float* boxes, const int32_t* counts, int B, int n
                          int32_t* keep, int32_t* keep_count, float* out_boxes, int cluster_size, int threads,
                          int64_t* dbg_cycles, int unit_boxes, frr_stream_t stream);
 
+/* Same, with the score order given as indices into an unsorted array: candidate i of image b is
+ * boxes_src[b][order[b][i]] (boxes_src [B,src_n,4]; order int32 [B,n] = out_idx of frr_topk_desc).  Only the
+ * candidates NMS visits are gathered; the top-k kernel then need not write sorted boxes at all.          */
+int frr_nms_sorted_indirect(const float* boxes_src, int src_n, const int32_t* order, const int32_t* counts, int B,
+                            int n, double iou_thr, int max_keep, int32_t* keep, int32_t* keep_count,
+                            float* out_boxes, int cluster_size, int unit_boxes, frr_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * RegionProposal.forward for a batch in one call -- models/model.py:17-58 (P1-P4 + N1 chained: the three
  * kernels above on `stream`, intermediates in `workspace`).  k = min(pre_nms_top_k, N) (:46-47).

@@ -286,3 +286,24 @@ def test_nms_unit_range_screen_gives_identical_keep_lists(oracle):
         assert torch.equal(k0, k1) and torch.equal(c0, c1) and torch.equal(r0, r1)
         want = oracle.nms(b, -np.arange(n, dtype=np.float32), thr)[:2000]
         assert np.array_equal(k1[0, :int(c1[0])].cpu().numpy(), want)
+
+
+def test_nms_indirect_order_matches_gathered_boxes(oracle):
+    """frr_nms_sorted_indirect(boxes_src, order) == frr_nms_sorted(boxes_src[order])."""
+    from faster_rcnn_pytorch_b200 import _lib
+    lib = _lib.load()
+    B, N, k = 3, 5000, 3000
+    rs = np.random.RandomState(77)
+    src = np.stack([synth.random_boxes(600 + i, N)[0] for i in range(B)])
+    order = np.stack([rs.permutation(N)[:k] for _ in range(B)]).astype(np.int32)
+    counts = np.asarray([k, k - 7, 100], np.int32)
+    gathered = np.stack([src[i][order[i]] for i in range(B)])
+    want_keep, want_cnt, want_rois = ops.nms_sorted(dev(gathered), 0.7, max_keep=500, counts=dev(counts))
+    d_src, d_ord, d_cnt = dev(src), dev(order), dev(counts)
+    keep = torch.empty((B, 500), dtype=torch.int32, device=DEV); cnt = torch.empty((B,), dtype=torch.int32, device=DEV)
+    rois = torch.empty((B, 500, 4), dtype=torch.float32, device=DEV)
+    for unit in (0, 1):
+        _lib.check(lib.frr_nms_sorted_indirect(d_src.data_ptr(), N, d_ord.data_ptr(), d_cnt.data_ptr(), B, k, 0.7, 500,
+                                               keep.data_ptr(), cnt.data_ptr(), rois.data_ptr(), 0, unit,
+                                               torch.cuda.current_stream().cuda_stream), "frr_nms_sorted_indirect")
+        assert torch.equal(keep, want_keep) and torch.equal(cnt, want_cnt) and torch.equal(rois, want_rois)
