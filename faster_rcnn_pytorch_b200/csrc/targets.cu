@@ -22,11 +22,13 @@ constexpr int kTgtThreads = 1024;
 constexpr int kTgtWarps = kTgtThreads / 32;
 
 // utils/util.py:66-102
-__device__ __forceinline__ float iou_eps(const float4& a, float area_a, const float4& b, float area_b) {
+// eps = 1e-5f: find_jaccard_overlap (utils/util.py:66-102, VGG variant); eps = 0: box_iou (util/box_ops.py:24-37, FPN
+// variant: union = (a1 + a2) - inter, and x + 0.0f == x bit for bit)
+__device__ __forceinline__ float iou_eps(const float4& a, float area_a, const float4& b, float area_b, float eps) {
     const float w = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.f);
     const float h = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.f);
     const float inter = __fmul_rn(w, h);
-    const float uni = __fadd_rn(__fsub_rn(__fadd_rn(area_a, area_b), inter), 1e-5f);
+    const float uni = __fadd_rn(__fsub_rn(__fadd_rn(area_a, area_b), inter), eps);
     return __fdiv_rn(inter, uni);
 }
 __device__ __forceinline__ float area_of(const float4& b) { return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y)); }
@@ -108,7 +110,8 @@ __device__ void ordered_lists(const int8_t* __restrict__ lab8, int n, int32_t* _
 __global__ void __launch_bounds__(kTgtThreads)
     rpn_assign_kernel(const float4* __restrict__ gt, const int32_t* __restrict__ gt_count, int Gmax,
                       const float4* __restrict__ anchors, AnchorTable tab, int N, int fw, float stride, float W, float H,
-                      float neg_thr, float pos_thr, float* __restrict__ iou_max, int32_t* __restrict__ argmax,
+                      float neg_thr, float pos_thr, float eps, int inside_only, int tie_inclusive,
+                      float* __restrict__ iou_max, int32_t* __restrict__ argmax,
                       int8_t* __restrict__ lab8, int32_t* __restrict__ pos_list, int32_t* __restrict__ neg_list,
                       int32_t* __restrict__ counts /* [B,2] */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(kTgtThreads)
     // pass 1: row max / first argmax, per-GT best inside anchor (iou bits, then lowest index)
     for (int i = tid; i < N; i += kTgtThreads) {
         const float4 a = anchor_at(anchors, tab, i, fw, stride, W, H);
-        const bool inside = (a.x >= 0.f) && (a.y >= 0.f) && (a.z <= 1.f) && (a.w <= 1.f);
+        const bool inside = !inside_only || ((a.x >= 0.f) && (a.y >= 0.f) && (a.z <= 1.f) && (a.w <= 1.f));
         float mx = 0.f;
         int arg = 0;
         int8_t l = -2;  // outside the image
@@ -144,7 +147,7 @@ __global__ void __launch_bounds__(kTgtThreads)
             const float aa = area_of(a);
             mx = -1.f;
             for (int g = 0; g < G; ++g) {
-                const float v = iou_eps(a, aa, sgt[g], sga[g]);
+                const float v = iou_eps(a, aa, sgt[g], sga[g], eps);
                 if (v > mx) { mx = v; arg = g; }
                 const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(~(unsigned int)i);
                 if (key > best[g]) atomicMax(&best[g], key);
@@ -157,10 +160,26 @@ __global__ void __launch_bounds__(kTgtThreads)
         lb[i] = l;
     }
     __syncthreads();
-    // label[argmax over anchors per GT] = 1  (:206-213); overrides the negative label
-    for (int g = tid; g < G; g += kTgtThreads) {
-        const unsigned long long k = best[g];
-        if (k != 0ull) lb[~(unsigned int)(k & 0xffffffffull)] = 1;
+    if (!tie_inclusive) {
+        // label[argmax over anchors per GT (first index on tie)] = 1  (models/model.py:206-213); overrides the negative label
+        for (int g = tid; g < G; g += kTgtThreads) {
+            const unsigned long long k = best[g];
+            if (k != 0ull) lb[~(unsigned int)(k & 0xffffffffull)] = 1;
+        }
+    } else {
+        // FPN variant (models/new_model.py:316-318): EVERY anchor whose IoU equals the per-GT maximum becomes positive
+        // (torch.where(iou == max)), including the degenerate "max == 0" case
+        for (int i = tid; i < N; i += kTgtThreads) {
+            if (lb[i] == -2) continue;
+            const float4 a = anchor_at(anchors, tab, i, fw, stride, W, H);
+            const float aa = area_of(a);
+            bool hit = false;
+            for (int g = 0; g < G; ++g) {
+                const unsigned long long k = best[g];
+                if (k != 0ull && iou_eps(a, aa, sgt[g], sga[g], eps) == __uint_as_float((unsigned int)(k >> 32))) hit = true;
+            }
+            if (hit) lb[i] = 1;
+        }
     }
     __syncthreads();
     ordered_lists(lb, N, pos_list + (size_t)b * N, neg_list + (size_t)b * N, cnt_a, cnt_b, ts, counts + 2 * b);
@@ -200,7 +219,7 @@ __global__ void __launch_bounds__(kTgtThreads)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTgtThreads)
     frcnn_assign_kernel(const float4* __restrict__ rois, const int32_t* __restrict__ roi_count, int Rmax,
-                        const float4* __restrict__ gt, const int32_t* __restrict__ gt_count, int Gmax, float fg_thr,
+                        const float4* __restrict__ gt, const int32_t* __restrict__ gt_count, int Gmax, float fg_thr, float eps,
                         float* __restrict__ iou_max, int32_t* __restrict__ argmax, int8_t* __restrict__ lab8,
                         int32_t* __restrict__ pos_list, int32_t* __restrict__ neg_list, int32_t* __restrict__ counts) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -234,7 +253,7 @@ __global__ void __launch_bounds__(kTgtThreads)
             const float aa = area_of(a);
             mx = -1.f;
             for (int g = 0; g < G; ++g) {
-                const float v = iou_eps(a, aa, sgt[g], sga[g]);
+                const float v = iou_eps(a, aa, sgt[g], sga[g], eps);
                 if (v > mx) { mx = v; arg = g; }
             }
             if (mx >= fg_thr) l = 1;               // :147
@@ -253,7 +272,7 @@ __global__ void __launch_bounds__(128)
                           const float4* __restrict__ gt, const int64_t* __restrict__ gt_label, int Gmax,
                           const int32_t* __restrict__ argmax, const int32_t* __restrict__ pos_list,
                           const int32_t* __restrict__ neg_list, const int32_t* __restrict__ sel /* [B,S] positions */,
-                          const int32_t* __restrict__ sel_n /* [B,2]: n_pos, n_total */, int S, float4 stdv,
+                          const int32_t* __restrict__ sel_n /* [B,2]: n_pos, n_total */, int S, float4 stdv, int label_offset,
                           int64_t* __restrict__ cls, float4* __restrict__ reg, float4* __restrict__ sample_rois,
                           int32_t* __restrict__ keep_index) {
     const int b = blockIdx.x;
@@ -267,7 +286,7 @@ __global__ void __launch_bounds__(128)
             const int idx = (j < n_pos) ? pos_list[(size_t)b * M + p] : neg_list[(size_t)b * M + p];
             const float4 box = (idx < R) ? rois[(size_t)b * Rmax + idx] : gt[(size_t)b * Gmax + (idx - R)];
             const int g = argmax[(size_t)b * M + idx];
-            cls[o] = (j < n_pos) ? gt_label[(size_t)b * Gmax + g] + 1 : 0;  // :141,:165
+            cls[o] = (j < n_pos) ? gt_label[(size_t)b * Gmax + g] + label_offset : 0;  // :141,:165 (+1) / new_model.py:166 (+0)
             float4 t = encode_box(gt[(size_t)b * Gmax + g], box);           // :171
             t.x = __fdiv_rn(t.x, stdv.x);                                   // :174-177 (mean is 0)
             t.y = __fdiv_rn(t.y, stdv.y);
@@ -314,8 +333,9 @@ extern "C" {
 
 int frr_rpn_targets_assign(const float* gt, const int32_t* gt_count, int B, int Gmax, const float* anchors,
                            const float* base_table_host, int A, int img_h, int img_w, int stride, int N, float neg_thr,
-                           float pos_thr, float* iou_max, int32_t* argmax, int8_t* label8, int32_t* pos_list,
-                           int32_t* neg_list, int32_t* counts, frr_stream_t stream) {
+                           float pos_thr, float iou_eps_, int inside_only, int tie_inclusive, float* iou_max,
+                           int32_t* argmax, int8_t* label8, int32_t* pos_list, int32_t* neg_list, int32_t* counts,
+                           frr_stream_t stream) {
     using namespace frr;
     FRR_CHECK_ARG(gt && iou_max && argmax && label8 && pos_list && neg_list && counts, "frr_rpn_targets_assign: null pointer");
     FRR_CHECK_ARG(B >= 0 && Gmax >= 1 && N >= 1, "frr_rpn_targets_assign: bad sizes (G = 0 is an error in the reference too)");
@@ -330,7 +350,7 @@ int frr_rpn_targets_assign(const float* gt, const int32_t* gt_count, int B, int 
     FRR_CUDA(cudaFuncSetAttribute(rpn_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     rpn_assign_kernel<<<B, kTgtThreads, smem, (cudaStream_t)stream>>>(
         (const float4*)gt, gt_count, Gmax, (const float4*)anchors, tab, N, fw, (float)stride, (float)img_w, (float)img_h,
-        neg_thr, pos_thr, iou_max, argmax, label8, pos_list, neg_list, counts);
+        neg_thr, pos_thr, iou_eps_, inside_only, tie_inclusive, iou_max, argmax, label8, pos_list, neg_list, counts);
     count_launch();
     FRR_CHECK_LAUNCH("rpn_assign_kernel");
     return FRR_OK;
@@ -358,8 +378,9 @@ int frr_rpn_targets_finalize(const float* gt, int B, int Gmax, const float* anch
 }
 
 int frr_frcnn_targets_assign(const float* rois, const int32_t* roi_count, int B, int Rmax, const float* gt,
-                             const int32_t* gt_count, int Gmax, float fg_thr, float* iou_max, int32_t* argmax,
-                             int8_t* label8, int32_t* pos_list, int32_t* neg_list, int32_t* counts, frr_stream_t stream) {
+                             const int32_t* gt_count, int Gmax, float fg_thr, float iou_eps_, float* iou_max,
+                             int32_t* argmax, int8_t* label8, int32_t* pos_list, int32_t* neg_list, int32_t* counts,
+                             frr_stream_t stream) {
     using namespace frr;
     FRR_CHECK_ARG(rois && gt && iou_max && argmax && label8 && pos_list && neg_list && counts,
                   "frr_frcnn_targets_assign: null pointer");
@@ -370,8 +391,8 @@ int frr_frcnn_targets_assign(const float* rois, const int32_t* roi_count, int B,
     FRR_CHECK_ARG(smem <= 227 * 1024, "frr_frcnn_targets_assign: needs %zu B shared memory", smem);
     FRR_CUDA(cudaFuncSetAttribute(frcnn_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     frcnn_assign_kernel<<<B, kTgtThreads, smem, (cudaStream_t)stream>>>((const float4*)rois, roi_count, Rmax,
-                                                                         (const float4*)gt, gt_count, Gmax, fg_thr, iou_max,
-                                                                         argmax, label8, pos_list, neg_list, counts);
+                                                                         (const float4*)gt, gt_count, Gmax, fg_thr, iou_eps_,
+                                                                         iou_max, argmax, label8, pos_list, neg_list, counts);
     count_launch();
     FRR_CHECK_LAUNCH("frcnn_assign_kernel");
     return FRR_OK;
@@ -380,8 +401,8 @@ int frr_frcnn_targets_assign(const float* rois, const int32_t* roi_count, int B,
 int frr_frcnn_targets_finalize(const float* rois, const int32_t* roi_count, int B, int Rmax, const float* gt,
                                const int64_t* gt_label, int Gmax, const int32_t* argmax, const int32_t* pos_list,
                                const int32_t* neg_list, const int32_t* sel, const int32_t* sel_n, int S,
-                               const float* std4_host, int64_t* cls, float* reg, float* sample_rois, int32_t* keep_index,
-                               frr_stream_t stream) {
+                               const float* std4_host, int label_offset, int64_t* cls, float* reg, float* sample_rois,
+                               int32_t* keep_index, frr_stream_t stream) {
     using namespace frr;
     FRR_CHECK_ARG(rois && gt && gt_label && argmax && pos_list && neg_list && sel && sel_n && cls && reg && sample_rois &&
                       keep_index && std4_host,
@@ -393,7 +414,8 @@ int frr_frcnn_targets_finalize(const float* rois, const int32_t* roi_count, int 
     const float4 stdv = make_float4(std4_host[0], std4_host[1], std4_host[2], std4_host[3]);
     frcnn_finalize_kernel<<<B, 128, 0, (cudaStream_t)stream>>>((const float4*)rois, roi_count, Rmax, (const float4*)gt,
                                                                gt_label, Gmax, argmax, pos_list, neg_list, sel, sel_n, S,
-                                                               stdv, cls, (float4*)reg, (float4*)sample_rois, keep_index);
+                                                               stdv, label_offset, cls, (float4*)reg, (float4*)sample_rois,
+                                                               keep_index);
     count_launch();
     FRR_CHECK_LAUNCH("frcnn_finalize_kernel");
     return FRR_OK;

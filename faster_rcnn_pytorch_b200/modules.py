@@ -16,7 +16,7 @@ import torch.nn as nn
 from . import ops, region, targets
 
 __all__ = ["nms", "roi_pool", "roi_align", "RoIPool", "RoIAlign", "RegionProposal", "RPNTargetMaker",
-           "FastRcnnTargetMaker", "predict_tail", "suppress"]
+           "FastRcnnTargetMaker", "predict_tail", "suppress", "fpn"]
 
 roi_pool = ops.roi_pool
 roi_align = ops.roi_align
@@ -112,6 +112,31 @@ class FastRcnnTargetMaker(nn.Module):
                                                       label.detach().to(torch.int64).unsqueeze(0))
         k = int(n[0])
         return cls[0, :k], reg[0, :k], srois[0, :k]
+
+
+class fpn:
+    """Drop-ins for the target makers of the FPN variant, models/new_model.py (what main.py trains today).  Same class
+    names and forward signatures as there (tensors, not per-image lists); normalised xyxy boxes like the reference."""
+
+    class RPNTargetMaker(nn.Module):
+        """models/new_model.py:299-349.  ``forward(boxes [G,4], anchors [N,4])`` -> (label int64 [N], tg_cxywh [N,4])."""
+
+        def forward(self, boxes, anchors):
+            anchors = _as_anchor_tensor(anchors, boxes.device)
+            labels, reg = targets.rpn_targets(boxes.detach().to(torch.float32).reshape(1, -1, 4), None, anchors=anchors,
+                                              variant="fpn")
+            return labels[0], reg[0]
+
+    class FRCNNTargetMaker(nn.Module):
+        """models/new_model.py:153-206.  ``forward(boxes [G,4], labels [G], rois [R,4])`` ->
+        (cls int64 [<=512], reg [<=512,4], sample_rois [<=512,4])."""
+
+        def forward(self, boxes, labels, rois):
+            cls, reg, srois, _, n = targets.frcnn_targets(rois.detach().to(torch.float32).unsqueeze(0), None,
+                                                          boxes.detach().to(torch.float32).unsqueeze(0), None,
+                                                          labels.detach().to(torch.int64).unsqueeze(0), variant="fpn")
+            k = int(n[0])
+            return cls[0, :k], reg[0, :k], srois[0, :k]
 
 
 def predict_tail(pred_cls, pred_reg, rois, num_classes: int):

@@ -289,8 +289,16 @@ def roi_align(input, boxes, output_size, spatial_scale: float = 1.0, sampling_ra
 _STD4 = np.array([0.1, 0.1, 0.2, 0.2], dtype=np.float32)       # models/model.py:176,372
 
 
-def rpn_targets_assign(gt, gt_count, N, image_hw=None, anchors=None, stride=16, table=None, neg_thr=0.3, pos_thr=0.7):
+VARIANTS = {   # (iou_eps, inside_only, tie_inclusive): models/model.py vs models/new_model.py target makers
+    "vgg": (float(np.float32(1e-5)), 1, 0),
+    "fpn": (0.0, 0, 1),
+}
+
+
+def rpn_targets_assign(gt, gt_count, N, image_hw=None, anchors=None, stride=16, table=None, neg_thr=0.3, pos_thr=0.7,
+                       variant: str = "vgg"):
     lib = _lib.load()
+    eps, inside_only, tie_inclusive = VARIANTS[variant]
     gt = _req(gt, "gt")
     if gt.dim() != 3 or gt.shape[-1] != 4:
         raise ValueError("gt must be [B,Gmax,4]")
@@ -314,8 +322,8 @@ def rpn_targets_assign(gt, gt_count, N, image_hw=None, anchors=None, stride=16, 
                   neg_list=torch.empty((B, N), dtype=torch.int32, device=dev),
                   counts=torch.empty((B, 2), dtype=torch.int32, device=dev))
         _lib.check(lib.frr_rpn_targets_assign(gt.data_ptr(), _ptr(gt_count), B, G, _ptr(anchors), tptr, A, H, W, stride, N,
-                                              float(np.float32(neg_thr)), float(np.float32(pos_thr)),
-                                              ws["iou_max"].data_ptr(), ws["argmax"].data_ptr(), ws["label8"].data_ptr(),
+                                              float(np.float32(neg_thr)), float(np.float32(pos_thr)), eps, inside_only,
+                                              tie_inclusive, ws["iou_max"].data_ptr(), ws["argmax"].data_ptr(), ws["label8"].data_ptr(),
                                               ws["pos_list"].data_ptr(), ws["neg_list"].data_ptr(), ws["counts"].data_ptr(),
                                               _stream()), "frr_rpn_targets_assign")
     ws.update(gt=gt, anchors=anchors, geom=(H, W, stride, table, N))
@@ -339,8 +347,9 @@ def rpn_targets_finalize(ws, disable=None, disable_off=None):
     return labels, reg
 
 
-def frcnn_targets_assign(rois, roi_count, gt, gt_count, fg_thr=0.5):
+def frcnn_targets_assign(rois, roi_count, gt, gt_count, fg_thr=0.5, variant: str = "vgg"):
     lib = _lib.load()
+    eps = VARIANTS[variant][0]
     rois = _req(rois, "rois")
     gt = _req(gt, "gt")
     B, R = rois.shape[0], rois.shape[1]
@@ -361,14 +370,14 @@ def frcnn_targets_assign(rois, roi_count, gt, gt_count, fg_thr=0.5):
                   neg_list=torch.empty((B, M), dtype=torch.int32, device=dev),
                   counts=torch.empty((B, 2), dtype=torch.int32, device=dev))
         _lib.check(lib.frr_frcnn_targets_assign(rois.data_ptr(), _ptr(roi_count), B, R, gt.data_ptr(), _ptr(gt_count), G,
-                                                float(np.float32(fg_thr)), ws["iou_max"].data_ptr(), ws["argmax"].data_ptr(),
+                                                float(np.float32(fg_thr)), eps, ws["iou_max"].data_ptr(), ws["argmax"].data_ptr(),
                                                 ws["label8"].data_ptr(), ws["pos_list"].data_ptr(), ws["neg_list"].data_ptr(),
                                                 ws["counts"].data_ptr(), _stream()), "frr_frcnn_targets_assign")
     ws.update(rois=rois, roi_count=roi_count, gt=gt)
     return ws
 
 
-def frcnn_targets_finalize(ws, gt_label, sel, sel_n, std=_STD4):
+def frcnn_targets_finalize(ws, gt_label, sel, sel_n, std=_STD4, label_offset: int = 1):
     lib = _lib.load()
     rois, gt = ws["rois"], ws["gt"]
     gt_label = _req(gt_label, "gt_label", torch.int64)
@@ -385,7 +394,7 @@ def frcnn_targets_finalize(ws, gt_label, sel, sel_n, std=_STD4):
         _lib.check(lib.frr_frcnn_targets_finalize(rois.data_ptr(), _ptr(ws["roi_count"]), B, R, gt.data_ptr(),
                                                   gt_label.data_ptr(), G, ws["argmax"].data_ptr(), ws["pos_list"].data_ptr(),
                                                   ws["neg_list"].data_ptr(), sel.data_ptr(), sel_n.data_ptr(), S,
-                                                  std.ctypes.data, cls.data_ptr(), reg.data_ptr(), srois.data_ptr(),
+                                                  std.ctypes.data, int(label_offset), cls.data_ptr(), reg.data_ptr(), srois.data_ptr(),
                                                   kidx.data_ptr(), _stream()), "frr_frcnn_targets_finalize")
     return cls, reg, srois, kidx
 

@@ -34,11 +34,15 @@ def rpn_disable_positions(n_pos: int, n_neg: int, randperm):
     return dis_pos, dis_neg
 
 
-def frcnn_select_positions(n_pos_cand: int, n_neg_cand: int, randperm):
+FRCNN_SAMPLING = {"vgg": (FRCNN_BATCH, FRCNN_MAX_POS), "fpn": (512, 128)}   # models/new_model.py:169-177
+
+
+def frcnn_select_positions(n_pos_cand: int, n_neg_cand: int, randperm, batch: int = FRCNN_BATCH,
+                           max_pos: int = FRCNN_MAX_POS):
     """models/model.py:144-156: both permutations are always drawn; returns (positions, n_pos)."""
-    n_pos = int(min(n_pos_cand, FRCNN_MAX_POS))
+    n_pos = int(min(n_pos_cand, max_pos))
     sel_pos = _perm(randperm, n_pos_cand)[:n_pos]
-    sel_neg = _perm(randperm, n_neg_cand)[:FRCNN_BATCH - n_pos]
+    sel_neg = _perm(randperm, n_neg_cand)[:batch - n_pos]
     return np.concatenate([sel_pos, sel_neg]).astype(np.int32), n_pos
 
 
@@ -54,9 +58,9 @@ def _upload_disable(per_image, device):
             torch.from_numpy(np.asarray(off, dtype=np.int32)).to(device, non_blocking=True))
 
 
-def _upload_select(per_image, device):
+def _upload_select(per_image, device, batch: int = FRCNN_BATCH):
     B = len(per_image)
-    sel = np.zeros((B, FRCNN_BATCH), np.int32)
+    sel = np.zeros((B, batch), np.int32)
     sel_n = np.zeros((B, 2), np.int32)
     for b, (s, n_pos) in enumerate(per_image):
         sel[b, :len(s)] = s
@@ -65,7 +69,8 @@ def _upload_select(per_image, device):
 
 
 def rpn_targets(gt, gt_count=None, image_hw=None, anchors=None, N=None, randperm=torch.randperm, **kw):
-    """Batched RPNTargetMaker: gt [B,Gmax,4] (+ gt_count) -> labels int64 [B,N], reg fp32 [B,N,4]."""
+    """Batched RPNTargetMaker: gt [B,Gmax,4] (+ gt_count) -> labels int64 [B,N], reg fp32 [B,N,4].
+    ``variant="fpn"`` = models/new_model.py:299-349 (no inside filter, eps-free IoU, tie-inclusive low-quality match)."""
     if N is None:
         N = anchors.shape[0] if anchors is not None else (image_hw[0] // 16) * (image_hw[1] // 16) * 9
     ws = ops.rpn_targets_assign(gt, gt_count, N, image_hw=image_hw, anchors=anchors, **kw)
@@ -75,13 +80,15 @@ def rpn_targets(gt, gt_count=None, image_hw=None, anchors=None, N=None, randperm
     return ops.rpn_targets_finalize(ws, disable, off)
 
 
-def frcnn_targets(rois, roi_count, gt, gt_count, gt_label, randperm=torch.randperm):
-    """Batched FastRcnnTargetMaker: -> cls int64 [B,128], reg [B,128,4], sample_rois [B,128,4], n int32 [B] (host)."""
-    ws = ops.frcnn_targets_assign(rois, roi_count, gt, gt_count)
+def frcnn_targets(rois, roi_count, gt, gt_count, gt_label, randperm=torch.randperm, variant: str = "vgg"):
+    """Batched FastRcnnTargetMaker: -> cls int64 [B,S], reg [B,S,4], sample_rois [B,S,4], n int32 [B] (host); S = 128
+    (``variant="vgg"``, models/model.py:127-179) or 512 (``"fpn"``, models/new_model.py:153-206)."""
+    batch, max_pos = FRCNN_SAMPLING[variant]
+    ws = ops.frcnn_targets_assign(rois, roi_count, gt, gt_count, variant=variant)
     counts = ws["counts"].cpu().numpy()
-    per_image = [frcnn_select_positions(int(c[0]), int(c[1]), randperm) for c in counts]
-    sel, sel_n = _upload_select(per_image, rois.device)
-    cls, reg, srois, kidx = ops.frcnn_targets_finalize(ws, gt_label, sel, sel_n)
+    per_image = [frcnn_select_positions(int(c[0]), int(c[1]), randperm, batch, max_pos) for c in counts]
+    sel, sel_n = _upload_select(per_image, rois.device, batch)
+    cls, reg, srois, kidx = ops.frcnn_targets_finalize(ws, gt_label, sel, sel_n, label_offset=0 if variant == "fpn" else 1)
     return cls, reg, srois, kidx, np.asarray([len(s) for s, _ in per_image], dtype=np.int32)
 
 

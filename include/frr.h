@@ -167,10 +167,14 @@ int frr_roi_debug_cycles(int64_t* host_out16);
  *                   (utils/util.py:39-43) and writes labels int64 [B,N], reg fp32 [B,N,4].
  *     gt [B,Gmax,4] + gt_count [B] (NULL = Gmax each); anchors [N,4] or NULL (generated, A2).
  *     Thresholds are fp32 compares (reference 0.3f / 0.7f).
+ *     Variant knobs: (iou_eps, inside_only, tie_inclusive) = (1e-5f, 1, 0) is models/model.py (VGG);
+ *     (0, 0, 1) is RPNTargetMaker of the FPN variant, models/new_model.py:299-349 (box_iou without eps,
+ *     util/box_ops.py:24-37; no inside-image filter; every anchor tied at a GT's best IoU becomes positive, :316-318).
  * ------------------------------------------------------------------------------------- */
 int frr_rpn_targets_assign(const float* gt, const int32_t* gt_count, int B, int Gmax, const float* anchors,
                            const float* base_table_host, int A, int img_h, int img_w, int stride, int N,
-                           float neg_thr, float pos_thr, float* iou_max, int32_t* argmax, int8_t* label8,
+                           float neg_thr, float pos_thr, float iou_eps, int inside_only, int tie_inclusive,
+                           float* iou_max, int32_t* argmax, int8_t* label8,
                            int32_t* pos_list, int32_t* neg_list, int32_t* counts, frr_stream_t stream);
 int frr_rpn_targets_finalize(const float* gt, int B, int Gmax, const float* anchors, const float* base_table_host,
                              int A, int img_h, int img_w, int stride, int N, const int32_t* argmax, int8_t* label8,
@@ -185,15 +189,17 @@ int frr_rpn_targets_finalize(const float* gt, int B, int Gmax, const float* anch
  *     (n_pos, n_total); writes cls int64 [B,S] (label+1 / 0 / -1 pad), reg [B,S,4] = encode / std,
  *     sample_rois [B,S,4], keep_index int32 [B,S] (index into the concatenated boxes).
  * ------------------------------------------------------------------------------------- */
+/* iou_eps: 1e-5f = models/model.py (find_jaccard_overlap), 0 = FRCNNTargetMaker of models/new_model.py:153-206 (box_iou;
+ * that variant samples 512 RoIs with <= 128 positives on the host side). */
 int frr_frcnn_targets_assign(const float* rois, const int32_t* roi_count, int B, int Rmax, const float* gt,
-                             const int32_t* gt_count, int Gmax, float fg_thr, float* iou_max, int32_t* argmax,
-                             int8_t* label8, int32_t* pos_list, int32_t* neg_list, int32_t* counts,
+                             const int32_t* gt_count, int Gmax, float fg_thr, float iou_eps, float* iou_max,
+                             int32_t* argmax, int8_t* label8, int32_t* pos_list, int32_t* neg_list, int32_t* counts,
                              frr_stream_t stream);
 int frr_frcnn_targets_finalize(const float* rois, const int32_t* roi_count, int B, int Rmax, const float* gt,
                                const int64_t* gt_label, int Gmax, const int32_t* argmax, const int32_t* pos_list,
                                const int32_t* neg_list, const int32_t* sel, const int32_t* sel_n, int S,
-                               const float* std4_host, int64_t* cls, float* reg, float* sample_rois,
-                               int32_t* keep_index, frr_stream_t stream);
+                               const float* std4_host, int label_offset /* 1: models/model.py:141, 0: new_model.py:166 */,
+                               int64_t* cls, float* reg, float* sample_rois, int32_t* keep_index, frr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * D1  predict tail -- models/model.py:369-378: prob = softmax(cls); boxes = clamp(cxcy_to_xy(

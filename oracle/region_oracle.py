@@ -265,8 +265,10 @@ class HostRandperm:
 # ----------------------------------------------------------------------------------------
 
 
-def rpn_targets(gt: np.ndarray, anchor: np.ndarray, randperm) -> dict:
-    """models/model.py:186-266  ``RPNTargetMaker.forward`` for one image.
+def rpn_targets(gt: np.ndarray, anchor: np.ndarray, randperm, variant: str = "vgg") -> dict:
+    """models/model.py:186-266  ``RPNTargetMaker.forward`` for one image; ``variant="fpn"`` restates
+    models/new_model.py:299-349 instead (box_iou without eps, util/box_ops.py:24-37; no inside-image filter;
+    every anchor whose IoU equals a GT's best IoU becomes positive, :316-318).
 
     ``randperm`` is a callable n -> int64 permutation (torch.randperm or HostRandperm).
     Returns labels int64 [N] in {-1,0,1}, reg fp32 [N,4], and the intermediates
@@ -276,15 +278,21 @@ def rpn_targets(gt: np.ndarray, anchor: np.ndarray, randperm) -> dict:
     anchor = np.asarray(anchor, dtype=f32)
     if gt.shape[0] == 0:
         raise IndexError("max(): Expected reduction dim 1 to have non-zero size")  # :199
+    fpn = variant == "fpn"
     inside = (anchor[:, 0] >= 0) & (anchor[:, 1] >= 0) & (anchor[:, 2] <= 1) & (anchor[:, 3] <= 1)
+    if fpn:
+        inside = np.ones(anchor.shape[0], dtype=bool)
     a_in = anchor[inside]
-    iou = pairwise_iou_eps(a_in, gt)                       # :198
+    iou = pairwise_iou_eps(a_in, gt, 0.0 if fpn else 1e-5)  # :198 / new_model.py:309
     iou_max = iou.max(axis=1)
     argmax = iou.argmax(axis=1).astype(np.int64)           # first index on ties
     gt_argmax = iou.argmax(axis=0).astype(np.int64)        # :206, first index on ties
     label = np.full(a_in.shape[0], -1, dtype=np.int64)
     label[iou_max < f32(0.3)] = 0                          # :202 fp32 compare
-    label[gt_argmax] = 1                                   # :213
+    if fpn:
+        label[(iou == iou.max(axis=0)[None, :]).any(axis=1)] = 1   # new_model.py:316-318, ties included
+    else:
+        label[gt_argmax] = 1                               # :213
     label[iou_max >= f32(0.7)] = 1                         # :216
     n_pos = int((label == 1).sum())
     n_neg = int((label == 0).sum())
@@ -313,8 +321,9 @@ def rpn_targets(gt: np.ndarray, anchor: np.ndarray, randperm) -> dict:
                 gt_argmax=np.nonzero(inside)[0][gt_argmax], n_pos=n_pos0, n_neg=n_neg0)
 
 
-def frcnn_targets(gt: np.ndarray, gt_label: np.ndarray, rois: np.ndarray, randperm) -> dict:
-    """models/model.py:127-179  ``FastRcnnTargetMaker.forward`` for one image.
+def frcnn_targets(gt: np.ndarray, gt_label: np.ndarray, rois: np.ndarray, randperm, variant: str = "vgg") -> dict:
+    """models/model.py:127-179  ``FastRcnnTargetMaker.forward`` for one image; ``variant="fpn"`` restates
+    models/new_model.py:153-206 (box_iou without eps, 512 samples with at most 128 positives).
 
     rois <- cat(rois, gt); IoU (with eps) vs gt; row max/argmax; cls = label[argmax]+1;
     n_pos = min(#(IoU>=0.5f), 32); pos/neg sampled with two randperm draws (always drawn);
@@ -322,16 +331,19 @@ def frcnn_targets(gt: np.ndarray, gt_label: np.ndarray, rois: np.ndarray, randpe
     """
     gt = np.asarray(gt, dtype=f32).reshape(-1, 4)
     rois = np.concatenate([np.asarray(rois, dtype=f32).reshape(-1, 4), gt], axis=0)      # :135
-    iou = pairwise_iou_eps(rois, gt)
+    fpn = variant == "fpn"
+    batch, max_pos = (512, 128) if fpn else (128, 32)
+    iou = pairwise_iou_eps(rois, gt, 0.0 if fpn else 1e-5)
     iou_max = iou.max(axis=1)
     argmax = iou.argmax(axis=1).astype(np.int64)
-    cls_all = np.asarray(gt_label)[argmax] + 1                                           # :141
+    # :141 adds 1 (labels are 0-based there); new_model.py:166 uses the labels as they are
+    cls_all = np.asarray(gt_label)[argmax] + (0 if fpn else 1)
     is_pos = iou_max >= f32(0.5)
-    n_pos = int(min(int(is_pos.sum()), 32))                                              # :144
+    n_pos = int(min(int(is_pos.sum()), max_pos))                                         # :144
     pos_idx = np.nonzero(is_pos)[0]
     perm = np.asarray(randperm(pos_idx.shape[0]))
     pos_idx = pos_idx[perm[:n_pos]]
-    n_neg = 128 - n_pos
+    n_neg = batch - n_pos
     neg_idx = np.nonzero((iou_max < f32(0.5)) & (iou_max >= f32(0.0)))[0]                # :153
     perm = np.asarray(randperm(neg_idx.shape[0]))
     neg_idx = neg_idx[perm[:n_neg]]

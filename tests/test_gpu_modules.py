@@ -128,3 +128,19 @@ def test_roi_pool_module_in_a_head_forward_backward(oracle):
     want = oracle.roi_pool_backward(go, wa, oracle.scale_rois(b, 37, 62), (1, 32, 37, 62))
     scale = np.abs(want).max()
     assert np.abs(feat.grad.cpu().numpy() - want).max() <= 1e-5 * scale
+
+
+def test_fpn_variant_target_maker_modules(oracle):
+    """models/new_model.py call pattern: RPNTargetMaker()(boxes, anchors), FRCNNTargetMaker()(boxes, labels, rois)."""
+    g = golden("targets_fpn")
+    hw = (320, 480)
+    anchors = dev(oracle.enumerate_anchors(hw))
+    gt, lab = synth.gt_boxes(7000, 5)
+    torch.manual_seed(7000)
+    label, tg = modules.fpn.RPNTargetMaker()(dev(gt), anchors)
+    assert label.dtype == torch.int64 and np.array_equal(label.cpu().numpy(), g["a_rpn_cls"].astype(np.int64))
+    rois, _ = synth.random_boxes(7050, 2000)
+    torch.manual_seed(7001)
+    fc, fr, fs = modules.fpn.FRCNNTargetMaker()(dev(gt), dev(lab + 1), dev(rois))
+    assert fc.shape == (512,) and np.array_equal(fc.cpu().numpy(), g["a_frcnn_cls"].astype(np.int64))
+    assert np.array_equal(fs.cpu().numpy(), g["a_frcnn_rois"])

@@ -162,3 +162,39 @@ def test_make_targets_single_sync_matches_sequential(oracle):
         assert np.array_equal(out["frcnn_cls"][i].cpu().numpy(), wf["cls"])
         assert np.array_equal(out["sample_rois"][i].cpu().numpy(), wf["sample_rois"])
         close(out["frcnn_reg"][i].cpu().numpy(), wf["reg"], atol=2e-5)
+
+
+# ------------------------------------------------------------------------------------ FPN-variant target makers
+FPN_CASES = [("a", (320, 480), 7000, 5, 7000), ("b", (600, 1000), 7001, 8, 7001), ("many", (320, 480), 7002, 150, 7002),
+             ("one", (160, 256), 7003, 1, 7003)]
+
+
+@pytest.mark.parametrize("name,hw,gseed,G,tseed", FPN_CASES)
+def test_fpn_variant_targets_reference_goldens(oracle, name, hw, gseed, G, tseed):
+    """models/new_model.py:153-206,299-349 through the same kernels with the variant knobs (eps-free IoU, no inside
+    filter, tie-inclusive low-quality match, 512 samples / <= 128 positives, labels used as they are)."""
+    g = golden("targets_fpn")
+    anchors = oracle.enumerate_anchors(hw)
+    gt, lab = synth.gt_boxes(gseed, G)
+    torch.manual_seed(tseed)
+    labels, reg = targets.rpn_targets(dev(gt[None]), None, anchors=dev(anchors), variant="fpn")
+    labels, reg = labels[0].cpu().numpy(), reg[0].cpu().numpy()
+    assert np.array_equal(labels, g[f"{name}_rpn_cls"].astype(np.int64))
+    close(reg[labels >= 0], g[f"{name}_rpn_reg_sampled"])
+    rois, _ = synth.random_boxes(tseed + 50, 2000)
+    torch.manual_seed(tseed + 1)
+    cls, freg, srois, kidx, n = targets.frcnn_targets(dev(rois[None]), None, dev(gt[None]), None, dev((lab + 1)[None]),
+                                                      variant="fpn")
+    assert int(n[0]) == 512 and cls.shape == (1, 512)
+    assert np.array_equal(cls[0].cpu().numpy(), g[f"{name}_frcnn_cls"].astype(np.int64))
+    assert np.array_equal(srois[0].cpu().numpy(), g[f"{name}_frcnn_rois"])
+    close(freg[0].cpu().numpy(), g[f"{name}_frcnn_reg"], atol=2e-5)
+
+
+def test_fpn_variant_tie_inclusive_zero_iou(oracle):
+    """A GT overlapping no anchor: every anchor with IoU == 0 for it becomes positive (torch.where(iou == max))."""
+    g = golden("targets_fpn")
+    gt = np.array([[0.2, 0.2, 0.6, 0.7], [5.0, 5.0, 5.1, 5.1]], np.float32)
+    torch.manual_seed(9)
+    labels, _ = targets.rpn_targets(dev(gt[None]), None, anchors=dev(g["far_anchors"]), variant="fpn")
+    assert np.array_equal(labels[0].cpu().numpy(), g["far_rpn_cls"].astype(np.int64))

@@ -226,3 +226,32 @@ def test_suppress_bit_exact_from_identical_inputs(oracle, C, seed, thres):
     assert np.array_equal(ss, g[f"sup{C}_score_{thres}"])
     assert np.array_equal(bb, g[f"sup{C}_bbox_{thres}"])
     assert len(ll) > 0
+
+
+# ------------------------------------------------------------------------------ FPN-variant target makers
+FPN_CASES = [("a", (320, 480), 7000, 5, 7000), ("b", (600, 1000), 7001, 8, 7001), ("many", (320, 480), 7002, 150, 7002),
+             ("one", (160, 256), 7003, 1, 7003)]
+
+
+@pytest.mark.parametrize("name,hw,gseed,G,tseed", FPN_CASES)
+def test_fpn_variant_targets(oracle, name, hw, gseed, G, tseed):
+    """models/new_model.py:153-206,299-349: eps-free box_iou, no inside filter, tie-inclusive match, 512/128 sampling."""
+    g = golden("targets_fpn")
+    anchors = oracle.enumerate_anchors(hw)
+    gt, lab = synth.gt_boxes(gseed, G)
+    r = oracle.rpn_targets(gt, anchors, oracle.HostRandperm(tseed), variant="fpn")
+    assert np.array_equal(r["labels"], g[f"{name}_rpn_cls"].astype(np.int64))
+    close(r["reg"][r["labels"] >= 0], g[f"{name}_rpn_reg_sampled"])
+    rois, _ = synth.random_boxes(tseed + 50, 2000)
+    f = oracle.frcnn_targets(gt, lab + 1, rois, oracle.HostRandperm(tseed + 1), variant="fpn")
+    assert f["cls"].shape == (512,)
+    assert np.array_equal(f["cls"], g[f"{name}_frcnn_cls"].astype(np.int64))
+    assert np.array_equal(f["sample_rois"], g[f"{name}_frcnn_rois"])
+    close(f["reg"], g[f"{name}_frcnn_reg"], atol=2e-5)
+
+
+def test_fpn_variant_tie_inclusive_zero_iou(oracle):
+    g = golden("targets_fpn")
+    gt = np.array([[0.2, 0.2, 0.6, 0.7], [5.0, 5.0, 5.1, 5.1]], np.float32)
+    r = oracle.rpn_targets(gt, g["far_anchors"], oracle.HostRandperm(9), variant="fpn")
+    assert np.array_equal(r["labels"], g["far_rpn_cls"].astype(np.int64))
