@@ -151,6 +151,37 @@ __global__ void __launch_bounds__(256)
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// Evaluation hand-off (test.py:68-88 + evaluation/coco_eval.py:70-92,156-158): scale the normalised boxes to pixels,
+// optionally convert xyxy -> xywh, and pack the first max_det detections of every image into fixed-shape rows
+// (x, y, x2|w, y2|h, score, label) for ONE tensor all-gather instead of a pickled one.
+__global__ void __launch_bounds__(128)
+    pack_detections_kernel(const float4* __restrict__ det_boxes, const int32_t* __restrict__ det_labels,
+                           const float* __restrict__ det_scores, const int32_t* __restrict__ det_count, int cap,
+                           int max_det, const float2* __restrict__ image_wh, int xywh, float* __restrict__ out,
+                           int32_t* __restrict__ out_count) {
+    const int b = blockIdx.x;
+    const int n = min(min(det_count[b], cap), max_det);
+    const float2 wh = image_wh ? image_wh[b] : make_float2(1.f, 1.f);
+    for (int j = threadIdx.x; j < max_det; j += blockDim.x) {
+        float* o = out + ((size_t)b * max_det + j) * 6;
+        if (j < n) {
+            const float4 bx = det_boxes[(size_t)b * cap + j];
+            const float x1 = __fmul_rn(bx.x, wh.x), y1 = __fmul_rn(bx.y, wh.y);
+            const float x2 = __fmul_rn(bx.z, wh.x), y2 = __fmul_rn(bx.w, wh.y);
+            o[0] = x1;
+            o[1] = y1;
+            o[2] = xywh ? __fsub_rn(x2, x1) : x2;
+            o[3] = xywh ? __fsub_rn(y2, y1) : y2;
+            o[4] = det_scores[(size_t)b * cap + j];
+            o[5] = (float)det_labels[(size_t)b * cap + j];
+        } else {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) o[q] = 0.f;
+        }
+    }
+    if (threadIdx.x == 0) out_count[b] = n;
+}
+
 }  // namespace frr
 
 extern "C" {
@@ -168,6 +199,22 @@ int frr_decode_classwise(const float* cls_logits, const float* reg, const float*
                                                                                (float4*)boxes);
     count_launch();
     FRR_CHECK_LAUNCH("decode_classwise_kernel");
+    return FRR_OK;
+}
+
+int frr_pack_detections(const float* det_boxes, const int32_t* det_labels, const float* det_scores, const int32_t* det_count,
+                        int B, int cap, int max_det, const float* image_wh, int xywh, float* out, int32_t* out_count,
+                        frr_stream_t stream) {
+    using namespace frr;
+    FRR_CHECK_ARG(B >= 0 && cap >= 0 && max_det >= 1, "frr_pack_detections: bad sizes");
+    if (B == 0) return FRR_OK;
+    FRR_CHECK_ARG(det_boxes && det_labels && det_scores && det_count && out && out_count, "frr_pack_detections: null pointer");
+    FRR_CHECK_ARG(aligned16(det_boxes) && (image_wh == nullptr || (reinterpret_cast<uintptr_t>(image_wh) & 7u) == 0),
+                  "frr_pack_detections: det_boxes must be 16-byte aligned, image_wh 8-byte aligned");
+    pack_detections_kernel<<<B, 128, 0, (cudaStream_t)stream>>>((const float4*)det_boxes, det_labels, det_scores, det_count,
+                                                                cap, max_det, (const float2*)image_wh, xywh, out, out_count);
+    count_launch();
+    FRR_CHECK_LAUNCH("pack_detections_kernel");
     return FRR_OK;
 }
 

@@ -27,19 +27,13 @@ def shard_range(n_items: int, rank: int | None = None, world_size: int | None = 
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def pack_detections(det_boxes, det_labels, det_scores, det_count, max_det: int):
+def pack_detections(det_boxes, det_labels, det_scores, det_count, max_det: int, image_wh=None, xywh: bool = False):
     """[B,cap,4] boxes, [B,cap] int32 labels, [B,cap] scores, [B] counts (class-major order as produced by
-    ``ops.class_nms``) -> ([B,max_det,6] fp32 rows (x1,y1,x2,y2,score,label), [B] int32 counts), truncated to the
-    first ``max_det`` detections of every image; rows past the count are zero."""
-    B, cap = det_labels.shape
-    m = min(int(max_det), cap)
-    out = torch.zeros((B, int(max_det), 6), dtype=torch.float32, device=det_boxes.device)
-    cnt = det_count.clamp(max=m).to(torch.int32)
-    live = (torch.arange(m, device=det_boxes.device)[None, :] < cnt[:, None]).to(torch.float32)[..., None]
-    out[:, :m, 0:4] = det_boxes[:, :m] * live
-    out[:, :m, 4:5] = det_scores[:, :m, None] * live
-    out[:, :m, 5:6] = det_labels[:, :m, None].to(torch.float32) * live
-    return out, cnt
+    ``ops.class_nms``) -> ([B,max_det,6] fp32 rows (x, y, x2|w, y2|h, score, label), [B] int32 counts): the first
+    ``max_det`` detections of every image, rows past the count zero; optional pixel scaling and xyxy -> xywh
+    (test.py:68-88, evaluation/coco_eval.py:156-158).  One ``frr_pack_detections`` kernel."""
+    from . import ops
+    return ops.pack_detections(det_boxes, det_labels, det_scores, det_count, max_det, image_wh=image_wh, xywh=xywh)
 
 
 def gather_detections(packed, counts, image_ids, group=None, equal_batch: bool = False):

@@ -445,3 +445,24 @@ def class_nms(prob, boxes, num_classes: int, score_thres: float = 0.05, iou_thr:
                                      float(np.float32(score_thres)), float(iou_thr), cap, db.data_ptr(), dl.data_ptr(),
                                      ds.data_ptr(), dc.data_ptr(), ws.data_ptr() + off, nbytes, _stream()), "frr_class_nms")
     return db, dl, ds, dc
+
+
+def pack_detections(det_boxes, det_labels, det_scores, det_count, max_det: int, image_wh=None, xywh: bool = False):
+    """Evaluation hand-off (test.py:68-88, evaluation/coco_eval.py:156-158): [B,cap,4] / [B,cap] / [B,cap] / [B] ->
+    ([B,max_det,6] rows (x, y, x2|w, y2|h, score, label) scaled by ``image_wh [B,2]`` = (w, h), int32 counts [B])."""
+    lib = _lib.load()
+    det_boxes = _req(det_boxes, "det_boxes")
+    det_labels = _req(det_labels, "det_labels", torch.int32)
+    det_scores = _req(det_scores, "det_scores")
+    det_count = _req(det_count, "det_count", torch.int32)
+    if image_wh is not None:
+        image_wh = _req(image_wh, "image_wh")
+    B, cap = det_labels.shape
+    dev = det_boxes.device
+    with torch.cuda.device(dev):
+        out = torch.empty((B, int(max_det), 6), dtype=torch.float32, device=dev)
+        cnt = torch.empty((B,), dtype=torch.int32, device=dev)
+        _lib.check(lib.frr_pack_detections(det_boxes.data_ptr(), det_labels.data_ptr(), det_scores.data_ptr(),
+                                           det_count.data_ptr(), B, cap, int(max_det), _ptr(image_wh), int(bool(xywh)),
+                                           out.data_ptr(), cnt.data_ptr(), _stream()), "frr_pack_detections")
+    return out, cnt

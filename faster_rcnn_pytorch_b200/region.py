@@ -21,6 +21,23 @@ PROPOSAL_MODES = {"train": (12000, 2000), "test": (6000, 300)}   # models/model.
 RPN_NMS_THRESH = 0.7                                              # models/model.py:53
 
 
+def rpn_head_views(cls_map, reg_map):
+    """RPN head hand-off (models/model.py:82-83): ``cls_map [B,2A,H,W]``, ``reg_map [B,4A,H,W]`` (the outputs of the
+    two 1x1 convs) -> ``cls [B,H*W*A,2]``, ``reg [B,H*W*A,4]`` in the reference's anchor order.
+
+    The reference does ``permute(0,2,3,1).contiguous().view(B,-1,k)``: a copy of 6N floats per image.  When the convs
+    run in ``torch.channels_last`` the permuted tensor IS contiguous and the views below alias the conv outputs
+    (zero copy: ``[B,H,W,A*4]`` is ``[B,N,4]``); for NCHW-contiguous maps this falls back to the reference's copy."""
+    B = cls_map.shape[0]
+    cls = cls_map.permute(0, 2, 3, 1)
+    reg = reg_map.permute(0, 2, 3, 1)
+    if not cls.is_contiguous():
+        cls = cls.contiguous()
+    if not reg.is_contiguous():
+        reg = reg.contiguous()
+    return cls.view(B, -1, 2), reg.view(B, -1, 4)
+
+
 def rpn_proposals(cls, reg, image_hw=None, mode: str = "train", anchors=None, stride: int = 16, table=None,
                   pre_nms_top_k: int | None = None, post_nms_top_k: int | None = None,
                   nms_thresh: float = RPN_NMS_THRESH, cluster_size: int = 0, return_all: bool = False):

@@ -218,6 +218,17 @@ int frr_class_nms(const float* prob, const float* boxes, const int32_t* roi_coun
                   float* det_scores, int32_t* det_count, void* workspace, size_t workspace_bytes,
                   frr_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Evaluation hand-off -- test.py:68-88 (boxes * (w,h,w,h)), evaluation/coco_eval.py:70-92,156-158 (convert_to_xywh).
+ *     Packs the first max_det detections of every image into fixed-shape rows (x, y, x2|w, y2|h, score, label)
+ *     [B,max_det,6] (zero padded) + int32 counts, ready for one tensor all-gather instead of the pickled
+ *     all_gather of util/misc.py:89-129.  image_wh [B,2] device floats (w, h) or NULL (keep normalised).
+ * ------------------------------------------------------------------------------------- */
+int frr_pack_detections(const float* det_boxes /* [B,cap,4] */, const int32_t* det_labels /* [B,cap] */,
+                        const float* det_scores /* [B,cap] */, const int32_t* det_count /* [B] */, int B, int cap,
+                        int max_det, const float* image_wh, int xywh, float* out /* [B,max_det,6] */,
+                        int32_t* out_count /* [B] */, frr_stream_t stream);
+
 #ifdef __cplusplus
 #pragma GCC visibility pop
 }

@@ -98,3 +98,29 @@ def test_class_nms_iou_threshold_is_compared_in_double(oracle):
     prob = np.array([[0.1, 0.9], [0.2, 0.8]], np.float32)
     bb, ll, ss = modules.suppress(dev(boxes.reshape(2, C * 4)), dev(prob), C, 0.05)
     assert ll.tolist() == [0] and ss.tolist() == [np.float32(0.9)]
+
+
+def test_pack_detections_kernel_scaling_xywh_and_truncation():
+    """Evaluation hand-off: pixel scaling (test.py:68-71), xyxy -> xywh (coco_eval.py:156-158), fixed-shape rows."""
+    from faster_rcnn_pytorch_b200 import dist as fdist
+    rs = np.random.RandomState(5)
+    B, cap = 4, 30
+    counts = np.asarray([30, 12, 0, 7], np.int32)
+    boxes = rs.uniform(0, 1, (B, cap, 4)).astype(np.float32)
+    labels = rs.randint(0, 80, (B, cap)).astype(np.int32)
+    scores = rs.uniform(0.05, 1, (B, cap)).astype(np.float32)
+    wh = np.asarray([[1333, 800], [640, 480], [500, 375], [1000, 600]], np.float32)
+    for max_det, xywh, use_wh in [(100, True, True), (10, False, True), (10, True, False)]:
+        out, cnt = fdist.pack_detections(dev(boxes), dev(labels), dev(scores), dev(counts), max_det,
+                                         image_wh=dev(wh) if use_wh else None, xywh=xywh)
+        out, cnt = out.cpu().numpy(), cnt.cpu().numpy()
+        for i in range(B):
+            k = min(int(counts[i]), max_det, cap)
+            assert cnt[i] == k
+            sc = np.asarray([wh[i, 0], wh[i, 1], wh[i, 0], wh[i, 1]], np.float32) if use_wh else np.ones(4, np.float32)
+            b = boxes[i, :k] * sc
+            if xywh:
+                b = np.stack([b[:, 0], b[:, 1], b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]], axis=1)
+            assert np.array_equal(out[i, :k, :4], b.astype(np.float32))
+            assert np.array_equal(out[i, :k, 4], scores[i, :k]) and np.array_equal(out[i, :k, 5], labels[i, :k].astype(np.float32))
+            assert (out[i, k:] == 0).all()

@@ -307,3 +307,32 @@ def test_nms_indirect_order_matches_gathered_boxes(oracle):
                                                keep.data_ptr(), cnt.data_ptr(), rois.data_ptr(), 0, unit,
                                                torch.cuda.current_stream().cuda_stream), "frr_nms_sorted_indirect")
         assert torch.equal(keep, want_keep) and torch.equal(cnt, want_cnt) and torch.equal(rois, want_rois)
+
+
+def test_rpn_head_views_zero_copy_in_channels_last(oracle):
+    """models/model.py:79-83 hand-off: with channels_last conv outputs the [B,N,2] / [B,N,4] views alias the conv
+    outputs (no permute copy) and feed the proposal layer with the same result as the reference's copy path."""
+    from faster_rcnn_pytorch_b200 import region
+    torch.manual_seed(0)
+    B, A, hw = 2, 9, (160, 256)
+    H, W = hw[0] // 16, hw[1] // 16
+    x = torch.randn(B, 64, H, W, device=DEV)
+    cls_conv = torch.nn.Conv2d(64, 2 * A, 1).to(DEV)
+    reg_conv = torch.nn.Conv2d(64, 4 * A, 1).to(DEV)
+    with torch.no_grad():
+        ref_cls = cls_conv(x).permute(0, 2, 3, 1).contiguous().view(B, -1, 2)        # the reference's path
+        ref_reg = reg_conv(x).permute(0, 2, 3, 1).contiguous().view(B, -1, 4)
+        xcl = x.contiguous(memory_format=torch.channels_last)
+        cm = cls_conv.to(memory_format=torch.channels_last)(xcl)
+        rm = reg_conv.to(memory_format=torch.channels_last)(xcl)
+    assert cm.is_contiguous(memory_format=torch.channels_last)
+    cls, reg = region.rpn_head_views(cm, rm)
+    assert cls.data_ptr() == cm.data_ptr() and reg.data_ptr() == rm.data_ptr()        # zero copy
+    assert cls.shape == (B, H * W * A, 2) and reg.shape == (B, H * W * A, 4)
+    torch.testing.assert_close(cls, ref_cls, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(reg, ref_reg, rtol=1e-4, atol=1e-5)
+    c2, r2 = region.rpn_head_views(cls_conv(x).contiguous(), reg_conv(x).contiguous())     # NCHW: copy fallback
+    torch.testing.assert_close(c2, ref_cls, rtol=1e-4, atol=1e-5)
+    rois, cnt = region.rpn_proposals(cls, reg * 0.1, image_hw=hw, mode="test")
+    rois2, cnt2 = region.rpn_proposals(cls.clone(), (reg * 0.1).clone(), image_hw=hw, mode="test")
+    assert torch.equal(rois, rois2) and torch.equal(cnt, cnt2)
