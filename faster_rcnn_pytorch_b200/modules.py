@@ -118,6 +118,21 @@ class fpn:
     """Drop-ins for the target makers of the FPN variant, models/new_model.py (what main.py trains today).  Same class
     names and forward signatures as there (tensors, not per-image lists); normalised xyxy boxes like the reference."""
 
+    PROPOSAL_MODES = {"train": (4000, 1000), "test": (2000, 1000)}   # models/new_model.py:52-56
+    MIN_SIZE = float(np.float32(10 / 1000))                          # models/new_model.py:21,66 (fp32 compare)
+
+    @staticmethod
+    def region_proposal(cls, reg, anchor, mode):
+        """Proposal part of ``RegionProposalNetwork.forward`` (models/new_model.py:46-83): cls [N,2] logits and reg [N,4]
+        of all pyramid levels concatenated, anchor [N,4] normalised (torchvision AnchorGenerator / (w,h,w,h)) ->
+        rois [<=1000, 4].  Same kernels as the VGG variant with min_size 10/1000 and 4000|2000 -> 1000."""
+        pre_k, post_k = fpn.PROPOSAL_MODES["test" if mode == "test" else "train"]
+        anchor = _as_anchor_tensor(anchor, reg.device)
+        rois, count = region.rpn_proposals(cls.detach().unsqueeze(0).to(torch.float32),
+                                           reg.detach().unsqueeze(0).to(torch.float32), anchors=anchor, mode="train",
+                                           pre_nms_top_k=pre_k, post_nms_top_k=post_k, min_size=fpn.MIN_SIZE)
+        return rois[0, :int(count[0])]
+
     class RPNTargetMaker(nn.Module):
         """models/new_model.py:299-349.  ``forward(boxes [G,4], anchors [N,4])`` -> (label int64 [N], tg_cxywh [N,4])."""
 

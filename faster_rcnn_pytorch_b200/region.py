@@ -40,12 +40,15 @@ def rpn_head_views(cls_map, reg_map):
 
 def rpn_proposals(cls, reg, image_hw=None, mode: str = "train", anchors=None, stride: int = 16, table=None,
                   pre_nms_top_k: int | None = None, post_nms_top_k: int | None = None,
-                  nms_thresh: float = RPN_NMS_THRESH, cluster_size: int = 0, return_all: bool = False):
-    """cls [B,N,2] logits (or [B,N] fg scores), reg [B,N,4] -> rois [B,post,4] (zero padded), count int32 [B]."""
+                  nms_thresh: float = RPN_NMS_THRESH, cluster_size: int = 0, return_all: bool = False,
+                  min_size: float = ops._MIN_SIZE):
+    """cls [B,N,2] logits (or [B,N] fg scores), reg [B,N,4] -> rois [B,post,4] (zero padded), count int32 [B].
+    ``min_size`` is the normalised side threshold (models/model.py:39: 1/1000; models/new_model.py:66: 10/1000)."""
     pre_k, post_k = PROPOSAL_MODES[mode]
     pre_k = pre_k if pre_nms_top_k is None else int(pre_nms_top_k)
     post_k = post_k if post_nms_top_k is None else int(post_nms_top_k)
-    boxes, scores, valid = ops.rpn_decode(reg, cls, image_hw=image_hw, anchors=anchors, stride=stride, table=table)
+    boxes, scores, valid = ops.rpn_decode(reg, cls, image_hw=image_hw, anchors=anchors, stride=stride, table=table,
+                                          min_size=min_size)
     k = min(pre_k, boxes.shape[1])
     top = ops.topk_desc(scores, k, valid=valid, boxes=boxes, want_cidx=return_all)
     keep, count, rois = ops.nms_sorted(top["boxes"], nms_thresh, max_keep=post_k, counts=top["count"],

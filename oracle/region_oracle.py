@@ -205,7 +205,7 @@ def sort_desc(scores: np.ndarray) -> np.ndarray:
     return np.argsort(-np.asarray(scores, dtype=f32).astype(np.float64), kind="stable").astype(np.int64)
 
 
-def region_proposal(cls_logits, reg, anchor, mode: str = "train", scores=None):
+def region_proposal(cls_logits, reg, anchor, mode: str = "train", scores=None, pre_k=None, post_k=None, min_size: float = 1.0):
     """models/model.py:17-58  full proposal layer for ONE image.
 
     Returns a dict with every intermediate the CUDA path is checked against:
@@ -215,10 +215,11 @@ def region_proposal(cls_logits, reg, anchor, mode: str = "train", scores=None):
     top-k list) and ``rois``.
     ``scores`` overrides the softmax (used to feed identical fp32 scores to both sides).
     """
-    pre_k, post_k = PROPOSAL_MODES[mode]
+    if pre_k is None or post_k is None:
+        pre_k, post_k = PROPOSAL_MODES[mode]        # models/new_model.py:52-56 passes 4000|2000 -> 1000, min_size 10
     score = fg_softmax(cls_logits) if scores is None else np.asarray(scores, dtype=f32)
     boxes = decode_clip(reg, anchor)
-    valid = min_size_mask(boxes)
+    valid = min_size_mask(boxes, min_size)
     comp_boxes = boxes[valid]
     comp_score = score[valid]
     src = np.nonzero(valid)[0].astype(np.int64)

@@ -67,5 +67,62 @@ def main():
     print("targets_fpn.npz", os.path.getsize(os.path.join(HERE, "targets_fpn.npz")))
 
 
+
+
+def proposals():
+    """RegionProposalNetwork.forward of models/new_model.py on a small synthetic pyramid: stores the head outputs,
+    the torchvision anchors and the reference's rois (tests/golden/proposal_fpn.npz)."""
+    torch.Tensor.get_device = lambda self: self.device
+    sys.modules.setdefault("gdown", types.ModuleType("gdown"))
+    sys.path.insert(0, "/root/reference")
+    import models.new_model as nm
+    g = {}
+    for name, hw, seed, mode in [("train", (128, 192), 8000, "train"), ("test", (160, 160), 8001, "test")]:
+        torch.manual_seed(seed)
+        rpn = nm.RegionProposalNetwork().eval()
+        with torch.no_grad():
+            for m in (rpn.rpn_head.cls_layer, rpn.rpn_head.reg_layer):
+                m.weight.normal_(0, 0.5)       # spread the scores / deltas (the default 0.01 init gives thousands of ties)
+        x = torch.zeros(1, 3, hw[0], hw[1])
+        feats = {str(l): torch.randn(1, 256, -(-hw[0] // s), -(-hw[1] // s)) for l, s in enumerate((4, 8, 16, 32, 64))}
+        with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+            cls, reg, rois, anchor = rpn(x, feats, mode)
+        g[f"{name}_cls"] = cls.numpy().copy()
+        rg = (reg.numpy() * 0.05).astype(np.float32)                   # keep exp() of the deltas tame
+        rg[::97, 2] = -6.0                                              # a few boxes thinner than min_size 10/1000
+        g[f"{name}_reg"] = rg
+        g[f"{name}_anchor"] = anchor.numpy().copy()
+        # the reference's own proposal arithmetic (models/new_model.py:46-83) on the stored (scaled) deltas and on
+        # tie-free scores (the reference's sort order of equal scores is unspecified, SURVEY section 8c)
+        import utils.util as U
+        import torchvision
+        sc = torch.softmax(cls, dim=-1)[..., 1].numpy().copy()
+        for _ in range(64):
+            _, first = np.unique(sc, return_index=True)
+            dup = np.ones(len(sc), bool); dup[first] = False
+            if not dup.any():
+                break
+            sc[dup] = np.nextafter(sc[dup], np.float32(2.0))
+        assert len(np.unique(sc)) == len(sc)
+        sc = torch.from_numpy(sc)
+        roi = U.cxcy_to_xy(U.decode(torch.from_numpy(g[f"{name}_reg"]), U.xy_to_cxcy(anchor))).clamp(0, 1)
+        ws, hs = roi[:, 2] - roi[:, 0], roi[:, 3] - roi[:, 1]
+        keep = (hs >= (10 / 1000)) & (ws >= (10 / 1000))
+        roi_c, sc_c = roi[keep], sc[keep]
+        ss, si = sc_c.sort(descending=True)
+        pre_k, post_k = (4000, 1000) if mode == "train" else (2000, 1000)
+        k = min(pre_k, si.numel())
+        kp = torchvision.ops.nms(roi_c[si[:k]], ss[:k], 0.7)[:post_k]
+        g[f"{name}_score"] = sc.numpy().copy()
+        g[f"{name}_boxes"] = roi.numpy().copy()              # the reference's decoded + clamped boxes
+        g[f"{name}_valid"] = keep.numpy().copy()
+        g[f"{name}_topk_idx"] = si[:k].numpy().astype(np.int32)
+        g[f"{name}_keep"] = kp.numpy().astype(np.int32)
+        g[f"{name}_rois"] = roi_c[si[:k]][kp].numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "proposal_fpn.npz"), **g)
+    print("proposal_fpn.npz", os.path.getsize(os.path.join(HERE, "proposal_fpn.npz")))
+
+
 if __name__ == "__main__":
     main()
+    proposals()

@@ -336,3 +336,42 @@ def test_rpn_head_views_zero_copy_in_channels_last(oracle):
     rois, cnt = region.rpn_proposals(cls, reg * 0.1, image_hw=hw, mode="test")
     rois2, cnt2 = region.rpn_proposals(cls.clone(), (reg * 0.1).clone(), image_hw=hw, mode="test")
     assert torch.equal(rois, rois2) and torch.equal(cnt, cnt2)
+
+
+# ------------------------------------------------------------------------------------ FPN-variant proposal layer
+@pytest.mark.parametrize("name,mode", [("train", "train"), ("test", "test")])
+def test_fpn_variant_proposals_reference_goldens(oracle, name, mode):
+    """models/new_model.py:46-83 (torchvision 5-level anchors, min_size 10/1000, 4000|2000 -> 1000): the reference's own
+    fp32 boxes / scores -> GPU top-k -> GPU NMS == the reference's keep list; decode within 1e-5."""
+    from faster_rcnn_pytorch_b200 import modules
+    g = golden("proposal_fpn")
+    pre_k, post_k = (4000, 1000) if mode == "train" else (2000, 1000)
+    min_size = float(np.float32(10 / 1000))
+    boxes, scores, valid = ops.rpn_decode(dev(g[f"{name}_reg"][None]), dev(g[f"{name}_score"][None]),
+                                          anchors=dev(g[f"{name}_anchor"]), min_size=min_size)
+    np.testing.assert_allclose(boxes[0].cpu().numpy(), g[f"{name}_boxes"], rtol=RTOL, atol=1e-6)
+    assert np.array_equal(valid[0].cpu().numpy().astype(bool), oracle.min_size_mask(boxes[0].cpu().numpy(), 10.0))
+    r = ops.topk_desc(dev(g[f"{name}_score"][None]), pre_k, valid=dev(g[f"{name}_valid"][None].astype(np.uint8)),
+                      boxes=dev(g[f"{name}_boxes"][None]), want_cidx=True)
+    n = int(r["count"][0])
+    assert np.array_equal(r["cidx"][0, :n].cpu().numpy(), g[f"{name}_topk_idx"])
+    keep, cnt, rois = ops.nms_sorted(r["boxes"], 0.7, max_keep=post_k, counts=r["count"], unit_boxes=True)
+    k = keep[0, :int(cnt[0])].cpu().numpy()
+    assert np.array_equal(k, g[f"{name}_keep"])
+    assert np.array_equal(rois[0, :len(k)].cpu().numpy(), g[f"{name}_rois"])
+    # the drop-in call (logits in, ragged rois out) runs the same kernels end to end
+    out = modules.fpn.region_proposal(dev(g[f"{name}_cls"]), dev(g[f"{name}_reg"]), dev(g[f"{name}_anchor"]), mode)
+    assert out.shape[1] == 4 and 0 < out.shape[0] <= post_k
+
+
+def test_topk_more_than_65536_anchors_takes_the_general_kernel(oracle):
+    """A full-size FPN pyramid (800x1333: 267 069 anchors) is beyond the u16-index fast path."""
+    rs = np.random.RandomState(12)
+    N, k = 267069, 4000
+    scores = synth.unique_scores(rs, N)
+    valid = (rs.uniform(size=N) > 0.01)
+    r = ops.topk_desc(dev(scores[None]), k, valid=dev(valid[None].astype(np.uint8)), want_cidx=True)
+    order, idx = _oracle_topk(oracle, scores, valid, k)
+    assert int(r["count"][0]) == k
+    assert np.array_equal(r["idx"][0].cpu().numpy(), idx)
+    assert np.array_equal(r["cidx"][0].cpu().numpy(), order)

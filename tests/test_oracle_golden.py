@@ -255,3 +255,21 @@ def test_fpn_variant_tie_inclusive_zero_iou(oracle):
     gt = np.array([[0.2, 0.2, 0.6, 0.7], [5.0, 5.0, 5.1, 5.1]], np.float32)
     r = oracle.rpn_targets(gt, g["far_anchors"], oracle.HostRandperm(9), variant="fpn")
     assert np.array_equal(r["labels"], g["far_rpn_cls"].astype(np.int64))
+
+
+@pytest.mark.parametrize("name,mode", [("train", "train"), ("test", "test")])
+def test_fpn_variant_proposals(oracle, name, mode):
+    """models/new_model.py:46-83: min_size 10/1000, 4000|2000 -> 1000, torchvision multi-level anchors."""
+    g = golden("proposal_fpn")
+    pre_k, post_k = (4000, 1000) if mode == "train" else (2000, 1000)
+    boxes = oracle.decode_clip(g[f"{name}_reg"], g[f"{name}_anchor"])
+    close(boxes, g[f"{name}_boxes"])
+    valid = oracle.min_size_mask(g[f"{name}_boxes"], 10.0)
+    assert np.array_equal(valid, g[f"{name}_valid"]) and not valid.all()
+    # index-valued stages from the reference's own fp32 boxes and scores
+    comp = g[f"{name}_boxes"][valid]
+    order = oracle.sort_desc(g[f"{name}_score"][valid])[:pre_k]
+    assert np.array_equal(order, g[f"{name}_topk_idx"])
+    keep = oracle.nms(comp[order], -np.arange(len(order), dtype=np.float32), 0.7)[:post_k]
+    assert np.array_equal(keep, g[f"{name}_keep"])
+    assert np.array_equal(comp[order][keep], g[f"{name}_rois"])
