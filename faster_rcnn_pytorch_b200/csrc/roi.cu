@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(256)
         const int ph = bin / PW, pw = bin - ph * PW;
         const float* r = rois + 5 * k;
         const int b = (int)r[0];
+        if (b < 0) continue;  // masked roi (belongs to another pyramid level): its output row is written elsewhere
         const float* base = nhwc ? feat + (size_t)b * H * W * C + c : feat + ((size_t)b * C + c) * H * W;
         const size_t ps = nhwc ? (size_t)C : 1;  // pixel stride
         if (!kAlign) {
@@ -227,6 +228,7 @@ __global__ void __launch_bounds__(256)
         const size_t k = o / ((size_t)bins * C);
         const float* r = rois + 5 * k;
         const int b = (int)r[0];
+        if (b < 0) continue;  // masked roi
         float* base = nhwc ? grad_in + (size_t)b * H * W * C + c : grad_in + ((size_t)b * C + c) * H * W;
         const size_t ps = nhwc ? (size_t)C : 1;
         const float go = grad_out[o];
@@ -351,9 +353,46 @@ static int roi_backward(const float* grad_out, const int32_t* argmax, const floa
     return FRR_OK;
 }
 
+// MultiScaleRoIAlign level assignment (TV ops/poolers.py LevelMapper, used by models/new_model.py:127,143):
+//   lvl = clamp(floor(lvl0 + log2(sqrt(area) / s0) + 1e-6), k_min, k_max) - k_min
+// and, for every level l, a copy of the rois whose batch index is kept for rois of that level and -1 otherwise: the
+// per-level RoIAlign launches then skip foreign rois and all write into ONE [K,C,7,7] output, no index gathers.
+__global__ void __launch_bounds__(256)
+    fpn_level_rois_kernel(const float* __restrict__ rois, int K, int k_min, int k_max, float lvl0, float s0, int L,
+                          int32_t* __restrict__ levels, float* __restrict__ rois_lvl) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const float* r = rois + 5 * (size_t)k;
+    const float area = __fmul_rn(__fsub_rn(r[3], r[1]), __fsub_rn(r[4], r[2]));
+    const float s = sqrtf(area);
+    float t = floorf(__fadd_rn(__fadd_rn(lvl0, log2f(__fdiv_rn(s, s0))), 1e-6f));
+    t = fminf(fmaxf(t, (float)k_min), (float)k_max);  // NaN (negative area) -> k_min, like torch.clamp + to(int64) is not defined
+    const int lvl = (int)t - k_min;
+    levels[k] = lvl;
+    for (int l = 0; l < L; ++l) {
+        float* o = rois_lvl + ((size_t)l * K + k) * 5;
+        o[0] = (l == lvl) ? r[0] : -1.0f;
+        o[1] = r[1]; o[2] = r[2]; o[3] = r[3]; o[4] = r[4];
+    }
+}
+
 }  // namespace frr
 
 extern "C" {
+
+int frr_fpn_level_rois(const float* rois5, int K, int k_min, int k_max, int canonical_level, float canonical_scale, int L,
+                       int32_t* levels, float* rois_per_level, frr_stream_t stream) {
+    using namespace frr;
+    FRR_CHECK_ARG(K >= 0 && L >= 1 && k_max >= k_min && k_max - k_min + 1 == L && canonical_scale > 0.f,
+                  "frr_fpn_level_rois: bad arguments (L must equal k_max - k_min + 1)");
+    if (K == 0) return FRR_OK;
+    FRR_CHECK_ARG(rois5 && levels && rois_per_level, "frr_fpn_level_rois: null pointer");
+    fpn_level_rois_kernel<<<(K + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rois5, K, k_min, k_max, (float)canonical_level,
+                                                                            canonical_scale, L, levels, rois_per_level);
+    count_launch();
+    FRR_CHECK_LAUNCH("fpn_level_rois_kernel");
+    return FRR_OK;
+}
 
 int frr_roi_pool_fwd(const float* feat, const float* rois, int K, int B, int C, int H, int W, int PH, int PW,
                      float spatial_scale, int channels_last, float* out, int32_t* argmax, frr_stream_t stream) {

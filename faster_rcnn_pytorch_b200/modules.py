@@ -15,7 +15,7 @@ import torch.nn as nn
 
 from . import ops, region, targets
 
-__all__ = ["nms", "roi_pool", "roi_align", "RoIPool", "RoIAlign", "RegionProposal", "RPNTargetMaker",
+__all__ = ["nms", "roi_pool", "roi_align", "RoIPool", "RoIAlign", "MultiScaleRoIAlign", "RegionProposal", "RPNTargetMaker",
            "FastRcnnTargetMaker", "predict_tail", "suppress", "fpn"]
 
 roi_pool = ops.roi_pool
@@ -67,6 +67,23 @@ class RoIAlign(nn.Module):
 
     def forward(self, input, rois):
         return ops.roi_align(input, rois, self.output_size, self.spatial_scale, self.sampling_ratio, self.aligned)
+
+
+class MultiScaleRoIAlign(nn.Module):
+    """Drop-in for ``torchvision.ops.MultiScaleRoIAlign(featmap_names, output_size, sampling_ratio)`` as constructed at
+    models/new_model.py:127 and called at :143 with ``(features: dict, boxes: list[Tensor[L,4]], image_shapes)``."""
+
+    def __init__(self, featmap_names, output_size, sampling_ratio, *, canonical_scale: int = 224, canonical_level: int = 4):
+        super().__init__()
+        self.featmap_names = list(featmap_names)
+        self.output_size = (output_size, output_size) if isinstance(output_size, int) else tuple(output_size)
+        self.sampling_ratio = sampling_ratio
+        self.canonical_scale, self.canonical_level = canonical_scale, canonical_level
+
+    def forward(self, x, boxes, image_shapes):
+        feats = [v for k, v in x.items() if k in self.featmap_names]      # TV ops/poolers.py _filter_input
+        return ops.multiscale_roi_align(feats, boxes, image_shapes, self.output_size, self.sampling_ratio,
+                                        float(self.canonical_scale), int(self.canonical_level))
 
 
 class RegionProposal(nn.Module):

@@ -201,7 +201,8 @@ def roi_pool_backward(grad_out, argmax, rois5, feat_shape, spatial_scale: float 
 
 
 def roi_align_forward(feat, rois5, output_size=(7, 7), spatial_scale: float = 1.0, sampling_ratio: int = 2,
-                      aligned: bool = False):
+                      aligned: bool = False, out=None):
+    """``out``: write into an existing [K,C,PH,PW] tensor (rows of rois with a negative batch index are left untouched)."""
     lib = _lib.load()
     if not feat.is_cuda or feat.dtype != torch.float32:
         raise ValueError("features must be a CUDA fp32 tensor: the region stage has no CPU path")
@@ -211,7 +212,10 @@ def roi_align_forward(feat, rois5, output_size=(7, 7), spatial_scale: float = 1.
     K = rois5.shape[0]
     PH, PW = int(output_size[0]), int(output_size[1])
     with torch.cuda.device(feat.device):
-        out = torch.empty((K, C, PH, PW), dtype=torch.float32, device=feat.device)
+        if out is None:
+            out = torch.empty((K, C, PH, PW), dtype=torch.float32, device=feat.device)
+        elif tuple(out.shape) != (K, C, PH, PW) or not out.is_contiguous() or out.dtype != torch.float32:
+            raise ValueError("roi_align_forward: out must be a contiguous fp32 [K,C,PH,PW] tensor")
         _lib.check(lib.frr_roi_align_fwd(feat.data_ptr(), rois5.data_ptr(), K, B, C, H, W, PH, PW, float(spatial_scale),
                                          int(sampling_ratio), int(aligned), cl, out.data_ptr(), _stream()),
                    "frr_roi_align_fwd")
@@ -466,3 +470,78 @@ def pack_detections(det_boxes, det_labels, det_scores, det_count, max_det: int, 
                                            det_count.data_ptr(), B, cap, int(max_det), _ptr(image_wh), int(bool(xywh)),
                                            out.data_ptr(), cnt.data_ptr(), _stream()), "frr_pack_detections")
     return out, cnt
+
+
+# ------------------------------------------------------------------------------------------------
+# MultiScaleRoIAlign (models/new_model.py:127,143; TV ops/poolers.py)
+# ------------------------------------------------------------------------------------------------
+def infer_scales(features, image_shapes):
+    """TV ops/poolers.py ``_setup_scales`` / ``_infer_scale``: scale_l = 2 ** round(log2(feat_dim0 / image_dim0)) with
+    image_dim0 = max over ``image_shapes`` of their first entry (used exactly as the caller passes them; the reference
+    passes (w, h)).  Returns (scales, k_min, k_max)."""
+    import math
+    if not image_shapes:
+        raise ValueError("images list should not be empty")
+    d0 = max(int(s[0]) for s in image_shapes)
+    scales = [2.0 ** float(round(math.log2(float(f.shape[-2]) / float(d0)))) for f in features]
+    return scales, int(-math.log2(scales[0])), int(-math.log2(scales[-1]))
+
+
+def fpn_level_rois(rois5, k_min: int, k_max: int, canonical_scale: float = 224.0, canonical_level: int = 4):
+    """LevelMapper on the device: (levels int32 [K], rois_per_level [L,K,5] with foreign rois masked by batch index -1)."""
+    lib = _lib.load()
+    rois5 = _req(rois5, "rois")
+    K, L = rois5.shape[0], k_max - k_min + 1
+    with torch.cuda.device(rois5.device):
+        levels = torch.empty((K,), dtype=torch.int32, device=rois5.device)
+        per = torch.empty((L, K, 5), dtype=torch.float32, device=rois5.device)
+        _lib.check(lib.frr_fpn_level_rois(rois5.data_ptr(), K, int(k_min), int(k_max), int(canonical_level),
+                                          float(canonical_scale), L, levels.data_ptr(), per.data_ptr(), _stream()),
+                   "frr_fpn_level_rois")
+    return levels, per
+
+
+class _MultiScaleRoIAlignFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rois5, output_size, sampling_ratio, scales, k_min, k_max, canonical_scale, canonical_level, *feats):
+        K, C = rois5.shape[0], feats[0].shape[1]
+        levels, per = fpn_level_rois(rois5, k_min, k_max, canonical_scale, canonical_level)
+        out = torch.empty((K, C, output_size[0], output_size[1]), dtype=torch.float32, device=rois5.device)
+        lay = []
+        for l, f in enumerate(feats):
+            f_l, cl = _feat_layout(f)
+            lay.append(bool(cl))
+            roi_align_forward(f_l, per[l], output_size, scales[l], sampling_ratio, False, out=out)
+        ctx.save_for_backward(per)
+        ctx.meta = ([tuple(f.shape) for f in feats], list(scales), int(sampling_ratio), lay)
+        ctx.mark_non_differentiable(levels)
+        return out, levels
+
+    @staticmethod
+    def backward(ctx, grad_out, _grad_levels):
+        (per,) = ctx.saved_tensors
+        shapes, scales, sr, lay = ctx.meta
+        go = grad_out.contiguous()
+        grads = [roi_align_backward(go, per[l], shapes[l], scales[l], sr, False, lay[l]) for l in range(len(shapes))]
+        return (None,) * 8 + tuple(grads)
+
+
+def multiscale_roi_align(features, boxes, image_shapes, output_size=7, sampling_ratio: int = 2,
+                         canonical_scale: float = 224.0, canonical_level: int = 4, return_levels: bool = False):
+    """Drop-in for ``torchvision.ops.MultiScaleRoIAlign(featmap_names, output_size, sampling_ratio)(x, boxes,
+    image_shapes)`` as called at models/new_model.py:127,143: ``features`` = list (or dict values, in order) of
+    [B,C,Hl,Wl] maps, ``boxes`` = Tensor[K,5] or list of Tensor[L,4] in image coordinates.  One level-assignment
+    kernel + one RoIAlign launch per level, all writing one [K,C,7,7] output; differentiable w.r.t. the features."""
+    if isinstance(features, dict):
+        features = list(features.values())
+    features = list(features)
+    if isinstance(output_size, int):
+        output_size = (output_size, output_size)
+    rois5 = convert_rois(boxes, features[0].device).to(torch.float32).contiguous()
+    scales, k_min, k_max = infer_scales(features, image_shapes)
+    if len(features) == 1:
+        out = roi_align(features[0], rois5, output_size, scales[0], sampling_ratio, False)
+        return (out, torch.zeros((rois5.shape[0],), dtype=torch.int32, device=rois5.device)) if return_levels else out
+    out, levels = _MultiScaleRoIAlignFn.apply(rois5, tuple(output_size), int(sampling_ratio), tuple(scales), k_min, k_max,
+                                              float(canonical_scale), int(canonical_level), *features)
+    return (out, levels) if return_levels else out

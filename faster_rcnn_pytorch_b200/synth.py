@@ -94,3 +94,20 @@ def random_boxes(seed: int, n: int, cluster: bool = True):
     b = np.clip(b, 0.0, 1.0).astype(f32)
     s = unique_scores(rs, n)
     return b, s
+
+
+def pyramid_inputs(seed=8100, B=2, C=8, image_hw=(256, 320), K=80):
+    """Seeded pyramid features (strides 4..32) and rois in image coordinates spanning all levels."""
+    rs = np.random.RandomState(seed)
+    feats = [rs.standard_normal((B, C, image_hw[0] // s, image_hw[1] // s)).astype(np.float32) for s in (4, 8, 16, 32)]
+    side = np.exp(rs.uniform(np.log(8), np.log(300), K))
+    ar = np.exp(rs.uniform(-0.7, 0.7, K))
+    w, h = side * np.sqrt(ar), side / np.sqrt(ar)
+    cx, cy = rs.uniform(0, image_hw[1], K), rs.uniform(0, image_hw[0], K)
+    x1, y1 = np.clip(cx - w / 2, 0, image_hw[1] - 2), np.clip(cy - h / 2, 0, image_hw[0] - 2)
+    x2, y2 = np.clip(cx + w / 2, x1 + 1, image_hw[1]), np.clip(cy + h / 2, y1 + 1, image_hw[0])
+    b = rs.randint(0, B, K)
+    rois5 = np.stack([b, x1, y1, x2, y2], axis=1).astype(np.float32)
+    rois5[0, 1:] = [10, 10, 10 + 112, 10 + 112]       # sqrt(area) = 112 = 224 / 2: exactly on a level boundary
+    rois5[1, 1:] = [0, 0, 224, 224]
+    return feats, rois5

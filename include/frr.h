@@ -152,6 +152,14 @@ int frr_roi_align_bwd(const float* grad_out, const float* rois, int K, int B, in
                       float spatial_scale, int sampling_ratio, int aligned, int channels_last, float* grad_in,
                       frr_stream_t stream);
 
+/* MultiScaleRoIAlign level assignment -- TV ops/poolers.py LevelMapper as used by models/new_model.py:127,143:
+ * level = clamp(floor(canonical_level + log2(sqrt(area)/canonical_scale) + 1e-6), k_min, k_max) - k_min, rois in image
+ * coordinates.  Writes levels int32 [K] and rois_per_level [L,K,5]: copy l keeps the batch index of the rois of level l
+ * and sets it to -1 for the others; frr_roi_align_fwd/bwd skip rois with a negative batch index, so the L per-level
+ * launches fill one [K,C,PH,PW] output without gathers or host synchronisation.  L = k_max - k_min + 1. */
+int frr_fpn_level_rois(const float* rois5, int K, int k_min, int k_max, int canonical_level, float canonical_scale, int L,
+                       int32_t* levels, float* rois_per_level, frr_stream_t stream);
+
 /* Developer hook: per-phase clock64() cycles of CTA (0,0) of the 7x7 fast kernels, accumulated since the last call
  * (16 slots, see roi_fast.cu); copies to host_out16 and clears.  Synchronises the device. */
 int frr_roi_debug_cycles(int64_t* host_out16);

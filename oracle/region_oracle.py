@@ -399,6 +399,39 @@ def roi_align_backward(grad_out, rois5, feat_shape, pooled=(7, 7), spatial_scale
                                   int(sampling_ratio), bool(aligned))
 
 
+def fpn_levels(rois5: np.ndarray, k_min: int, k_max: int, canonical_scale: float = 224.0, canonical_level: int = 4):
+    """TV ops/poolers.py ``LevelMapper.__call__`` (used by MultiScaleRoIAlign, models/new_model.py:127,143):
+    floor(lvl0 + log2(sqrt(area) / s0) + 1e-6) clamped to [k_min, k_max], minus k_min; fp32 throughout."""
+    r = np.asarray(rois5, dtype=f32)
+    area = (r[:, 3] - r[:, 1]) * (r[:, 4] - r[:, 2])
+    s = np.sqrt(area).astype(f32)
+    t = np.floor((f32(canonical_level) + np.log2(s / f32(canonical_scale)).astype(f32)) + f32(1e-6))
+    return (np.clip(t, k_min, k_max).astype(np.int64) - k_min)
+
+
+def infer_scales(feature_shapes, image_shapes):
+    """TV ops/poolers.py ``_setup_scales``: 2 ** round(log2(feat_dim0 / max image_dim0)) per level -> (scales, k_min, k_max)."""
+    import math
+    d0 = max(int(sh[0]) for sh in image_shapes)
+    scales = [2.0 ** float(round(math.log2(float(fs[-2]) / float(d0)))) for fs in feature_shapes]
+    return scales, int(-math.log2(scales[0])), int(-math.log2(scales[-1]))
+
+
+def multiscale_roi_align(features, rois5, image_shapes, pooled=(7, 7), sampling_ratio=2):
+    """TV ops/poolers.py ``_multiscale_roi_align``: every roi is pooled from the pyramid level LevelMapper assigns."""
+    scales, k_min, k_max = infer_scales([f.shape for f in features], image_shapes)
+    rois5 = np.asarray(rois5, dtype=f32)
+    if len(features) == 1:
+        return roi_align_forward(features[0], rois5, pooled, scales[0], sampling_ratio, False), np.zeros(len(rois5), np.int64)
+    lv = fpn_levels(rois5, k_min, k_max)
+    out = np.zeros((rois5.shape[0], features[0].shape[1]) + tuple(pooled), dtype=f32)
+    for l, (f, sc) in enumerate(zip(features, scales)):
+        idx = np.nonzero(lv == l)[0]
+        if len(idx):
+            out[idx] = roi_align_forward(f, rois5[idx], pooled, sc, sampling_ratio, False)
+    return out, lv
+
+
 def scale_rois(rois: np.ndarray, fh: int, fw: int, batch_index: int = 0) -> np.ndarray:
     """models/model.py:104-110 + TV ops/_utils.py:18-25: roi*[fw,fh,fw,fh], prepend batch idx."""
     r = np.asarray(rois, dtype=f32) * np.array([fw, fh, fw, fh], dtype=f32)

@@ -123,6 +123,40 @@ def proposals():
     print("proposal_fpn.npz", os.path.getsize(os.path.join(HERE, "proposal_fpn.npz")))
 
 
+def multiscale():
+    """torchvision.ops.MultiScaleRoIAlign (CPU) as called at models/new_model.py:127,143 -> tests/golden/msroialign.npz"""
+    import torchvision
+    from torchvision.ops.poolers import LevelMapper
+    image_hw = (256, 320)
+    feats, rois5 = synth.pyramid_inputs(image_hw=image_hw)
+    pool = torchvision.ops.MultiScaleRoIAlign(featmap_names=["0", "1", "2", "3"], output_size=7, sampling_ratio=2)
+    x = {str(i): torch.from_numpy(f) for i, f in enumerate(feats)}
+    boxes = [torch.from_numpy(rois5[rois5[:, 0] == b, 1:]) for b in range(feats[0].shape[0])]
+    order = np.concatenate([np.nonzero(rois5[:, 0] == b)[0] for b in range(feats[0].shape[0])])
+    g = {}
+    for tag, shapes in [("hw", [image_hw] * 2), ("wh_like_reference", [(image_hw[1], image_hw[0])] * 2)]:
+        for f in x.values():
+            f.requires_grad_(True); f.grad = None
+        out = pool(x, boxes, shapes)
+        go = torch.from_numpy(np.random.RandomState(8101).standard_normal(tuple(out.shape)).astype(np.float32))
+        out.backward(go)
+        full = np.zeros(out.shape, np.float32); full[order] = out.detach().numpy()
+        gfull = np.zeros(out.shape, np.float32); gfull[order] = go.numpy()
+        g[f"{tag}_out"] = full                          # rows in the order of rois5
+        g[f"{tag}_grad_out"] = gfull
+        for i, f in enumerate(x.values()):
+            g[f"{tag}_gin{i}"] = f.grad.numpy().copy()
+        scales = pool.scales
+        k_min, k_max = int(-np.log2(scales[0])), int(-np.log2(scales[-1]))
+        lv = LevelMapper(k_min, k_max)([torch.from_numpy(rois5[:, 1:])]).numpy()
+        g[f"{tag}_levels"] = lv.astype(np.int32)
+        g[f"{tag}_scales"] = np.asarray(scales, np.float64)
+        pool.scales = None; pool.map_levels = None
+    np.savez_compressed(os.path.join(HERE, "msroialign.npz"), **g)
+    print("msroialign.npz", os.path.getsize(os.path.join(HERE, "msroialign.npz")))
+
+
 if __name__ == "__main__":
     main()
     proposals()
+    multiscale()

@@ -144,3 +144,19 @@ def test_fpn_variant_target_maker_modules(oracle):
     fc, fr, fs = modules.fpn.FRCNNTargetMaker()(dev(gt), dev(lab + 1), dev(rois))
     assert fc.shape == (512,) and np.array_equal(fc.cpu().numpy(), g["a_frcnn_cls"].astype(np.int64))
     assert np.array_equal(fs.cpu().numpy(), g["a_frcnn_rois"])
+
+
+def test_multiscale_roi_align_module_matches_torchvision_call():
+    """modules.MultiScaleRoIAlign(['0','1','2','3'], 7, 2)(features, [boxes], [image_shape]) -- models/new_model.py:127,143."""
+    from conftest import golden
+    from faster_rcnn_pytorch_b200 import modules
+    g = golden("msroialign")
+    feats_np, rois5 = synth.pyramid_inputs(image_hw=(256, 320))
+    B = feats_np[0].shape[0]
+    x = {str(i): torch.from_numpy(f).to("cuda:0") for i, f in enumerate(feats_np)}
+    x["pool"] = torch.zeros(1, device="cuda:0")                     # extra map the pooler must ignore (featmap_names)
+    order = np.concatenate([np.nonzero(rois5[:, 0] == b)[0] for b in range(B)])
+    boxes = [torch.from_numpy(rois5[rois5[:, 0] == b, 1:]).to("cuda:0") for b in range(B)]
+    pool = modules.MultiScaleRoIAlign(["0", "1", "2", "3"], 7, 2)
+    out = pool(x, boxes, [(320, 256)] * B)                          # the reference passes (w, h)
+    np.testing.assert_allclose(out.cpu().numpy(), g["wh_like_reference_out"][order], rtol=1e-5, atol=1e-6)

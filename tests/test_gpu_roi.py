@@ -134,3 +134,37 @@ def test_autograd_and_edge_cases(oracle):
     assert empty.shape == (0, 12, 7, 7)
     with pytest.raises(ValueError):
         ops.roi_pool(feat.detach().cpu(), torch.zeros((1, 5)), 7, 1.0)
+
+
+@pytest.mark.parametrize("tag,shapes", [("hw", [(256, 320)] * 2), ("wh_like_reference", [(320, 256)] * 2)])
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_multiscale_roi_align_goldens(tag, shapes, channels_last):
+    """MultiScaleRoIAlign(['0'..'3'], 7, 2)(x, boxes, image_shapes) as called at models/new_model.py:127,143: levels
+    bit-exact (incl. boxes exactly on a LevelMapper boundary), output within 1e-5, feature gradients norm-wise 1e-5."""
+    g = golden("msroialign")
+    feats_np, rois5 = synth.pyramid_inputs(image_hw=(256, 320))
+    feats = [dev(f) for f in feats_np]
+    if channels_last:
+        feats = [f.contiguous(memory_format=torch.channels_last) for f in feats]
+    feats = [f.requires_grad_(True) for f in feats]
+    scales, k_min, k_max = ops.infer_scales(feats, shapes)
+    assert np.array_equal(np.asarray(scales), g[f"{tag}_scales"])
+    out, levels = ops.multiscale_roi_align({str(i): f for i, f in enumerate(feats)}, dev(rois5), shapes, 7, 2,
+                                           return_levels=True)
+    assert np.array_equal(levels.cpu().numpy(), g[f"{tag}_levels"])
+    np.testing.assert_allclose(out.detach().cpu().numpy(), g[f"{tag}_out"], rtol=RTOL, atol=ATOL)
+    out.backward(dev(g[f"{tag}_grad_out"]))
+    for i, f in enumerate(feats):
+        close_accum(f.grad.cpu().numpy(), g[f"{tag}_gin{i}"])
+
+
+def test_multiscale_roi_align_list_boxes_and_oracle(oracle):
+    """Boxes as the reference passes them (list of [L,4] per image) on a larger pyramid; checked against the oracle."""
+    feats_np, rois5 = synth.pyramid_inputs(seed=8200, B=3, C=16, image_hw=(384, 512), K=300)
+    order = np.concatenate([np.nonzero(rois5[:, 0] == b)[0] for b in range(3)])
+    boxes = [dev(rois5[rois5[:, 0] == b, 1:]) for b in range(3)]
+    shapes = [(384, 512)] * 3
+    out, levels = ops.multiscale_roi_align([dev(f) for f in feats_np], boxes, shapes, 7, 2, return_levels=True)
+    want, lv = oracle.multiscale_roi_align(feats_np, rois5[order], shapes)
+    assert np.array_equal(levels.cpu().numpy().astype(np.int64), lv)
+    np.testing.assert_allclose(out.cpu().numpy(), want, rtol=RTOL, atol=ATOL)

@@ -273,3 +273,15 @@ def test_fpn_variant_proposals(oracle, name, mode):
     keep = oracle.nms(comp[order], -np.arange(len(order), dtype=np.float32), 0.7)[:post_k]
     assert np.array_equal(keep, g[f"{name}_keep"])
     assert np.array_equal(comp[order][keep], g[f"{name}_rois"])
+
+
+@pytest.mark.parametrize("tag,shapes", [("hw", [(256, 320)] * 2), ("wh_like_reference", [(320, 256)] * 2)])
+def test_multiscale_roi_align_vs_torchvision(oracle, tag, shapes):
+    """MultiScaleRoIAlign(['0'..'3'], 7, 2) as called at models/new_model.py:127,143 (the reference passes (w, h))."""
+    g = golden("msroialign")
+    feats, rois5 = synth.pyramid_inputs(image_hw=(256, 320))
+    scales, k_min, k_max = oracle.infer_scales([f.shape for f in feats], shapes)
+    assert np.array_equal(np.asarray(scales), g[f"{tag}_scales"])
+    out, lv = oracle.multiscale_roi_align(feats, rois5, shapes)
+    assert np.array_equal(lv, g[f"{tag}_levels"].astype(np.int64))          # incl. the boxes exactly on a level boundary
+    assert np.array_equal(out, g[f"{tag}_out"])
