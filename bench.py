@@ -412,9 +412,12 @@ def run_extra(args):
         bidx = torch.arange(B, device=dev, dtype=torch.float32).repeat_interleave(per)[:, None]
         stats = {}
 
+        torch.manual_seed(3000 + rank)
+        gen = targets.DeviceGenerator(dev) if args.sampling == "device" else None    # torch's mt19937 stream on the device
+
         def step(i):
-            torch.manual_seed(3000 + i)
-            t = targets.make_targets(gt, None, lab, props, pcnt, image_hw=hw)    # 4 kernels + ONE D2H of counts
+            # device sampling: 6 kernels, no host synchronisation; host sampling: 4 kernels + ONE D2H of counts
+            t = targets.make_targets(gt, None, lab, props, pcnt, image_hw=hw, generator=gen)
             rois5 = torch.cat([bidx, (t["sample_rois"] * scale).reshape(-1, 4)], dim=1)
             out, arg = ops.roi_pool_forward(feats[i % NR], rois5)
             gin = ops.roi_pool_backward(gouts[i % NR], arg, rois5, feats[0].shape)
@@ -433,6 +436,8 @@ def run_extra(args):
         ms_f = _events_ms(torch, lambda i: ops.roi_pool_forward(feats[i % NR], rois5), 12, sync_all) / 12
         ms_b = _events_ms(torch, lambda i: ops.roi_pool_backward(gouts[i % NR], arg, rois5, feats[0].shape), 12, sync_all) / 12
         ms_t = _events_ms(torch, lambda i: targets.make_targets(gt, None, lab, props, pcnt, image_hw=hw), 12, sync_all) / 12
+        gen2 = targets.DeviceGenerator(dev)
+        ms_td = _events_ms(torch, lambda i: targets.make_targets(gt, None, lab, props, pcnt, image_hw=hw, generator=gen2), 12, sync_all) / 12
         clocks = sampler.stop() if sampler else None
         if rank == 0:
             fb = fbytes + 2 * obytes
@@ -443,7 +448,9 @@ def run_extra(args):
                 "config": {"workload": "configs[2]: training targets (256 anchor / 128 RoI sampling, G=8) + RoIPool 7x7 fwd/bwd on "
                                        "512-ch stride-16 features (37x62), batch 16 images/GPU, RoIs sampled from the RPN proposals",
                            "l2": f"features/grad_out rotated over {NR} resident sets (> 126 MB L2)"},
-                "kernels_ms_per_batch": {"roi_pool_fwd": ms_f, "roi_pool_bwd": ms_b, "make_targets(4 kernels + D2H + host randperm + H2D)": ms_t},
+                "kernels_ms_per_batch": {"roi_pool_fwd": ms_f, "roi_pool_bwd": ms_b, "make_targets(4 kernels + D2H + host randperm + H2D)": ms_t,
+                                         "make_targets(device sampling: 6 kernels, no sync)": ms_td},
+                "sampling": args.sampling,
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"kernel": "roi_fwd_fast_kernel", "bound": "hbm", "achieved": fb / (ms_f * 1e-3) / 1e9, "peak": peak,
                              "unit": "GB/s", "frac": fb / (ms_f * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": how,
@@ -507,6 +514,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--sampling", default="device", choices=["device", "host"],
+                    help="--workload train: where the reference's torch.randperm draws are replayed")
     ap.add_argument("--workload", default="rpn", choices=["rpn", "train", "infer"],
                     help="rpn = BASELINE configs[1] (the driver's line); train = configs[2]; infer = configs[3]")
     args = ap.parse_args()

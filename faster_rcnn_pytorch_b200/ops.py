@@ -403,6 +403,40 @@ def frcnn_targets_finalize(ws, gt_label, sel, sel_n, std=_STD4, label_offset: in
     return cls, reg, srois, kidx
 
 
+def sample_targets(mt_state, ws_rpn=None, ws_frcnn=None, rpn_batch: int = 256, rpn_max_pos: int = 128,
+                   frcnn_batch: int = 128, frcnn_max_pos: int = 32):
+    """The reference's torch.randperm sampling replayed on the device (``frr_sample_targets``): ``mt_state`` is the
+    uint32 [626] device copy of torch's CPU mt19937 state (``targets.DeviceGenerator``), advanced in place.  Edits
+    ``ws_rpn['label8']`` in place and returns (sel int32 [B,frcnn_batch], sel_n int32 [B,2]) for the Fast R-CNN finalize
+    (None, None when ``ws_frcnn`` is None).  No host synchronisation."""
+    lib = _lib.load()
+    if ws_rpn is None and ws_frcnn is None:
+        raise ValueError("sample_targets: nothing to sample")
+    ref = ws_rpn if ws_rpn is not None else ws_frcnn
+    dev = ref["counts"].device
+    B = ref["counts"].shape[0]
+    if mt_state.device != dev or mt_state.dtype != torch.int32 or mt_state.numel() != 626:
+        raise ValueError("mt_state must be an int32 [626] tensor on the device of the targets")
+    S = max(rpn_batch if ws_rpn is not None else 0, frcnn_batch if ws_frcnn is not None else 0)
+    with torch.cuda.device(dev):
+        jobs = torch.empty((B, 4, 4), dtype=torch.int32, device=dev)
+        draws = torch.empty((B, 4, S), dtype=torch.int32, device=dev)
+        sel = sel_n = None
+        if ws_frcnn is not None:
+            sel = torch.zeros((B, frcnn_batch), dtype=torch.int32, device=dev)
+            sel_n = torch.zeros((B, 2), dtype=torch.int32, device=dev)
+        N = ws_rpn["label8"].shape[1] if ws_rpn is not None else 0
+        _lib.check(lib.frr_sample_targets(_ptr(ws_rpn["counts"]) if ws_rpn is not None else None,
+                                          _ptr(ws_frcnn["counts"]) if ws_frcnn is not None else None, B, int(rpn_batch),
+                                          int(rpn_max_pos), int(frcnn_batch), int(frcnn_max_pos), mt_state.data_ptr(), N,
+                                          _ptr(ws_rpn["label8"]) if ws_rpn is not None else None,
+                                          _ptr(ws_rpn["pos_list"]) if ws_rpn is not None else None,
+                                          _ptr(ws_rpn["neg_list"]) if ws_rpn is not None else None, _ptr(sel), _ptr(sel_n),
+                                          int(frcnn_batch), jobs.data_ptr(), draws.data_ptr(), S, _stream()),
+                   "frr_sample_targets")
+    return sel, sel_n
+
+
 # ------------------------------------------------------------------------------------------------
 # detection post-processing (D1, D2)
 # ------------------------------------------------------------------------------------------------

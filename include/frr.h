@@ -210,6 +210,23 @@ int frr_frcnn_targets_finalize(const float* rois, const int32_t* roi_count, int 
                                int64_t* cls, float* reg, float* sample_rois, int32_t* keep_index, frr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * T1/T3 sampling without the host round trip -- the torch.randperm draws of models/model.py:149,155,228,235
+ *     (models/new_model.py:169-177,328-343) replayed on the device from a device-resident copy of torch's CPU
+ *     mt19937 state: mt_state uint32 [626] = the 624 state words, [624] = index of the next unread word (624 =
+ *     exhausted), [625] reserved; read and advanced in place exactly as the reference's draws would advance it
+ *     (per image: RPN positives if n_pos > rpn_max_pos, RPN negatives if n_neg > rpn_batch - n_pos, then both
+ *     Fast R-CNN permutations, always).  rpn_counts / frcnn_counts = the counts [B,2] of the assign kernels (either may
+ *     be NULL: that maker is not sampled).  RPN: label8 [B,N] is edited in place (then call frr_rpn_targets_finalize
+ *     with disable = NULL); Fast R-CNN: writes sel int32 [B,sel_stride] and sel_n [B,2] for frr_frcnn_targets_finalize.
+ *     Workspace: jobs int32 [B,4,4] (16-byte aligned), draws uint32 [B,4,draws_stride], draws_stride >= the batch sizes
+ *     (<= 512).  Two launches, no synchronisation, no host memory.
+ * ------------------------------------------------------------------------------------- */
+int frr_sample_targets(const int32_t* rpn_counts, const int32_t* frcnn_counts, int B, int rpn_batch, int rpn_max_pos,
+                       int frcnn_batch, int frcnn_max_pos, uint32_t* mt_state, int N, int8_t* rpn_label8,
+                       const int32_t* rpn_pos_list, const int32_t* rpn_neg_list, int32_t* sel, int32_t* sel_n,
+                       int sel_stride, int32_t* jobs, uint32_t* draws, int draws_stride, frr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * D1  predict tail -- models/model.py:369-378: prob = softmax(cls); boxes = clamp(cxcy_to_xy(
  *     decode(reg*std, xy_to_cxcy(roi))), 0, 1) per class.  cls [rows,C], reg [rows,C,4],
  *     rois [rows,4] -> prob [rows,C], boxes [rows,C,4].

@@ -198,3 +198,87 @@ def test_fpn_variant_tie_inclusive_zero_iou(oracle):
     torch.manual_seed(9)
     labels, _ = targets.rpn_targets(dev(gt[None]), None, anchors=dev(g["far_anchors"]), variant="fpn")
     assert np.array_equal(labels[0].cpu().numpy(), g["far_rpn_cls"].astype(np.int64))
+
+
+# ------------------------------------------------------------------------------------ device-side sampling
+@pytest.mark.parametrize("name,hw,gseed,G,tseed", CASES)
+def test_device_sampling_reference_goldens(name, hw, gseed, G, tseed):
+    """frr_sample_targets: torch's mt19937 state copied to the device once, the randperm draws of
+    models/model.py:149,155,228,235 replayed there -- same goldens as the host path, no synchronisation in between."""
+    g = golden("targets")
+    gt, lab = _gt(gseed, G)
+    torch.manual_seed(tseed)
+    gen = targets.DeviceGenerator(DEV)
+    labels, reg = targets.rpn_targets(dev(gt[None]), None, image_hw=hw, generator=gen)
+    labels = labels[0].cpu().numpy()
+    assert np.array_equal(labels, g[f"{name}_rpn_cls"].astype(np.int64))
+    rois, _ = synth.random_boxes(tseed + 50, 2000)
+    torch.manual_seed(tseed + 1)
+    gen.sync_from_torch()
+    cls, freg, srois, kidx, n = targets.frcnn_targets(dev(rois[None]), None, dev(gt[None]), None, dev(lab[None]), generator=gen)
+    assert n.is_cuda and int(n[0]) == 128
+    assert np.array_equal(cls[0].cpu().numpy(), g[f"{name}_frcnn_cls"].astype(np.int64))
+    assert np.array_equal(srois[0].cpu().numpy(), g[f"{name}_frcnn_rois"])
+    close(freg[0].cpu().numpy(), g[f"{name}_frcnn_reg"], atol=2e-5)
+
+
+@pytest.mark.parametrize("name,hw,gseed,G,tseed", FPN_CASES)
+def test_device_sampling_fpn_variant_goldens(oracle, name, hw, gseed, G, tseed):
+    g = golden("targets_fpn")
+    anchors = oracle.enumerate_anchors(hw)
+    gt, lab = synth.gt_boxes(gseed, G)
+    torch.manual_seed(tseed)
+    gen = targets.DeviceGenerator(DEV)
+    labels, _ = targets.rpn_targets(dev(gt[None]), None, anchors=dev(anchors), variant="fpn", generator=gen)
+    assert np.array_equal(labels[0].cpu().numpy(), g[f"{name}_rpn_cls"].astype(np.int64))
+    rois, _ = synth.random_boxes(tseed + 50, 2000)
+    torch.manual_seed(tseed + 1)
+    gen.sync_from_torch()
+    cls, _, srois, _, n = targets.frcnn_targets(dev(rois[None]), None, dev(gt[None]), None, dev((lab + 1)[None]),
+                                                variant="fpn", generator=gen)
+    assert int(n[0]) == 512
+    assert np.array_equal(cls[0].cpu().numpy(), g[f"{name}_frcnn_cls"].astype(np.int64))
+    assert np.array_equal(srois[0].cpu().numpy(), g[f"{name}_frcnn_rois"])
+
+
+def test_device_sampling_batch_equals_host_stream_and_state():
+    """Two consecutive batches (crowded image with > 128 positives, ragged GT, an image with too few negatives) through
+    make_targets: the device generator yields bit-identical targets AND leaves torch's generator, after
+    sync_to_torch(), exactly where the host path leaves it."""
+    hw, B, G, R = (600, 1000), 6, 160, 2000
+    gts = np.zeros((B, G, 4), np.float32); labs = np.zeros((B, G), np.int64)
+    gc = np.asarray([8, 160, 1, 40, 3, 8], np.int32)
+    rc = np.asarray([2000, 2000, 1500, 2000, 20, 700], np.int32)
+    rois = np.zeros((B, R, 4), np.float32)
+    for i in range(B):
+        b, l = synth.gt_boxes(9000 + i, int(gc[i]))
+        gts[i, :gc[i]] = b; labs[i, :gc[i]] = l
+        rois[i, :rc[i]] = synth.random_boxes(9100 + i, int(rc[i]))[0]
+    args = (dev(gts), dev(gc), dev(labs), dev(rois), dev(rc))
+
+    torch.manual_seed(777)
+    host = [targets.make_targets(*args, image_hw=hw) for _ in range(2)]
+    host_state = torch.get_rng_state().clone()
+    host_next = torch.randperm(1000)
+
+    torch.manual_seed(777)
+    gen = targets.DeviceGenerator(DEV)
+    devo = [targets.make_targets(*args, image_hw=hw, generator=gen) for _ in range(2)]   # no sync between the batches
+    gen.sync_to_torch()
+    assert torch.equal(torch.get_rng_state(), host_state)
+    assert torch.equal(torch.randperm(1000), host_next)
+    for h, d in zip(host, devo):
+        for k in ("rpn_cls", "rpn_reg", "frcnn_cls", "frcnn_reg", "sample_rois", "keep_index"):
+            assert torch.equal(h[k], d[k]), k
+        assert np.array_equal(d["n_samples"].cpu().numpy(), h["n_samples"])
+    assert (host[0]["rpn_cls"][1] == 1).sum() == 128          # the crowded image exercised the positive draw
+    assert int(host[0]["n_samples"][4]) < 128                 # too few negatives -> short sample
+
+
+def test_device_generator_round_trip_without_draws():
+    torch.manual_seed(5)
+    before = torch.get_rng_state().clone()
+    want = torch.randperm(50)
+    torch.set_rng_state(before)
+    targets.DeviceGenerator(DEV).sync_to_torch()              # freshly seeded: left = 1 <-> position 624
+    assert torch.equal(torch.randperm(50), want)

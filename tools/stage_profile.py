@@ -118,6 +118,13 @@ def main():
     torch.manual_seed(0)
     us = timeit(lambda: targets.make_targets(gt, None, lab, props, None, image_hw=hw), reps=10)
     report("cfg3/make_targets_host_roundtrip(4 kernels + 1 D2H + randperm + H2D)", us, B=B)
+    gen = targets.DeviceGenerator(gt.device)
+    us = timeit(lambda: targets.make_targets(gt, None, lab, props, None, image_hw=hw, generator=gen), reps=10)
+    report("cfg3/make_targets_device_sampling(6 kernels, no sync)", us, B=B)
+    wr = ops.rpn_targets_assign(gt, None, synth.num_anchors(hw), image_hw=hw)
+    wf = ops.frcnn_targets_assign(props, None, gt, None)
+    us = timeit(lambda: ops.sample_targets(gen.state, ws_rpn=wr, ws_frcnn=wf), reps=10)
+    report("cfg3/sample_targets(mt19937 stream + Fisher-Yates apply)", us, B=B)
 
     # ---- detection post-processing (config 4: B=8, R=300, C=81)
     B, R, C = 8, 300, 81
