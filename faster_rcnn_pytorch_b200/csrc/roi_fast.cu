@@ -4,15 +4,17 @@
 // A CTA owns CB channel planes of ONE image; every feature element is read from HBM once and every output
 // element written once (HBM traffic = the algorithmic bytes), for NCHW and channels_last inputs alike.
 //
-// Forward (CB = 16, 8 or 4): the features are staged in shared memory PIXEL-MAJOR ([pixel][CB], chunk-swizzled): a
-//   thread owns one bin and ALL CB channels, so CB/4 LDS.128 feed CB running maxima and every loop / bounds / index
-//   instruction is shared by CB channels (one channel per thread cost 131 warp instructions per bin and channel,
-//   this layout ~25).  The lanes of a warp take the 49 bins of the SAME roi (same window size +-1 -> no
-//   divergence in the window loops).  The per-roi geometry (bin boundaries for RoIPool, 1-D bilinear sample
-//   records for RoIAlign) is computed once per roi into shared memory, not once per output element.  Results go
-//   to a shared-memory tile laid out exactly like the [K,C,7,7] output (the CB*49 values of one roi are
-//   contiguous there) and leave as coalesced 16-byte streaming stores.  (One cp.async.bulk store per roi was
-//   measured slower here: ~60 cycles of issue per 1.5 KB transfer on the critical path of warp 0.)
+// Forward (CB = 16, 8 or 4): the features are staged in shared memory PIXEL-MAJOR ([pixel][CB], chunk-rotated so that the
+//   8 lanes of a quarter-warp hit 8 different bank groups unless their pixels agree mod 8): a thread owns one bin and
+//   ALL CB channels, so CB/4 LDS.128 feed CB running maxima and every loop / bounds / index instruction is shared by
+//   CB channels (one channel per thread cost 131 warp instructions per bin and channel, this layout ~25).  The
+//   per-roi geometry (bin boundaries for RoIPool, 1-D bilinear sample records for RoIAlign) is computed once per roi
+//   into shared memory, not once per output element.
+//   RoIPool (roi_pool_fwd_flat_kernel): a warp owns a share of the image's rois (ordered by window size) and walks
+//   their flattened bins 32 at a time, storing straight to the [K,C,7,7] output (lanes = consecutive bins =
+//   consecutive addresses): no per-pass barriers, no staging tile, every lane busy.
+//   RoIAlign (roi_align_fwd_fast_kernel): 9 rois x 49 bins per pass, results staged in a [roi][channel][49] tile (= the
+//   output layout) and written with coalesced 16-byte streaming stores.
 // Backward (RoIPool, CB = 16 or 8): shared-memory float atomics are a CAS loop on sm_100 (LDS / FADD /
 //   ATOMS.CAST.SPIN) and global RED.ADD.F32 costs ~1.3 cycles per lane, so neither is used.  A WARP owns a plane
 //   exclusively (no inter-warp conflicts) and adds with plain LDS / FADD / STS.  Its lanes are 4 rois x 8
@@ -31,7 +33,6 @@ namespace frr {
 
 constexpr int kFastFwdThreads = 448;
 constexpr int kIdCap = 512;  // rois scanned per tile (one per thread, blockDim <= 512)
-constexpr int kPoolGeoCap = 126;  // RoIPool bin boundaries are computed for up to 126 rois at once (14 passes of 9)
 
 // developer instrumentation: clock64() cycles of CTA (0,0) per phase, accumulated over launches
 __device__ long long g_roi_dbg[16];
@@ -45,8 +46,10 @@ __device__ long long g_roi_dbg[16];
 struct FastHdr {
     int cnt[16];
     int id[kIdCap];
+    int id2[kIdCap];              // forward RoIPool: the same rois ordered by window size
+    unsigned short key[kIdCap];
 };
-constexpr int kHdrBytes = 2304;
+constexpr int kHdrBytes = 5376;
 static_assert(sizeof(FastHdr) <= kHdrBytes, "header does not fit");
 
 struct AlignRec {  // 1-D half of torchvision's bilinear_interpolate for one sample coordinate
@@ -79,6 +82,31 @@ __device__ __forceinline__ int stage_ids(const float* __restrict__ rois, int K, 
     return tot;
 }
 
+// RoIPool forward processes RS rois per pass with a barrier per pass, so a pass costs as much as its LARGEST window:
+// order the image's rois by their per-bin window size (descending rank sort, ns <= 512 keys in shared memory) so that
+// every pass works on rois of similar cost.  The output position of a roi is its id, so the order is free.
+__device__ __forceinline__ void order_ids_by_window(const float* __restrict__ rois, float scale, int ns, FastHdr* hd) {
+    const int tid = threadIdx.x;
+    if (tid < ns) {
+        const PoolGeom gm = pool_geom(rois + 5 * (size_t)hd->id[tid], scale);
+        const int kh = min(gm.rh, 4096) / 7 + 2, kw = min(gm.rw, 4096) / 7 + 2;
+        hd->key[tid] = (unsigned short)min(kh * kw, 65535);
+    }
+    __syncthreads();
+    if (tid < ns) {
+        const unsigned int my = hd->key[tid];
+        int rank = 0;
+        for (int j = 0; j < ns; ++j) {
+            const unsigned int kj = hd->key[j];
+            rank += (kj > my || (kj == my && j < tid)) ? 1 : 0;
+        }
+        hd->id2[rank] = hd->id[tid];
+    }
+    __syncthreads();
+    if (tid < ns) hd->id[tid] = hd->id2[tid];
+    __syncthreads();
+}
+
 __device__ __forceinline__ AlignRec align_rec(float v, int size) {
     AlignRec r;
     if (v < -1.0f || v > (float)size) {
@@ -99,9 +127,14 @@ __device__ __forceinline__ AlignRec align_rec(float v, int size) {
 // ---------------------------------------------------------------------------------------------
 // Shared-memory feature layout: px[p][CB] -- the CB channels of pixel p are contiguous (CB/4 float4 chunks); chunk k of
 // pixel p is stored at chunk slot (k + p) % NCH so that lanes reading neighbouring pixels hit different bank groups.
+// A quarter-warp (8 lanes x 16 bytes) is conflict-free when its 8 chunks fall into 8 different 4-bank groups; the group
+// of (p, k) is ((p * NCH + slot) mod 8), so the rotation must depend on p / (8 / NCH): then pixels that differ mod 8 never
+// collide (with the rotation (k + p) pixels that agree mod 4 always collided: 8 lanes into 4 groups).
 template <int CB>
 __device__ __forceinline__ int chunk_slot(int p, int k) {
-    return (k + p) & (CB / 4 - 1);
+    constexpr int NCH = CB / 4;
+    constexpr int SH = NCH >= 8 ? 0 : NCH == 4 ? 1 : NCH == 2 ? 2 : 3;
+    return (k + (p >> SH)) & (NCH - 1);
 }
 
 // NCHW: consecutive threads read consecutive pixels of 4 planes (coalesced), 2 trips (8 loads) in flight; channels_last:
@@ -173,22 +206,19 @@ __device__ __forceinline__ void load_pixels(float4* px, const float* __restrict_
     __syncthreads();
 }
 
-template <int CB, bool kAlign, bool kArg>
+// RoIAlign forward (R4): 441 threads = 9 rois x 49 bins per pass, results staged as [roi][channel][49] tiles.
+template <int CB>
 __global__ void __launch_bounds__(kFastFwdThreads, (CB <= 8) ? 2 : 1)
-    roi_fwd_fast_kernel(const float* __restrict__ feat, const float* __restrict__ rois, int K, int C, int H, int W, int RP,
-                        float scale, int aligned, int nhwc, float* __restrict__ out, int32_t* __restrict__ argmax) {
-    constexpr int NCH = CB / 4;                      // float4 chunks per pixel
-    constexpr int RS = kFastFwdThreads / 49;         // rois worked on at the same time (9)
-    constexpr int kGeoPer = kAlign ? 28 * 16 : 28 * 2;  // geometry bytes per roi
+    roi_align_fwd_fast_kernel(const float* __restrict__ feat, const float* __restrict__ rois, int K, int C, int H, int W,
+                              int RP, float scale, int aligned, int nhwc, float* __restrict__ out) {
+    constexpr int NCH = CB / 4;               // float4 chunks per pixel
+    constexpr int RS = kFastFwdThreads / 49;  // rois worked on at the same time (9)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FastHdr* hd = reinterpret_cast<FastHdr*>(smem_raw);
-    unsigned char* geo = smem_raw + kHdrBytes;  // [GC] rois
-    const int GC = kAlign ? RP : kPoolGeoCap;    // rois whose geometry is computed together
-    const int stage = RP * CB * 49;              // values in the staging tile: [roi][channel][49]
-    float* s_out = reinterpret_cast<float*>(geo + ((GC * kGeoPer + 127) & ~127));
-    int32_t* s_arg = reinterpret_cast<int32_t*>(s_out + stage);  // (kArg only)
-    float4* px = reinterpret_cast<float4*>(kArg ? reinterpret_cast<unsigned char*>(s_arg + stage)
-                                                : reinterpret_cast<unsigned char*>(s_arg));
+    AlignRec* geo = reinterpret_cast<AlignRec*>(smem_raw + kHdrBytes);  // [RP][28] 1-D sample records
+    const int stage = RP * CB * 49;                                     // values in the staging tile: [roi][channel][49]
+    float* s_out = reinterpret_cast<float*>(smem_raw + kHdrBytes + ((RP * 28 * 16 + 127) & ~127));
+    float4* px = reinterpret_cast<float4*>(s_out + stage);
 
     const int tid = threadIdx.x;
     const int b = blockIdx.y, c0 = blockIdx.x * CB;
@@ -199,123 +229,63 @@ __global__ void __launch_bounds__(kFastFwdThreads, (CB <= 8) ? 2 : 1)
     load_pixels<CB>(px, feat, b, c0, C, HW, nhwc != 0);
     ROI_TICK(0);
 
-    // thread -> (roi slot rs, bin): the 49 bins of a roi sit in consecutive lanes (same window size +-1)
+    // thread -> (roi slot rs, bin): the 49 bins of a roi sit in consecutive lanes
     const int rs = tid / 49;
     const int bin = tid - rs * 49;
     const int ph = bin / 7, pw = bin - ph * 7;
     const bool worker = rs < RS;
     // vector copy-out needs 16-byte aligned runs of cb*49 values
     const bool vec_ok = ((cb * 196) % 16 == 0) && (((size_t)C * 196) % 16 == 0) && (((size_t)c0 * 196) % 16 == 0) &&
-                        ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) &&
-                        (!kArg || (reinterpret_cast<uintptr_t>(argmax) & 15u) == 0);
+                        ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
 
     for (int tile = 0; tile < K; tile += kFastFwdThreads) {
         const int ns = stage_ids(rois, K, tile, b, hd);
         ROI_TICK(1);
-        for (int g0 = 0; g0 < ns; g0 += GC) {
-          // ---- geometry of rois g0 .. g0+GC, once per roi ------------------------------------------------
-          const int ng = min(GC, ns - g0);
-          for (int t = tid; t < ng * 28; t += kFastFwdThreads) {
-              const int s = t / 28, j = t - s * 28;
-              const float* r = rois + 5 * (size_t)hd->id[g0 + s];
-              if (!kAlign) {
-                  const int kind = j / 7, p = j - kind * 7;  // hs[7] he[7] ws[7] we[7]
-                  const PoolGeom gm = pool_geom(r, scale);
-                  int v;
-                  if (kind < 2) {
-                      const float bsz = __fdiv_rn((float)gm.rh, 7.0f);
-                      v = (kind == 0 ? (int)floorf(__fmul_rn((float)p, bsz)) : (int)ceilf(__fmul_rn((float)(p + 1), bsz))) + gm.sh;
-                      v = min(max(v, 0), H);
-                  } else {
-                      const float bsz = __fdiv_rn((float)gm.rw, 7.0f);
-                      v = (kind == 2 ? (int)floorf(__fmul_rn((float)p, bsz)) : (int)ceilf(__fmul_rn((float)(p + 1), bsz))) + gm.sw;
-                      v = min(max(v, 0), W);
-                  }
-                  reinterpret_cast<short*>(geo)[t] = (short)v;
-              } else {  // y samples 0..13, x samples 0..13
-                  const AlignGeom gm = align_geom(r, scale, 7, 7, 2, aligned != 0);
-                  reinterpret_cast<AlignRec*>(geo)[t] = (j < 14) ? align_rec(sample_y(gm, j >> 1, j & 1), H)
-                                                                 : align_rec(sample_x(gm, (j - 14) >> 1, (j - 14) & 1), W);
-              }
-          }
-          __syncthreads();
-          ROI_TICK(2);
-          for (int p0 = g0; p0 < g0 + ng; p0 += RP) {
-            const int nr = min(RP, g0 + ng - p0);
-            const int gs = p0 - g0;  // geometry slot of the pass's first roi
+        for (int p0 = 0; p0 < ns; p0 += RP) {
+            const int nr = min(RP, ns - p0);
+            // ---- 14 y-sample and 14 x-sample records per roi, once per roi ---------------------------------
+            for (int t = tid; t < nr * 28; t += kFastFwdThreads) {
+                const int s = t / 28, j = t - s * 28;
+                const AlignGeom gm = align_geom(rois + 5 * (size_t)hd->id[p0 + s], scale, 7, 7, 2, aligned != 0);
+                geo[t] = (j < 14) ? align_rec(sample_y(gm, j >> 1, j & 1), H)
+                                  : align_rec(sample_x(gm, (j - 14) >> 1, (j - 14) & 1), W);
+            }
+            __syncthreads();
+            ROI_TICK(2);
             if (worker) {
 #pragma unroll 1
                 for (int s = rs; s < nr; s += RS) {
                     float* so = s_out + s * CB * 49 + bin;
-                    if (!kAlign) {
-                        const short* bnd = reinterpret_cast<const short*>(geo) + (gs + s) * 28;
-                        const int hs = bnd[ph], he = bnd[7 + ph], ws = bnd[14 + pw], we = bnd[21 + pw];
-                        const float init = ((he <= hs) || (we <= ws)) ? 0.f : -FLT_MAX;
-                        float best[CB];
-                        int bidx[CB];
+                    const AlignRec* rec = geo + s * 28;
+                    float acc[CB];
 #pragma unroll
-                        for (int c = 0; c < CB; ++c) { best[c] = init; bidx[c] = -1; }
+                    for (int c = 0; c < CB; ++c) acc[c] = 0.f;
 #pragma unroll 1
-                        for (int h = hs; h < he; ++h) {
-#pragma unroll 1
-                            for (int idx = h * W + ws; idx < h * W + we; ++idx) {
-                                const float4* pp = px + (size_t)idx * NCH;
+                    for (int s4 = 0; s4 < 4; ++s4) {
+                        const AlignRec yy = rec[2 * ph + (s4 >> 1)];
+                        const AlignRec xx = rec[14 + 2 * pw + (s4 & 1)];
+                        if (yy.lo >= 0 && xx.lo >= 0) {
+                            const float w1 = __fmul_rn(yy.h, xx.h), w2 = __fmul_rn(yy.h, xx.l);
+                            const float w3 = __fmul_rn(yy.l, xx.h), w4 = __fmul_rn(yy.l, xx.l);
+                            const int i1 = yy.lo * W + xx.lo, i2 = yy.lo * W + xx.hi;
+                            const int i3 = yy.hi * W + xx.lo, i4 = yy.hi * W + xx.hi;
 #pragma unroll
-                                for (int k = 0; k < NCH; ++k) {
-                                    const float4 v = pp[chunk_slot<CB>(idx, k)];
-                                    if (kArg) {
-                                        if (v.x > best[4 * k + 0]) { best[4 * k + 0] = v.x; bidx[4 * k + 0] = idx; }
-                                        if (v.y > best[4 * k + 1]) { best[4 * k + 1] = v.y; bidx[4 * k + 1] = idx; }
-                                        if (v.z > best[4 * k + 2]) { best[4 * k + 2] = v.z; bidx[4 * k + 2] = idx; }
-                                        if (v.w > best[4 * k + 3]) { best[4 * k + 3] = v.w; bidx[4 * k + 3] = idx; }
-                                    } else {
-                                        best[4 * k + 0] = fmaxf(best[4 * k + 0], v.x);
-                                        best[4 * k + 1] = fmaxf(best[4 * k + 1], v.y);
-                                        best[4 * k + 2] = fmaxf(best[4 * k + 2], v.z);
-                                        best[4 * k + 3] = fmaxf(best[4 * k + 3], v.w);
-                                    }
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int c = 0; c < CB; ++c) so[c * 49] = best[c];
-                        if (kArg) {
-                            int32_t* sa = s_arg + s * CB * 49 + bin;
-#pragma unroll
-                            for (int c = 0; c < CB; ++c) sa[c * 49] = bidx[c];
-                        }
-                    } else {
-                        const AlignRec* rec = reinterpret_cast<const AlignRec*>(geo) + (gs + s) * 28;
-                        float acc[CB];
-#pragma unroll
-                        for (int c = 0; c < CB; ++c) acc[c] = 0.f;
-#pragma unroll 1
-                        for (int s4 = 0; s4 < 4; ++s4) {
-                            const AlignRec yy = rec[2 * ph + (s4 >> 1)];
-                            const AlignRec xx = rec[14 + 2 * pw + (s4 & 1)];
-                            if (yy.lo >= 0 && xx.lo >= 0) {
-                                const float w1 = __fmul_rn(yy.h, xx.h), w2 = __fmul_rn(yy.h, xx.l);
-                                const float w3 = __fmul_rn(yy.l, xx.h), w4 = __fmul_rn(yy.l, xx.l);
-                                const int i1 = yy.lo * W + xx.lo, i2 = yy.lo * W + xx.hi;
-                                const int i3 = yy.hi * W + xx.lo, i4 = yy.hi * W + xx.hi;
-#pragma unroll
-                                for (int k = 0; k < NCH; ++k) {
-                                    const float4 v1 = px[(size_t)i1 * NCH + chunk_slot<CB>(i1, k)];
-                                    const float4 v2 = px[(size_t)i2 * NCH + chunk_slot<CB>(i2, k)];
-                                    const float4 v3 = px[(size_t)i3 * NCH + chunk_slot<CB>(i3, k)];
-                                    const float4 v4 = px[(size_t)i4 * NCH + chunk_slot<CB>(i4, k)];
+                            for (int k = 0; k < NCH; ++k) {
+                                const float4 v1 = px[(size_t)i1 * NCH + chunk_slot<CB>(i1, k)];
+                                const float4 v2 = px[(size_t)i2 * NCH + chunk_slot<CB>(i2, k)];
+                                const float4 v3 = px[(size_t)i3 * NCH + chunk_slot<CB>(i3, k)];
+                                const float4 v4 = px[(size_t)i4 * NCH + chunk_slot<CB>(i4, k)];
 #define FRR_BIL(e, c)                                                                                                   \
     acc[4 * k + e] = __fadd_rn(acc[4 * k + e],                                                                          \
                                __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, v1.c), __fmul_rn(w2, v2.c)), __fmul_rn(w3, v3.c)), \
                                          __fmul_rn(w4, v4.c)))
-                                    FRR_BIL(0, x); FRR_BIL(1, y); FRR_BIL(2, z); FRR_BIL(3, w);
+                                FRR_BIL(0, x); FRR_BIL(1, y); FRR_BIL(2, z); FRR_BIL(3, w);
 #undef FRR_BIL
-                                }
                             }
                         }
-#pragma unroll
-                        for (int c = 0; c < CB; ++c) so[c * 49] = __fdiv_rn(acc[c], 4.0f);
                     }
+#pragma unroll
+                    for (int c = 0; c < CB; ++c) so[c * 49] = __fdiv_rn(acc[c], 4.0f);
                 }
             }
             __syncthreads();
@@ -328,22 +298,134 @@ __global__ void __launch_bounds__(kFastFwdThreads, (CB <= 8) ? 2 : 1)
                     const size_t o = ((size_t)hd->id[p0 + s] * C + c0) * 49;
                     if (vec_ok) {
                         const float4* so4 = reinterpret_cast<const float4*>(s_out + s * CB * 49);
-                        const int4* sa4 = reinterpret_cast<const int4*>(s_arg + s * CB * 49);
-                        for (int e = lane; e < cb * 49 / 4; e += 32) {
-                            st_stream(reinterpret_cast<float4*>(out + o) + e, so4[e]);
-                            if (kArg) reinterpret_cast<int4*>(argmax + o)[e] = sa4[e];
-                        }
+                        for (int e = lane; e < cb * 49 / 4; e += 32) st_stream(reinterpret_cast<float4*>(out + o) + e, so4[e]);
                     } else {
-                        for (int e = lane; e < cb * 49; e += 32) {
-                            out[o + e] = s_out[s * CB * 49 + e];
-                            if (kArg) argmax[o + e] = s_arg[s * CB * 49 + e];
-                        }
+                        for (int e = lane; e < cb * 49; e += 32) out[o + e] = s_out[s * CB * 49 + e];
                     }
                 }
             }
-            __syncthreads();  // the staging tile (and, after the last pass, the geometry) is rewritten next
+            __syncthreads();  // the staging tile and the sample records are rewritten next
             ROI_TICK(4);
-          }
+        }
+    }
+    ROI_TICK(5);
+}
+
+// ---------------------------------------------------------------------------------------------
+// RoIPool forward without per-pass barriers (R1/R2)
+// ---------------------------------------------------------------------------------------------
+// The staged version above spends more issue slots waiting at its per-pass barriers (compute -> copy-out -> next 9
+// rois) than in any other stall (ncu: 3.7 of 12 stall cycles per issued instruction).  Here a WARP owns a share of the
+// image's rois (round-robin over the list ordered by window size, so the shares are balanced) and walks the
+// flattened (roi, bin) sequence of its share 32 bins at a time: every lane always has a bin (49 bins per roi do not
+// leave 15 of 64 lanes idle), neighbouring lanes work on the same or a similarly sized roi, and the only barriers
+// left are the ones around the per-image roi list.  Results are stored directly: the lanes of a warp hold consecutive
+// bins of one (roi, channel) row, i.e. consecutive addresses of the [K,C,7,7] output -- no staging tile, which also
+// frees ~28 KB of shared memory per CTA.
+constexpr int kFlatThreads = 448;
+constexpr int kFlatGeoCap = 252;  // rois whose bin boundaries are held at once (56 bytes each)
+
+template <int CB, bool kArg>
+__global__ void __launch_bounds__(kFlatThreads, (CB <= 8) ? 2 : 1)
+    roi_pool_fwd_flat_kernel(const float* __restrict__ feat, const float* __restrict__ rois, int K, int C, int H, int W,
+                             float scale, int nhwc, float* __restrict__ out, int32_t* __restrict__ argmax) {
+    constexpr int NCH = CB / 4;
+    constexpr int kWarps = kFlatThreads / 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FastHdr* hd = reinterpret_cast<FastHdr*>(smem_raw);
+    short* geo = reinterpret_cast<short*>(smem_raw + kHdrBytes);  // [kFlatGeoCap][28]: hs[7] he[7] ws[7] we[7]
+    float4* px = reinterpret_cast<float4*>(smem_raw + kHdrBytes + ((kFlatGeoCap * 56 + 127) & ~127));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y, c0 = blockIdx.x * CB;
+    const int HW = H * W;
+    const int cb = min(CB, C - c0);
+    const bool prof = (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0);
+    long long t0_ = clock64();
+    load_pixels<CB>(px, feat, b, c0, C, HW, nhwc != 0);
+    ROI_TICK(0);
+
+    for (int tile = 0; tile < K; tile += kFlatThreads) {
+        const int ns = stage_ids(rois, K, tile, b, hd);
+        if (ns == 0) continue;  // block-uniform
+        if (ns > kWarps) order_ids_by_window(rois, scale, ns, hd);
+        ROI_TICK(1);
+        for (int g0 = 0; g0 < ns; g0 += kFlatGeoCap) {
+            const int ng = min(kFlatGeoCap, ns - g0);
+            for (int t = tid; t < ng * 28; t += kFlatThreads) {
+                const int s = t / 28, j = t - s * 28;
+                const int kind = j / 7, p = j - kind * 7;
+                const PoolGeom gm = pool_geom(rois + 5 * (size_t)hd->id[g0 + s], scale);
+                int v;
+                if (kind < 2) {
+                    const float bsz = __fdiv_rn((float)gm.rh, 7.0f);
+                    v = (kind == 0 ? (int)floorf(__fmul_rn((float)p, bsz)) : (int)ceilf(__fmul_rn((float)(p + 1), bsz))) + gm.sh;
+                    v = min(max(v, 0), H);
+                } else {
+                    const float bsz = __fdiv_rn((float)gm.rw, 7.0f);
+                    v = (kind == 2 ? (int)floorf(__fmul_rn((float)p, bsz)) : (int)ceilf(__fmul_rn((float)(p + 1), bsz))) + gm.sw;
+                    v = min(max(v, 0), W);
+                }
+                geo[t] = (short)v;
+            }
+            __syncthreads();
+            ROI_TICK(2);
+            const int nr = (ng > warp) ? (ng - warp + kWarps - 1) / kWarps : 0;  // rois of this warp: warp, warp + 14, ...
+            const int total = nr * 49;
+#pragma unroll 1
+            for (int f = lane; f < total; f += 32) {
+                const int li = f / 49, bin = f - li * 49;
+                const int s = warp + li * kWarps;
+                const int ph = bin / 7, pw = bin - ph * 7;
+                const short* bnd = geo + s * 28;
+                const int hs = bnd[ph], he = bnd[7 + ph], ws = bnd[14 + pw], we = bnd[21 + pw];
+                const float init = ((he <= hs) || (we <= ws)) ? 0.f : -FLT_MAX;
+                float best[CB];
+                int bidx[CB];
+#pragma unroll
+                for (int c = 0; c < CB; ++c) { best[c] = init; bidx[c] = -1; }
+#pragma unroll 1
+                for (int h = hs; h < he; ++h) {
+#pragma unroll 1
+                    for (int idx = h * W + ws; idx < h * W + we; ++idx) {
+                        const float4* pp = px + (size_t)idx * NCH;
+#pragma unroll
+                        for (int k = 0; k < NCH; ++k) {
+                            const float4 v = pp[chunk_slot<CB>(idx, k)];
+                            if (kArg) {
+                                // first strict maximum in scan order (torchvision).  Compare + index select on the ALU
+                                // pipe, the conditional move of the maximum as a predicated FFMA (x * 1 - 0, exact) on
+                                // the FMA pipe
+#define FRR_UPD(val, c)                                                                                                   \
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %2, %0;\n\t@p fma.rn.f32 %0, %2, 0f3F800000, 0f80000000;\n\tselp.b32 %1, %3, %1, p;\n\t}" \
+        : "+f"(best[c]), "+r"(bidx[c])                                                                                     \
+        : "f"(val), "r"(idx))
+                                FRR_UPD(v.x, 4 * k + 0); FRR_UPD(v.y, 4 * k + 1);
+                                FRR_UPD(v.z, 4 * k + 2); FRR_UPD(v.w, 4 * k + 3);
+#undef FRR_UPD
+                            } else {
+                                best[4 * k + 0] = fmaxf(best[4 * k + 0], v.x);
+                                best[4 * k + 1] = fmaxf(best[4 * k + 1], v.y);
+                                best[4 * k + 2] = fmaxf(best[4 * k + 2], v.z);
+                                best[4 * k + 3] = fmaxf(best[4 * k + 3], v.w);
+                            }
+                        }
+                    }
+                }
+                // lanes = consecutive bins of a (roi, channel) row = consecutive addresses; write-once -> streaming stores
+                const size_t o = ((size_t)hd->id[g0 + s] * C + c0) * 49 + bin;
+#pragma unroll
+                for (int c = 0; c < CB; ++c)
+                    if (c < cb) __stcs(out + o + c * 49, best[c]);
+                if (kArg) {
+#pragma unroll
+                    for (int c = 0; c < CB; ++c)
+                        if (c < cb) __stcs(argmax + o + c * 49, bidx[c]);
+                }
+            }
+            ROI_TICK(3);
+            __syncthreads();  // the boundaries (and, after the last group, the id list) are rewritten next
+            ROI_TICK(4);
         }
     }
     ROI_TICK(5);
@@ -585,19 +667,18 @@ __global__ void __launch_bounds__(CB * 32, 1)
 // ---------------------------------------------------------------------------------------------
 static const size_t kSmemLimit = 227 * 1024;
 
-// rois per pass for a shared-memory budget: as many as fit beside the pixels, a multiple of 9 (9 rois are worked on
-// at the same time: 448 threads / 49 bins), capped; 0 = no fit
-static int fwd_fast_rp(int CB, int HW, bool align, bool arg, size_t budget) {
-    const size_t fixed = kHdrBytes + 128 + (size_t)CB * HW * 4 + (align ? 0 : (size_t)kPoolGeoCap * 56);
+// RoIAlign: rois per pass for a shared-memory budget: as many as fit beside the pixels, a multiple of 9 (9 rois are
+// worked on at the same time: 448 threads / 49 bins), capped; 0 = no fit
+static int align_fwd_rp(int CB, int HW, size_t budget) {
+    const size_t fixed = kHdrBytes + 128 + (size_t)CB * HW * 4;
     if (fixed >= budget) return 0;
-    const size_t per_roi = (size_t)CB * 49 * 4 * (arg ? 2 : 1) + (align ? 28 * 16 : 0);
+    const size_t per_roi = (size_t)CB * 49 * 4 + 28 * 16;
     int rp = (int)((budget - fixed) / per_roi);
     if (rp > 36) rp = 36;
     return rp / 9 * 9;
 }
-static size_t fwd_fast_smem(int CB, int HW, bool align, bool arg, int rp) {
-    const size_t geo = ((align ? (size_t)rp * 28 * 16 : (size_t)kPoolGeoCap * 56) + 127) & ~(size_t)127;
-    return kHdrBytes + geo + (size_t)rp * CB * 49 * 4 * (arg ? 2 : 1) + (size_t)CB * HW * 4;
+static size_t align_fwd_smem(int CB, int HW, int rp) {
+    return kHdrBytes + (((size_t)rp * 28 * 16 + 127) & ~(size_t)127) + (size_t)rp * CB * 49 * 4 + (size_t)CB * HW * 4;
 }
 // CB <= 8 kernels are built for two CTAs per SM (28 warps hide the shared-memory latency of the window loops)
 static size_t fwd_budget(int CB) { return CB <= 8 ? (kSmemLimit - 2048) / 2 : kSmemLimit; }
@@ -605,16 +686,28 @@ static size_t bwd_fast_smem(int CB, int HW) {
     return kHdrBytes + (size_t)CB * HW * 4 + (size_t)CB * ((HW + 15) & ~15) + (size_t)CB * 7 * 32 * 8;
 }
 
-template <bool kAlign, bool kArg, int CB>
-static int launch_fwd(const float* feat, const float* rois, int K, int B, int C, int H, int W, float scale, int aligned,
-                      int nhwc, float* out, int32_t* argmax, cudaStream_t st) {
-    auto kern = roi_fwd_fast_kernel<CB, kAlign, kArg>;
-    int rp = fwd_fast_rp(CB, H * W, kAlign, kArg, fwd_budget(CB));
-    if (rp == 0) rp = fwd_fast_rp(CB, H * W, kAlign, kArg, kSmemLimit);
-    const size_t smem = fwd_fast_smem(CB, H * W, kAlign, kArg, rp);
+template <int CB>
+static int launch_align_fwd(const float* feat, const float* rois, int K, int B, int C, int H, int W, float scale, int aligned,
+                            int nhwc, float* out, cudaStream_t st) {
+    auto kern = roi_align_fwd_fast_kernel<CB>;
+    int rp = align_fwd_rp(CB, H * W, fwd_budget(CB));
+    if (rp == 0) rp = align_fwd_rp(CB, H * W, kSmemLimit);
     FRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-    kern<<<dim3((C + CB - 1) / CB, B), kFastFwdThreads, smem, st>>>(feat, rois, K, C, H, W, rp, scale, aligned, nhwc, out,
-                                                                     argmax);
+    kern<<<dim3((C + CB - 1) / CB, B), kFastFwdThreads, align_fwd_smem(CB, H * W, rp), st>>>(feat, rois, K, C, H, W, rp, scale,
+                                                                                              aligned, nhwc, out);
+    return FRR_OK;
+}
+
+static size_t flat_smem(int CB, int HW) {
+    return kHdrBytes + ((kFlatGeoCap * 56 + 127) & ~(size_t)127) + (size_t)CB * HW * 4;
+}
+template <bool kArg, int CB>
+static int launch_flat(const float* feat, const float* rois, int K, int B, int C, int H, int W, float scale, int nhwc,
+                       float* out, int32_t* argmax, cudaStream_t st) {
+    auto kern = roi_pool_fwd_flat_kernel<CB, kArg>;
+    FRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    kern<<<dim3((C + CB - 1) / CB, B), kFlatThreads, flat_smem(CB, H * W), st>>>(feat, rois, K, C, H, W, scale, nhwc, out,
+                                                                                  argmax);
     return FRR_OK;
 }
 
@@ -623,24 +716,38 @@ int roi_fwd_fast(bool align, const float* feat, const float* rois, int K, int B,
     if (PH != 7 || PW != 7 || (align && sampling != 2) || H > 32767 || W > 32767) return 1;
     const bool arg = !align && argmax != nullptr;
     const int HW = H * W;
-    // CB = 8 when two CTAs fit an SM, else 4 when two fit, else the largest of {16, 8, 4} that fits at all
-    int cbk = 0;
-    for (int t = 8; t >= 4 && cbk == 0; t >>= 1)
-        if (fwd_fast_rp(t, HW, align, arg, fwd_budget(t)) > 0) cbk = t;
-    for (int t = 16; t >= 4 && cbk == 0; t >>= 1)
-        if (fwd_fast_rp(t, HW, align, arg, kSmemLimit) > 0) cbk = t;
-    if (cbk == 0) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-#define FRR_FWD(CBK)                                                                                                 \
-    (align ? launch_fwd<true, false, CBK>(feat, rois, K, B, C, H, W, scale, aligned, nhwc, out, argmax, st)          \
-     : arg ? launch_fwd<false, true, CBK>(feat, rois, K, B, C, H, W, scale, aligned, nhwc, out, argmax, st)          \
-           : launch_fwd<false, false, CBK>(feat, rois, K, B, C, H, W, scale, aligned, nhwc, out, argmax, st))
-    rc = cbk == 16 ? FRR_FWD(16) : cbk == 8 ? FRR_FWD(8) : FRR_FWD(4);
-#undef FRR_FWD
+    if (!align) {
+        // CB = 8 (else 4) when two CTAs fit an SM, else the largest of {16, 8, 4} that fits at all
+        int cbk = 0;
+        if (flat_smem(8, HW) <= fwd_budget(8)) cbk = 8;
+        else if (flat_smem(4, HW) <= fwd_budget(4)) cbk = 4;
+        for (int t = 16; t >= 4 && cbk == 0; t >>= 1)
+            if (flat_smem(t, HW) <= kSmemLimit) cbk = t;
+        if (cbk == 0) return 1;
+#define FRR_FLAT(CBK)                                                                                   \
+    (arg ? launch_flat<true, CBK>(feat, rois, K, B, C, H, W, scale, nhwc, out, argmax, st)              \
+         : launch_flat<false, CBK>(feat, rois, K, B, C, H, W, scale, nhwc, out, argmax, st))
+        rc = cbk == 16 ? FRR_FLAT(16) : cbk == 8 ? FRR_FLAT(8) : FRR_FLAT(4);
+#undef FRR_FLAT
+        if (rc) return rc;
+        count_launch();
+        FRR_CHECK_LAUNCH("roi_pool_fwd_flat_kernel");
+        return FRR_OK;
+    }
+    int cbk = 0;
+    for (int t = 8; t >= 4 && cbk == 0; t >>= 1)
+        if (align_fwd_rp(t, HW, fwd_budget(t)) > 0) cbk = t;
+    for (int t = 16; t >= 4 && cbk == 0; t >>= 1)
+        if (align_fwd_rp(t, HW, kSmemLimit) > 0) cbk = t;
+    if (cbk == 0) return 1;
+    rc = cbk == 16 ? launch_align_fwd<16>(feat, rois, K, B, C, H, W, scale, aligned, nhwc, out, st)
+         : cbk == 8 ? launch_align_fwd<8>(feat, rois, K, B, C, H, W, scale, aligned, nhwc, out, st)
+                    : launch_align_fwd<4>(feat, rois, K, B, C, H, W, scale, aligned, nhwc, out, st);
     if (rc) return rc;
     count_launch();
-    FRR_CHECK_LAUNCH("roi_fwd_fast_kernel");
+    FRR_CHECK_LAUNCH("roi_align_fwd_fast_kernel");
     return FRR_OK;
 }
 
