@@ -40,6 +40,7 @@ SIGNATURES = {
     "frr_roi_align_bwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _i, _p, _p]),
     "frr_roi_debug_cycles": (_i, [_p]),
     "frr_fpn_level_rois": (_i, [_p, _i, _i, _i, _i, _f, _i, _p, _p, _p]),
+    "frr_region_loss": (_i, [_p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p, _p]),
     "frr_sample_targets": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _i, _p, _p, _i, _p]),
     "frr_rpn_targets_assign": (_i, [_p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _f, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "frr_rpn_targets_finalize": (_i, [_p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),

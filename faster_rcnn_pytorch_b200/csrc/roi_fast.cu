@@ -370,12 +370,14 @@ __global__ void __launch_bounds__(kFlatThreads, (CB <= 8) ? 2 : 1)
             }
             __syncthreads();
             ROI_TICK(2);
-            const int nr = (ng > warp) ? (ng - warp + kWarps - 1) / kWarps : 0;  // rois of this warp: warp, warp + 14, ...
-            const int total = nr * 49;
+            // rois of this warp: one of every 14 consecutive ranks, in boustrophedon order (rank 14 g + warp for even g,
+            // 14 g + 13 - warp for odd g) so that no warp always gets the largest roi of its group
+            const int total = ((ng + kWarps - 1) / kWarps) * 49;
 #pragma unroll 1
             for (int f = lane; f < total; f += 32) {
                 const int li = f / 49, bin = f - li * 49;
-                const int s = warp + li * kWarps;
+                const int s = li * kWarps + ((li & 1) ? kWarps - 1 - warp : warp);
+                if (s >= ng) continue;  // last, partial group
                 const int ph = bin / 7, pw = bin - ph * 7;
                 const short* bnd = geo + s * 28;
                 const int hs = bnd[ph], he = bnd[7 + ph], ws = bnd[14 + pw], we = bnd[21 + pw];

@@ -16,7 +16,7 @@ import torch.nn as nn
 from . import ops, region, targets
 
 __all__ = ["nms", "roi_pool", "roi_align", "RoIPool", "RoIAlign", "MultiScaleRoIAlign", "RegionProposal", "RPNTargetMaker",
-           "FastRcnnTargetMaker", "predict_tail", "suppress", "fpn"]
+           "FastRcnnTargetMaker", "predict_tail", "suppress", "fpn", "RPNLoss", "FastRCNNLoss", "FRCNNLoss"]
 
 roi_pool = ops.roi_pool
 roi_align = ops.roi_align
@@ -169,6 +169,50 @@ class fpn:
                                                           labels.detach().to(torch.int64).unsqueeze(0), variant="fpn")
             k = int(n[0])
             return cls[0, :k], reg[0, :k], srois[0, :k]
+
+
+class RPNLoss(nn.Module):
+    """Drop-in for losses/loss.py:17-41: ``forward(pred_cls [1,N,2], pred_reg [1,N,4], target_cls [N], target_reg [N,4])``
+    -> (rpn_cls_loss, rpn_reg_loss), differentiable w.r.t. the predictions (one fused kernel)."""
+
+    def forward(self, pred_cls, pred_reg, target_cls, target_reg):
+        n = target_cls.shape[-1]
+        loss = ops.region_loss(rpn_cls=pred_cls.reshape(1, n, 2), rpn_reg=pred_reg.reshape(1, n, 4),
+                               rpn_target_cls=target_cls.reshape(1, n).to(torch.int64),
+                               rpn_target_reg=target_reg.reshape(1, n, 4))
+        return loss[0, 1], loss[0, 2]
+
+
+class FastRCNNLoss(nn.Module):
+    """Drop-in for losses/loss.py:44-59: ``forward(pred_cls [S,C], pred_reg, target_cls [S], target_reg [S,4])`` ->
+    (fast_rcnn_cls_loss, fast_rcnn_reg_loss).  ``pred_reg`` is either the gathered [S,4] the reference passes
+    (models/model.py:340-341) or the head's [S,C*4]: the class row is then picked inside the kernel."""
+
+    def forward(self, pred_cls, pred_reg, target_cls, target_reg):
+        s = target_cls.shape[-1]
+        c = pred_cls.shape[-1]
+        loss = ops.region_loss(frcnn_cls=pred_cls.reshape(1, s, c), frcnn_reg=pred_reg.reshape(1, s, -1),
+                               frcnn_target_cls=target_cls.reshape(1, s).to(torch.int64),
+                               frcnn_target_reg=target_reg.reshape(1, s, 4))
+        return loss[0, 3], loss[0, 4]
+
+
+class FRCNNLoss(nn.Module):
+    """Drop-in for losses/loss.py:62-82: ``forward(pred, target)`` with the 4-tuples of ``FRCNN.forward`` ->
+    (total, rpn_cls, rpn_reg, fast_rcnn_cls, fast_rcnn_reg)."""
+
+    def __init__(self, opts=None):
+        super().__init__()
+        self.opts = opts
+
+    def forward(self, pred, target):
+        rc, rr, fc, fr = pred
+        t_rc, t_rr, t_fc, t_fr = target
+        n, s, c = t_rc.shape[-1], t_fc.shape[-1], fc.shape[-1]
+        loss = ops.region_loss(rc.reshape(1, n, 2), rr.reshape(1, n, 4), t_rc.reshape(1, n).to(torch.int64),
+                               t_rr.reshape(1, n, 4), fc.reshape(1, s, c), fr.reshape(1, s, -1),
+                               t_fc.reshape(1, s).to(torch.int64), t_fr.reshape(1, s, 4))
+        return loss[0, 0], loss[0, 1], loss[0, 2], loss[0, 3], loss[0, 4]
 
 
 def predict_tail(pred_cls, pred_reg, rois, num_classes: int):

@@ -438,6 +438,83 @@ def sample_targets(mt_state, ws_rpn=None, ws_frcnn=None, rpn_batch: int = 256, r
 
 
 # ------------------------------------------------------------------------------------------------
+# loss side (losses/loss.py:5-59 + the class-row gather of models/model.py:340-341)
+# ------------------------------------------------------------------------------------------------
+RPN_BETA, FRCNN_BETA = float(np.float32(1 / 9)), 1.0      # losses/loss.py:21,47
+
+
+class _RegionLossFn(torch.autograd.Function):
+    """One kernel computes the four losses and, for a unit upstream gradient, their gradients w.r.t. the predictions;
+    backward only scales the saved gradients by the upstream values."""
+
+    @staticmethod
+    def forward(ctx, rpn_cls, rpn_reg, frc_cls, frc_reg, rpn_tcls, rpn_treg, frc_tcls, frc_treg):
+        lib = _lib.load()
+        have_rpn, have_frc = rpn_cls is not None, frc_cls is not None
+        ref = rpn_cls if have_rpn else frc_cls
+        dev = ref.device
+        B = ref.shape[0]
+        N = rpn_cls.shape[1] if have_rpn else 0
+        S, C = (frc_cls.shape[1], frc_cls.shape[2]) if have_frc else (0, 0)
+        CR = frc_reg.shape[2] if have_frc else 0
+        need = [have_rpn and ctx.needs_input_grad[0], have_rpn and ctx.needs_input_grad[1],
+                have_frc and ctx.needs_input_grad[2], have_frc and ctx.needs_input_grad[3]]
+        with torch.cuda.device(dev):
+            loss = torch.empty((B, 5), dtype=torch.float32, device=dev)
+            grads = [torch.empty_like(t) if n else None for t, n in zip((rpn_cls, rpn_reg, frc_cls, frc_reg), need)]
+            _lib.check(lib.frr_region_loss(_ptr(rpn_cls), _ptr(rpn_reg), _ptr(rpn_tcls), _ptr(rpn_treg), B, N, _ptr(frc_cls),
+                                           _ptr(frc_reg), _ptr(frc_tcls), _ptr(frc_treg), S, C, CR, RPN_BETA, FRCNN_BETA,
+                                           loss.data_ptr(), _ptr(grads[0]), _ptr(grads[1]), _ptr(grads[2]), _ptr(grads[3]),
+                                           _stream()), "frr_region_loss")
+        ctx.grads = grads
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):            # g [B,5]: upstream of (total, rpn_cls, rpn_reg, frcnn_cls, frcnn_reg)
+        out = []
+        for j, saved in enumerate(ctx.grads):
+            if saved is None:
+                out.append(None)
+                continue
+            up = (g[:, 0] + g[:, 1 + j]).reshape((-1,) + (1,) * (saved.dim() - 1))
+            out.append(saved * up)
+        return tuple(out) + (None, None, None, None)
+
+
+def region_loss(rpn_cls=None, rpn_reg=None, rpn_target_cls=None, rpn_target_reg=None, frcnn_cls=None, frcnn_reg=None,
+                frcnn_target_cls=None, frcnn_target_reg=None):
+    """Batched FRCNNLoss (losses/loss.py:62-82): per image (total, rpn_cls, rpn_reg, frcnn_cls, frcnn_reg) -> [B,5],
+    differentiable w.r.t. the four prediction tensors.  rpn_cls [B,N,2], rpn_reg [B,N,4], rpn_target_cls int64 [B,N],
+    rpn_target_reg [B,N,4]; frcnn_cls [B,S,C], frcnn_reg [B,S,C,4] (or [B,S,C*4]: the head output, the class row is
+    gathered in the kernel, models/model.py:340-341) or [B,S,4] (already gathered), frcnn_target_cls int64 [B,S]
+    (negative = padding), frcnn_target_reg [B,S,4].  Either half may be omitted."""
+    if rpn_cls is None and frcnn_cls is None:
+        raise ValueError("region_loss: nothing to compute")
+    if rpn_cls is not None:
+        rpn_cls, rpn_reg, rpn_target_reg = _req(rpn_cls, "rpn_cls"), _req(rpn_reg, "rpn_reg"), _req(rpn_target_reg, "rpn_target_reg")
+        rpn_target_cls = _req(rpn_target_cls, "rpn_target_cls", torch.int64)
+        B, N = rpn_cls.shape[0], rpn_cls.shape[1]
+        if tuple(rpn_cls.shape) != (B, N, 2) or tuple(rpn_reg.shape) != (B, N, 4) or tuple(rpn_target_cls.shape) != (B, N) \
+                or tuple(rpn_target_reg.shape) != (B, N, 4):
+            raise ValueError("region_loss: RPN tensors must be [B,N,2], [B,N,4], [B,N], [B,N,4]")
+    if frcnn_cls is not None:
+        frcnn_cls, frcnn_reg = _req(frcnn_cls, "frcnn_cls"), _req(frcnn_reg, "frcnn_reg")
+        frcnn_target_cls = _req(frcnn_target_cls, "frcnn_target_cls", torch.int64)
+        frcnn_target_reg = _req(frcnn_target_reg, "frcnn_target_reg")
+        B, S, C = frcnn_cls.shape
+        if frcnn_reg.numel() == B * S * C * 4:
+            frcnn_reg = frcnn_reg.reshape(B, S, C, 4)
+        elif frcnn_reg.numel() == B * S * 4:
+            frcnn_reg = frcnn_reg.reshape(B, S, 1, 4)
+        else:
+            raise ValueError("region_loss: frcnn_reg must hold C or 1 rows of 4 per sample")
+        if tuple(frcnn_target_cls.shape) != (B, S) or tuple(frcnn_target_reg.shape) != (B, S, 4):
+            raise ValueError("region_loss: Fast R-CNN targets must be [B,S] and [B,S,4]")
+    return _RegionLossFn.apply(rpn_cls, rpn_reg, frcnn_cls, frcnn_reg, rpn_target_cls, rpn_target_reg, frcnn_target_cls,
+                               frcnn_target_reg)
+
+
+# ------------------------------------------------------------------------------------------------
 # detection post-processing (D1, D2)
 # ------------------------------------------------------------------------------------------------
 def decode_classwise(cls_logits, reg, rois, num_classes: int, std=_STD4):

@@ -111,3 +111,26 @@ def pyramid_inputs(seed=8100, B=2, C=8, image_hw=(256, 320), K=80):
     rois5[0, 1:] = [10, 10, 10 + 112, 10 + 112]       # sqrt(area) = 112 = 224 / 2: exactly on a level boundary
     rois5[1, 1:] = [0, 0, 224, 224]
     return feats, rois5
+
+
+def loss_inputs(seed=8300, N=20646, S=128, C=21, n_pos=40, n_neg=216, frc_pos=32):
+    """Seeded predictions / targets with the shapes of losses/loss.py:24-59: RPN labels with n_pos ones, n_neg zeros and
+    -1 elsewhere; Fast R-CNN classes with frc_pos foreground rows first (like models/model.py:165); some regression
+    differences fall on either side of the SmoothL1 beta (1/9 and 1)."""
+    rs = np.random.RandomState(seed)
+    f32 = np.float32
+    rpn_cls = rs.standard_normal((N, 2)).astype(f32)
+    rpn_reg = (rs.standard_normal((N, 4)) * 0.3).astype(f32)
+    t = np.full((N,), -1, np.int64)
+    sel = rs.permutation(N)[:n_pos + n_neg]
+    t[sel[:n_pos]] = 1
+    t[sel[n_pos:]] = 0
+    rpn_treg = (rs.standard_normal((N, 4)) * 0.3).astype(f32)
+    frc_cls = rs.standard_normal((S, C)).astype(f32) * 2
+    frc_reg = rs.standard_normal((S, C, 4)).astype(f32)
+    c = np.zeros((S,), np.int64)
+    c[:frc_pos] = rs.randint(1, C, frc_pos)
+    frc_treg = rs.standard_normal((S, 4)).astype(f32)
+    frc_treg[0] = frc_reg[0, c[0]]            # a zero difference (gradient 0 at the kink of |x|)
+    return dict(rpn_cls=rpn_cls, rpn_reg=rpn_reg, rpn_tcls=t, rpn_treg=rpn_treg, frc_cls=frc_cls, frc_reg=frc_reg,
+                frc_tcls=c, frc_treg=frc_treg)

@@ -227,6 +227,21 @@ int frr_sample_targets(const int32_t* rpn_counts, const int32_t* frcnn_counts, i
                        int sel_stride, int32_t* jobs, uint32_t* draws, int draws_stride, frr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Loss side -- losses/loss.py:5-59 (SmoothL1Loss, RPNLoss, FastRCNNLoss) fused with the class-row gather of
+ *     models/model.py:340-341, per image: rpn_cls [B,N,2], rpn_reg [B,N,4], rpn_target_cls int64 [B,N] in {-1,0,1},
+ *     rpn_target_reg [B,N,4]; frcnn_cls [B,S,C], frcnn_reg [B,S,frcnn_reg_rows,4] (frcnn_reg_rows = C: the head output,
+ *     the row of the target class is picked here; 1: already gathered like the reference's loss input),
+ *     frcnn_target_cls int64 [B,S] (negative = padding of a short sample), frcnn_target_reg [B,S,4].
+ *     loss [B,5] = (total, rpn_cls, rpn_reg, frcnn_cls, frcnn_reg).  The grad_* tensors (same shapes as the predictions,
+ *     any may be NULL) receive d loss_component / d prediction for a unit upstream gradient.  Either half may be NULL.
+ * ------------------------------------------------------------------------------------- */
+int frr_region_loss(const float* rpn_cls, const float* rpn_reg, const int64_t* rpn_target_cls, const float* rpn_target_reg,
+                    int B, int N, const float* frcnn_cls, const float* frcnn_reg, const int64_t* frcnn_target_cls,
+                    const float* frcnn_target_reg, int S, int C, int frcnn_reg_rows, float rpn_beta, float frcnn_beta,
+                    float* loss, float* grad_rpn_cls, float* grad_rpn_reg, float* grad_frcnn_cls, float* grad_frcnn_reg,
+                    frr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * D1  predict tail -- models/model.py:369-378: prob = softmax(cls); boxes = clamp(cxcy_to_xy(
  *     decode(reg*std, xy_to_cxcy(roi))), 0, 1) per class.  cls [rows,C], reg [rows,C,4],
  *     rois [rows,4] -> prob [rows,C], boxes [rows,C,4].

@@ -432,6 +432,38 @@ def multiscale_roi_align(features, rois5, image_shapes, pooled=(7, 7), sampling_
     return out, lv
 
 
+def smooth_l1(pred, target, beta):
+    """losses/loss.py:5-14."""
+    x = np.abs(np.asarray(pred, f32) - np.asarray(target, f32))
+    return np.where(x >= f32(beta), x - f32(0.5) * f32(beta), f32(0.5) * x * x / f32(beta)).astype(f32)
+
+
+def _cross_entropy_rows(logits, target):
+    l = np.asarray(logits, np.float64)
+    m = l.max(axis=1, keepdims=True)
+    lse = (m + np.log(np.exp(l - m).sum(axis=1, keepdims=True)))[:, 0]
+    return lse - l[np.arange(len(l)), target]
+
+
+def region_loss(rpn_cls, rpn_reg, rpn_tcls, rpn_treg, frc_cls, frc_reg, frc_tcls, frc_treg):
+    """losses/loss.py:17-82 + the class-row gather of models/model.py:340-341 for one image ->
+    (total, rpn_cls, rpn_reg, frcnn_cls, frcnn_reg).  frc_reg [S,C,4] (head output) or [S,4] (already gathered);
+    negative Fast R-CNN classes mark padding rows of a short sample.  Sums are accumulated in float64 (the checker)."""
+    t = np.asarray(rpn_tcls)
+    valid, pos = t >= 0, t > 0
+    nv = float(valid.sum())
+    l_rc = _cross_entropy_rows(np.asarray(rpn_cls)[valid], t[valid]).sum() / nv if nv else float("nan")      # :32
+    l_rr = smooth_l1(np.asarray(rpn_reg)[pos], np.asarray(rpn_treg)[pos], 1 / 9).astype(np.float64).sum() / nv if nv else float("nan")
+    c = np.asarray(frc_tcls)
+    use, fpos = c >= 0, c > 0
+    nf = float(use.sum())
+    l_fc = _cross_entropy_rows(np.asarray(frc_cls)[use], c[use]).sum() / nf                                   # :55
+    reg = np.asarray(frc_reg)
+    rows = reg[np.arange(len(c)), np.maximum(c, 0)] if reg.ndim == 3 else reg                                # model.py:340-341
+    l_fr = smooth_l1(rows[fpos], np.asarray(frc_treg)[fpos], 1.0).astype(np.float64).sum() / nf              # :56-59
+    return np.asarray([l_rc + l_rr + l_fc + l_fr, l_rc, l_rr, l_fc, l_fr], np.float64)
+
+
 def scale_rois(rois: np.ndarray, fh: int, fw: int, batch_index: int = 0) -> np.ndarray:
     """models/model.py:104-110 + TV ops/_utils.py:18-25: roi*[fw,fh,fw,fh], prepend batch idx."""
     r = np.asarray(rois, dtype=f32) * np.array([fw, fh, fw, fh], dtype=f32)

@@ -285,3 +285,15 @@ def test_multiscale_roi_align_vs_torchvision(oracle, tag, shapes):
     out, lv = oracle.multiscale_roi_align(feats, rois5, shapes)
     assert np.array_equal(lv, g[f"{tag}_levels"].astype(np.int64))          # incl. the boxes exactly on a level boundary
     assert np.array_equal(out, g[f"{tag}_out"])
+
+
+@pytest.mark.parametrize("name,kw", [("voc", dict(seed=8300, N=20646, S=128, C=21)),
+                                     ("coco", dict(seed=8301, N=37350, S=128, C=81, n_pos=128, n_neg=128)),
+                                     ("small", dict(seed=8302, N=1440, S=128, C=21, n_pos=3, n_neg=253, frc_pos=5))])
+def test_region_loss_vs_reference(oracle, name, kw):
+    """losses/loss.py FRCNNLoss (+ models/model.py:340-341 gather) run by tests/golden/make_golden_loss.py."""
+    g = golden("loss")
+    x = synth.loss_inputs(**kw)
+    got = oracle.region_loss(x["rpn_cls"], x["rpn_reg"], x["rpn_tcls"], x["rpn_treg"], x["frc_cls"], x["frc_reg"],
+                             x["frc_tcls"], x["frc_treg"])
+    np.testing.assert_allclose(got, g[f"{name}_loss"], rtol=2e-6)
