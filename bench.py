@@ -32,6 +32,15 @@ WORKLOAD = ("configs[1]: RPN proposal layer, 9 anchors x 38x63 map (608x1008), 1
             "@ IoU 0.7, batch 64 images/GPU")
 
 
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json), or None."""
+    try:
+        t = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))[kernel]
+        return t["dram_bytes_read"] + t["dram_bytes_write"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -309,7 +318,7 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        sample = max(threads, 8) * 2
+        sample = max(threads, 8) * 4        # ~20 CPU-seconds of work
         v, dt = cpu_images_per_s(sample, threads)
         cpu = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
                "sample": f"{sample} images of the same workload (seeds 2000..), oracle port: numpy decode/sort + C NMS, "
@@ -340,7 +349,11 @@ def run_ours(args):
             # (see DESIGN.md); its HBM traffic is ~0.2 MB/image.  The HBM roofline entry is the decode kernel.
             "roofline": {"kernel": "rpn_decode_kernel", "bound": "hbm", "achieved": dec_bytes / (ms_dec * 1e-3) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": dec_bytes / (ms_dec * 1e-3) / 1e9 / peak,
-                         "traffic": None, "peak_source": how, "bytes_per_launch": dec_bytes},
+                         "traffic": ncu_traffic("rpn_decode_kernel"), "peak_source": how, "bytes_per_launch": dec_bytes,
+                         "traffic_note": "ncu dram read+write of one launch; below the algorithmic bytes because the "
+                                         "28 MB of outputs stay in the 126 MB L2 for the top-k / NMS kernels"},
+            "dominant_kernel": {"kernel": "nms_keeplist_kernel", "share_of_step": ms_nms / (ms / args.steps),
+                                "bound": "ALU-pipe issue (pair screening), not HBM or tensor: see profiles/ and DESIGN.md"},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))
@@ -453,7 +466,7 @@ def run_extra(args):
                 "sampling": args.sampling,
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"kernel": "roi_fwd_fast_kernel", "bound": "hbm", "achieved": fb / (ms_f * 1e-3) / 1e9, "peak": peak,
-                             "unit": "GB/s", "frac": fb / (ms_f * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": how,
+                             "unit": "GB/s", "frac": fb / (ms_f * 1e-3) / 1e9 / peak, "traffic": ncu_traffic("roi_pool_fwd_flat_kernel"), "peak_source": how,
                              "bytes_per_launch": fb},
                 "roofline_bwd": {"kernel": "roi_pool_bwd_fast_kernel", "bound": "hbm", "achieved": fb / (ms_b * 1e-3) / 1e9,
                                  "peak": peak, "unit": "GB/s", "frac": fb / (ms_b * 1e-3) / 1e9 / peak, "bytes_per_launch": fb},
