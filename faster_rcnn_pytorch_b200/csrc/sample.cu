@@ -5,7 +5,7 @@
 //
 //   sample_stream_kernel (one CTA): reads the candidate counts of the assign kernels, lays out the draws exactly in the
 //     reference's order (per image: RPN positives, RPN negatives, Fast R-CNN positives, Fast R-CNN negatives), then
-//     walks the mt19937 stream block by block (624-word twists, three dependent phases, double buffered) and keeps only
+//     walks the mt19937 stream block by block (624-word twists, one barrier each, double buffered) and keeps only
 //     the tempered words the samplers will look at -- torch's randperm(n) is a forward Fisher-Yates shuffle
 //     (r[i] <-> r[i + random() % (n - i)], i = 0 .. n-2), so the first `take` entries of the permutation need only the
 //     first `take` draws although the call consumes n - 1 of them.  The advanced state is written back.
@@ -20,10 +20,12 @@ namespace frr {
 
 constexpr int kMtN = 624;
 constexpr int kMtM = 397;
-constexpr int kStreamThreads = 256;
-constexpr int kApplyThreads = 256;
+constexpr int kD = kMtN - kMtM;  // 227: distance below which the twist has no dependency on its own output
+constexpr int kStreamThreads = 640;  // one state word per thread in the twist
+constexpr int kApplyThreads = 512;
 constexpr int kMaxTake = 512;    // entries of a permutation that are ever looked at (256 RPN, 128 / 512 Fast R-CNN)
 constexpr int kHashSize = 2048;  // >= 4 x kMaxTake
+constexpr int kJobsSmem = 1024;  // the stream kernel walks its job table in shared memory: <= 256 images per launch
 
 __device__ __forceinline__ uint32_t mt_mix(uint32_t cur, uint32_t nxt, uint32_t far) {
     const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
@@ -48,6 +50,7 @@ __global__ void __launch_bounds__(kStreamThreads)
                          uint32_t* __restrict__ draws, int S) {
     __shared__ uint32_t mt_buf[2][kMtN];
     __shared__ unsigned int warp_tmp[32];
+    __shared__ int4 sjobs[kJobsSmem];  // the job table is walked once per twist: keep it out of the global-load latency
     const int tid = threadIdx.x;
 
     // ---- job table (one image per thread, images in order) --------------------------------------
@@ -78,7 +81,9 @@ __global__ void __launch_bounds__(kStreamThreads)
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int take = min(max(want[q], 0), n[q]);
-                jobs[4 * b + q] = make_int4(n[q], min(take, max(n[q] - 1, 0)), take, (int)off);
+                const int4 jb = make_int4(n[q], min(take, max(n[q] - 1, 0)), take, (int)off);
+                jobs[4 * b + q] = jb;
+                sjobs[4 * b + q] = jb;
                 off += (unsigned int)max(n[q] - 1, 0);
             }
         }
@@ -93,22 +98,40 @@ __global__ void __launch_bounds__(kStreamThreads)
     __syncthreads();
     int cur = 0;
     unsigned int consumed = 0;
-    int jc = 0;
+    // Every thread walks the (uniform) job table, so the walk must cost nothing in the common case of a 624-word block
+    // nobody reads: j = next job with draws still to emit, [lo_j, hi_j) = its stream range (lo_j = "never" when done).
+    int j = 0;
+    unsigned int lo_j = 0xffffffffu, hi_j = 0;
+    auto next_job = [&]() {
+        while (j < J && sjobs[j].y == 0) ++j;
+        if (j < J) { lo_j = (unsigned int)sjobs[j].w; hi_j = lo_j + (unsigned int)sjobs[j].y; }
+        else lo_j = 0xffffffffu;
+    };
+    next_job();
     while (consumed < T) {
         if (pos >= kMtN) {
+            // One barrier per twist: the sequential algorithm updates word i from the OLD words i, i + 1 and the word
+            // 397 ahead (already NEW for i >= 227).  Substituting the new words by their own definitions expresses every
+            // new word through old words only (the recurrence is XOR-linear in the far operand):
+            //   i < 227        : o[i+397]                                                     ^ f(i)
+            //   227 <= i < 454 : o[i+170] ^ f(i-227)                                          ^ f(i)
+            //   454 <= i < 623 : o[i-57]  ^ f(i-454) ^ f(i-227)                               ^ f(i)
+            //   i = 623        : new[396] ^ g(o[623], new[0])   (both expanded the same way)
+            // with f(j) = g(o[j], o[j+1]); the state is double buffered, so all 624 words are computed in one phase.
             const uint32_t* o = mt_buf[cur];
             uint32_t* w = mt_buf[cur ^ 1];
-            if (tid < kMtN - kMtM) w[tid] = mt_mix(o[tid], o[tid + 1], o[tid + kMtM]);
-            __syncthreads();
-            if (tid < kMtN - kMtM) {
-                const int i = tid + (kMtN - kMtM);  // 227 .. 453
-                w[i] = mt_mix(o[i], o[i + 1], w[i - (kMtN - kMtM)]);
-            }
-            __syncthreads();
-            {
-                const int i = tid + 2 * (kMtN - kMtM);  // 454 .. 623
-                if (i < kMtN - 1) w[i] = mt_mix(o[i], o[i + 1], w[i - (kMtN - kMtM)]);
-                else if (i == kMtN - 1) w[i] = mt_mix(o[i], w[0], w[kMtM - 1]);
+            auto f = [&](int q) { return mt_mix(o[q], o[q + 1], 0u); };
+            for (int i = tid; i < kMtN; i += kStreamThreads) {
+                uint32_t v;
+                if (i < kD) v = o[i + kMtM] ^ f(i);
+                else if (i < 2 * kD) v = o[i + kMtM - kD] ^ f(i - kD) ^ f(i);
+                else if (i < kMtN - 1) v = o[i + kMtM - 2 * kD] ^ f(i - 2 * kD) ^ f(i - kD) ^ f(i);
+                else {
+                    const uint32_t n0 = o[kMtM] ^ f(0);                                              // new[0]
+                    const uint32_t n396 = o[kMtM - 1 + kMtM - kD] ^ f(kMtM - 1 - kD) ^ f(kMtM - 1);  // new[396]
+                    v = mt_mix(o[kMtN - 1], n0, n396);
+                }
+                w[i] = v;
             }
             __syncthreads();
             cur ^= 1;
@@ -116,22 +139,19 @@ __global__ void __launch_bounds__(kStreamThreads)
         }
         const uint32_t* mt = mt_buf[cur];
         const unsigned int blk_end = min(consumed + (unsigned int)(kMtN - pos), T);
-        int j = jc;
-        while (j < J) {
-            const int4 jb = jobs[j];
-            const unsigned int lo_j = (unsigned int)jb.w, hi_j = lo_j + (unsigned int)jb.y;
-            if (jb.y == 0 || hi_j <= consumed) { ++j; continue; }
-            if (lo_j >= blk_end) break;
+        while (lo_j < blk_end) {  // (hi_j > consumed always holds for the current job)
             const unsigned int lo = max(lo_j, consumed), hi = min(hi_j, blk_end);
             for (unsigned int s = lo + tid; s < hi; s += kStreamThreads)
                 draws[(size_t)j * S + (s - lo_j)] = mt_temper(mt[pos + (int)(s - consumed)]);
-            if (hi_j <= blk_end) ++j; else break;
+            if (hi_j > blk_end) break;
+            ++j;
+            next_job();
         }
-        jc = j;
         pos += (int)(blk_end - consumed);
         consumed = blk_end;
-        __syncthreads();  // every read of mt[] is done before the next twist overwrites the other buffer's source
+        // no barrier here: the next twist writes the OTHER buffer, whose last readers finished before the barrier above
     }
+    __syncthreads();
     for (int i = tid; i < kMtN; i += kStreamThreads) state[i] = mt_buf[cur][i];
     if (tid == 0) state[kMtN] = (uint32_t)pos;
 }
@@ -140,6 +160,7 @@ struct ApplySmem {
     int hkey[kHashSize];
     int hval[kHashSize];
     int perm[kMaxTake];
+    uint32_t draw[kMaxTake];
 };
 
 __device__ __forceinline__ int hash_slot(const int* hkey, int key) {
@@ -163,11 +184,15 @@ __global__ void __launch_bounds__(kApplyThreads)
     if (kind < 2 && (n == 0 || rpn_label8 == nullptr)) return;  // the reference does not sample here
     if (kind >= 2 && sel == nullptr) return;
     for (int i = tid; i < kHashSize; i += kApplyThreads) sm.hkey[i] = -1;
+    // swap partner of step i, i + random() % (n - i): the division is done by all threads, off the serial chain
+    for (int i = tid; i < need; i += kApplyThreads) sm.draw[i] = (uint32_t)i + draws[(size_t)j * S + i] % (uint32_t)(n - i);
     __syncthreads();
+    const int32_t* list = kind < 2 ? (kind == 0 ? rpn_pos_list : rpn_neg_list) + (size_t)b * N : nullptr;
+    int8_t* lb = kind < 2 ? rpn_label8 + (size_t)b * N : nullptr;
     if (tid == 0) {
-        const uint32_t* d = draws + (size_t)j * S;
+        // the serial part: `need` Fisher-Yates steps (shared-memory hash map of the displaced entries)
         for (int i = 0; i < need; ++i) {
-            const int jj = i + (int)(d[i] % (uint32_t)(n - i));
+            const int jj = (int)sm.draw[i];
             const int si = hash_slot(sm.hkey, i);
             const int vi = (sm.hkey[si] == i) ? sm.hval[si] : i;
             const int sj = hash_slot(sm.hkey, jj);
@@ -179,14 +204,13 @@ __global__ void __launch_bounds__(kApplyThreads)
             const int si = hash_slot(sm.hkey, i);
             sm.perm[i] = (sm.hkey[si] == i) ? sm.hval[si] : i;
         }
+    } else if (kind < 2 && tid >= 32) {
+        // meanwhile the other warps mark the whole candidate list as ignore (models/model.py:228-236: everything after
+        // the first `take` entries of the permutation becomes -1; the kept ones are restored below)
+        for (int p = tid - 32; p < n; p += kApplyThreads - 32) lb[list[p]] = -1;
     }
     __syncthreads();
     if (kind < 2) {
-        // models/model.py:228-236: everything after the first `take` entries of the permutation becomes ignore (-1)
-        const int32_t* list = (kind == 0 ? rpn_pos_list : rpn_neg_list) + (size_t)b * N;
-        int8_t* lb = rpn_label8 + (size_t)b * N;
-        for (int p = tid; p < n; p += kApplyThreads) lb[list[p]] = -1;
-        __syncthreads();
         const int8_t v = kind == 0 ? 1 : 0;
         for (int i = tid; i < take; i += kApplyThreads) lb[list[sm.perm[i]]] = v;
     } else {
@@ -217,13 +241,23 @@ extern "C" int frr_sample_targets(const int32_t* rpn_counts, const int32_t* frcn
     FRR_CHECK_ARG(aligned16(jobs), "frr_sample_targets: jobs must be 16-byte aligned");
     if (B == 0) return FRR_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    sample_stream_kernel<<<1, kStreamThreads, 0, st>>>(rpn_counts, frcnn_counts, B, rpn_batch, rpn_max_pos, frcnn_batch,
-                                                       frcnn_max_pos, mt_state, (int4*)jobs, draws, draws_stride);
-    count_launch();
-    FRR_CHECK_LAUNCH("sample_stream_kernel");
-    sample_apply_kernel<<<4 * B, kApplyThreads, 0, st>>>((const int4*)jobs, draws, draws_stride, N, rpn_label8, rpn_pos_list,
-                                                         rpn_neg_list, sel, sel_n, sel_stride);
-    count_launch();
-    FRR_CHECK_LAUNCH("sample_apply_kernel");
+    // larger batches go through in slices of 256 images: the launches are stream-ordered, so the generator advances
+    // through the images in order exactly as one launch would
+    for (int b0 = 0; b0 < B; b0 += kJobsSmem / 4) {
+        const int nb = (B - b0 < kJobsSmem / 4) ? B - b0 : kJobsSmem / 4;
+        int4* jb = (int4*)jobs + 4 * (size_t)b0;
+        uint32_t* dr = draws + 4 * (size_t)b0 * draws_stride;
+        sample_stream_kernel<<<1, kStreamThreads, 0, st>>>(rpn_counts ? rpn_counts + 2 * (size_t)b0 : nullptr,
+                                                           frcnn_counts ? frcnn_counts + 2 * (size_t)b0 : nullptr, nb, rpn_batch,
+                                                           rpn_max_pos, frcnn_batch, frcnn_max_pos, mt_state, jb, dr, draws_stride);
+        count_launch();
+        FRR_CHECK_LAUNCH("sample_stream_kernel");
+        sample_apply_kernel<<<4 * nb, kApplyThreads, 0, st>>>(
+            jb, dr, draws_stride, N, rpn_label8 ? rpn_label8 + (size_t)b0 * N : nullptr,
+            rpn_pos_list ? rpn_pos_list + (size_t)b0 * N : nullptr, rpn_neg_list ? rpn_neg_list + (size_t)b0 * N : nullptr,
+            sel ? sel + (size_t)b0 * sel_stride : nullptr, sel_n ? sel_n + 2 * (size_t)b0 : nullptr, sel_stride);
+        count_launch();
+        FRR_CHECK_LAUNCH("sample_apply_kernel");
+    }
     return FRR_OK;
 }
