@@ -282,3 +282,23 @@ def test_device_generator_round_trip_without_draws():
     torch.set_rng_state(before)
     targets.DeviceGenerator(DEV).sync_to_torch()              # freshly seeded: left = 1 <-> position 624
     assert torch.equal(torch.randperm(50), want)
+
+
+def test_device_sampling_more_than_256_images():
+    """frr_sample_targets walks its job table in shared memory 256 images at a time: a batch of 300 goes through two
+    stream-ordered slices and must still equal the host stream image by image."""
+    hw, B, G, R = (160, 256), 300, 3, 200
+    gts = np.stack([synth.gt_boxes(9500 + i, G)[0] for i in range(B)])
+    labs = np.stack([synth.gt_boxes(9500 + i, G)[1] for i in range(B)])
+    rois = np.stack([synth.random_boxes(9900 + (i % 7), R)[0] for i in range(B)])
+    args = (dev(gts), None, dev(labs), dev(rois), None)
+    torch.manual_seed(4242)
+    host = targets.make_targets(*args, image_hw=hw)
+    host_state = torch.get_rng_state().clone()
+    torch.manual_seed(4242)
+    gen = targets.DeviceGenerator(DEV)
+    devo = targets.make_targets(*args, image_hw=hw, generator=gen)
+    gen.sync_to_torch()
+    assert torch.equal(torch.get_rng_state(), host_state)
+    for k in ("rpn_cls", "frcnn_cls", "keep_index", "sample_rois"):
+        assert torch.equal(host[k], devo[k]), k
