@@ -409,6 +409,52 @@ def run_extra(args):
 
     rs = np.random.RandomState(9000 + rank)
     C = 512
+    if args.workload == "joint":
+        # configs[4]: approximate joint training step, 4 images/GPU at 600x1000, VGG16 backbone + FC head on torch /
+        # cuDNN / cuBLAS under DDP (NCCL all-reduce of the 548 MB of fp32 gradients), region stage = libfrr
+        sys.path.insert(0, os.path.join(REPO, "tools"))
+        import frcnn_harness as fh_
+        hw, B, G = (600, 1000), 4, 8
+        torch.manual_seed(1234)
+        model = fh_.FRCNNTrain(21).to(dev).to(memory_format=torch.channels_last)
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
+        opt = torch.optim.SGD(net.parameters(), lr=1e-3, momentum=0.9)
+        torch.manual_seed(4000 + rank)
+        gen = targets.DeviceGenerator(dev)
+        batches = [fh_.make_batch(B, hw, G, dev, seed=10 * rank + i) for i in range(3)]
+
+        def step(i):
+            x, gt, lab = batches[i % 3]
+            opt.zero_grad(set_to_none=True)
+            loss = net(x, gt, lab, gen)
+            loss[:, 0].mean().backward()
+            opt.step()
+            return loss
+
+        for i in range(max(args.warmup, 3)):
+            step(i)
+        l0 = _lib.launch_count()
+        ms = maxms(_events_ms(torch, step, args.steps, sync_all))
+        launches = _lib.launch_count() - l0
+        model.timer.enabled = True
+        for i in range(4):
+            step(i)
+        region_ms = model.timer.total_ms() / 4          # forward-side region calls (their backward runs inside autograd)
+        model.timer.enabled = False
+        last = step(0).detach().cpu().numpy()
+        if rank == 0:
+            print(json.dumps({
+                "metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "configs[4]: approximate joint training step (fwd + bwd + SGD), VGG16 Faster R-CNN, 4 images/GPU "
+                                       "at 600x1000, G=8; backbone/heads torch+cuDNN under DDP (NCCL), region stage libfrr",
+                           "parallelism": f"dp{world}"},
+                "region_stage_forward_ms_per_step": region_ms, "region_stage_share": region_ms / (ms / args.steps),
+                "loss_last_step": [float(v) for v in last.mean(axis=0)], "gpu_launches": int(launches)}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.workload == "train":
         hw, B, G, per = (600, 1000), 16, 8, 128
         fh, fw = hw[0] // 16, hw[1] // 16
@@ -529,8 +575,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--sampling", default="device", choices=["device", "host"],
                     help="--workload train: where the reference's torch.randperm draws are replayed")
-    ap.add_argument("--workload", default="rpn", choices=["rpn", "train", "infer"],
-                    help="rpn = BASELINE configs[1] (the driver's line); train = configs[2]; infer = configs[3]")
+    ap.add_argument("--workload", default="rpn", choices=["rpn", "train", "infer", "joint"],
+                    help="rpn = BASELINE configs[1] (the driver's line); train = configs[2]; infer = configs[3]; joint = configs[4]")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
