@@ -39,11 +39,11 @@ constexpr int kGroup = kChunk / kTile;  // threads that together cover one chunk
 struct NmsThr {
     float up;  // smallest fp32 with (double)up > thr
     float c2;  // up/(1+up) * (1 - 2^-19): screening constant
-    float fy;  // a box of height h can only be suppressed by boxes whose y-centre is within fy * h of its own
+    float alo, ahi;  // a box of area A can only be suppressed by boxes with area in [alo * A, ahi * A] (IoU <= min/max area)
     int fast;  // screening usable (1e-6 <= thr, finite)
 };
 
-constexpr int kStrips = 64;         // y-strips of the sorted kept slice; strip kStrips = boxes that must always be tested
+constexpr int kStrips = 88;         // area classes of the sorted kept slice (4 per octave, 2^-22 .. 1); class kStrips = boxes that must always be tested
 constexpr int kGroupCands = 4;      // candidates per warp pass in the sorted phase 1
 
 __device__ __forceinline__ float box_area(const float4& b) {
@@ -94,21 +94,26 @@ struct NmsSmem {
     float4 sbox[kChunk];  // survivor boxes (compacted)
     float sarea[kChunk];
     short ssrc[kChunk];  // survivor -> position inside the chunk
-    // sorted phase 1 (kUnit): kept slice bucketed by y-strip, chunk candidates ordered by y-strip
+    // sorted phase 1 (kUnit): kept slice bucketed by area class, chunk candidates ordered by area class
     unsigned int shist[kStrips + 2];
     unsigned int scursor[kStrips + 2];
     unsigned int chist[kStrips + 2];
     unsigned int ccursor[kStrips + 2];
     unsigned short sstart[kStrips + 2];  // sstart[s] = first sorted position of strip s; [kStrips+1] = total
-    unsigned char cord[kChunk];          // chunk positions ordered by y-strip
+    unsigned short cord[kChunk];         // chunk positions ordered by area class
 };
 
-// y-strip of a box: monotone in the y-centre; boxes without a usable screening area (degenerate / malformed, NaN sa)
-// go to the extra strip kStrips and are tested against everything
-__device__ __forceinline__ int strip_of_y(float y) { return min(kStrips - 1, max(0, (int)(y * (float)kStrips))); }
-// (strips run along x: detection images are usually landscape, so boxes are narrower relative to the x-extent)
+// Area class of a box: the top bits of the fp32 area (exponent + 2 mantissa bits = 4 classes per octave), an exactly
+// monotone integer function of the area.  IoU <= min(area) / max(area) (in fp32 as well: w <= both widths and RN is
+// monotone, so inter <= both areas), hence only kept boxes whose area lies within [thr, 1/thr] of the candidate's can
+// suppress it: for RPN proposals (three anchor scales, a factor 4 apart in area) that is a far sharper cut than any
+// position strip, because the large boxes overlap every strip.  Boxes without a usable screening area (degenerate /
+// malformed, NaN sa) go to the extra class kStrips and are tested against everything.
+__device__ __forceinline__ int strip_of_area(float a) {
+    return min(kStrips - 1, max(0, (__float_as_int(a) >> 21) - ((127 - 22) << 2)));
+}
 __device__ __forceinline__ int strip_of(const float4& b, float sa) {
-    return (sa != sa) ? kStrips : strip_of_y(0.5f * (b.x + b.z));
+    return (sa != sa) ? kStrips : strip_of_area(box_area(b));
 }
 
 // barrier over the first `n` threads of the CTA with an OR reduction of `pred`
@@ -190,12 +195,12 @@ __global__ void __launch_bounds__(kThreads)
 
         const int ns = (nk - rank + S - 1) / S;  // kept ordinals o with o % S == rank
         if (kSorted) {
-            // ---- phase 1 (sorted): the slice is bucketed by x-strip, the chunk's candidates are ordered by x-strip;
-            //      a warp takes 4 x-adjacent candidates (warp-uniform registers) and its LANES walk only the kept
-            //      boxes whose strip can reach them: |cx_K - cx_c| <= fy * w_c is necessary for IoU >= thr (the
-            //      bound is the same in x and y), so everything outside that x-range is skipped exactly.
+            // ---- phase 1 (sorted): the slice is bucketed by area class, the chunk's candidates are ordered by area class;
+            //      a warp takes 4 class-adjacent candidates (warp-uniform registers) and its LANES walk only the kept
+            //      boxes whose area can reach them: min(area) / max(area) >= thr is necessary for IoU >= thr, so
+            //      everything outside that range of classes is skipped exactly.
             // (a) re-bucket the slice when boxes were appended by the previous chunk (counting sort into the other
-            //     buffer) and (b) order the chunk's candidates by y-strip (counting sort of <= 256 positions; positions
+            //     buffer) and (b) order the chunk's candidates by class (counting sort of <= 256 positions; positions
             //     past the end of the list are marked suppressed right away) -- the two sorts share their barriers
             const bool resort = ns > ns_sorted;
             if (tid < kStrips + 2) { sm->shist[tid] = 0u; sm->chist[tid] = 0u; }
@@ -249,10 +254,10 @@ __global__ void __launch_bounds__(kThreads)
                 float* ta = karea; karea = karea_alt; karea_alt = ta;
                 ns_sorted = ns;
             }
-            if (tid < kChunk) sm->cord[atomicAdd(&sm->ccursor[cst], 1u)] = (unsigned char)tid;
+            if (tid < kChunk) sm->cord[atomicAdd(&sm->ccursor[cst], 1u)] = (unsigned short)tid;
             __syncthreads();
             FRR_TICK(10);  // bucketing time (reported separately, not part of the phase-1 slot)
-            // (c) groups of 4 y-adjacent candidates
+            // (c) groups of 4 class-adjacent candidates: warp-uniform registers, the LANES walk the admissible kept boxes
             const int sp_lo = sm->sstart[kStrips], sp_hi = sm->sstart[kStrips + 1];  // always-tested boxes
             for (int g = warp; g < kChunk / kGroupCands; g += kWarps) {
                 float4 cb[kGroupCands];
@@ -260,7 +265,7 @@ __global__ void __launch_bounds__(kThreads)
                 int cpos[kGroupCands];
                 bool has[kGroupCands];
                 bool all_range = false;
-                float ylo = 3.0e38f, yhi = -3.0e38f;
+                float alo = 3.0e38f, ahi = -3.0e38f;
                 bool any = false;
 #pragma unroll
                 for (int j = 0; j < kGroupCands; ++j) {
@@ -273,20 +278,19 @@ __global__ void __launch_bounds__(kThreads)
                         if (ca[j] != ca[j]) {
                             all_range = true;  // no usable screening area: test against the whole slice
                         } else {
-                            const float cy = 0.5f * (cb[j].x + cb[j].z);
-                            const float r = thr.fy * (cb[j].z - cb[j].x) * 1.0001f + 2.0e-6f;
-                            ylo = fminf(ylo, cy - r);
-                            yhi = fmaxf(yhi, cy + r);
+                            const float a = box_area(cb[j]);
+                            alo = fminf(alo, a * thr.alo);
+                            ahi = fmaxf(ahi, a * thr.ahi);
                         }
                     }
                 }
                 if (!any) continue;  // warp-uniform
                 int lo = 0, hi = ns;
                 if (!all_range) {
-                    lo = sm->sstart[strip_of_y(ylo)];
-                    hi = sm->sstart[strip_of_y(yhi) + 1];
+                    lo = sm->sstart[strip_of_area(alo)];
+                    hi = sm->sstart[strip_of_area(ahi) + 1];
                 }
-                // two segments: the y-range and (unless already covered) the always-tested strip
+                // two segments: the admissible area classes and (unless already covered) the always-tested class
                 int pk[kGroupCands];
 #pragma unroll
                 for (int j = 0; j < kGroupCands; ++j) pk[j] = -1;
@@ -306,20 +310,35 @@ __global__ void __launch_bounds__(kThreads)
                         }
                     }
                 }
+                // Verdicts.  The exact test of one screen hit per candidate is enough almost always (the screen is tight to
+                // 2^-19), and the four candidates' tests run side by side in lanes 0..3: ONE call of the division path per
+                // group instead of one per candidate (the sequential form cost twice as many issue slots as the scan).
+                int kj = -1;  // lane j < 4: a kept box that passed the screen against candidate j
+                unsigned int hit_any = 0u;
 #pragma unroll
                 for (int j = 0; j < kGroupCands; ++j) {
-                    if (!has[j]) continue;  // warp-uniform
-                    bool r = false;
-                    if (pk[j] >= 0) r = suppress_exact(kbox[pk[j]], cb[j], thr.up);
-                    bool sup = __any_sync(0xffffffffu, r);
-                    if (!sup && __any_sync(0xffffffffu, pk[j] >= 0)) {
-                        // a screen hit was not confirmed by the exact test (rare): exact walk of both segments
-                        for (int k = lo + lane; k < hi; k += 32) r = r || suppress_exact(kbox[k], cb[j], thr.up);
-                        if (!all_range)
-                            for (int k = sp_lo + lane; k < sp_hi; k += 32) r = r || suppress_exact(kbox[k], cb[j], thr.up);
-                        sup = __any_sync(0xffffffffu, r);
-                    }
-                    if (sup && lane == 0) atomicOr(&sm->acc[par][cpos[j] >> 5], 1u << (cpos[j] & 31));
+                    const unsigned int m = __ballot_sync(0xffffffffu, has[j] && pk[j] >= 0);
+                    const int v = __shfl_sync(0xffffffffu, pk[j], m ? __ffs(m) - 1 : 0);
+                    if (lane == j && m) kj = v;
+                    hit_any |= m ? (1u << j) : 0u;
+                }
+                bool r = false;
+                if (kj >= 0) r = suppress_exact(kbox[kj], sm->cbox[sm->cord[g * kGroupCands + lane]], thr.up);
+                unsigned int confirmed = __ballot_sync(0xffffffffu, r);
+                unsigned int redo = hit_any & ~confirmed;
+                while (redo) {  // a screen hit was not confirmed by the exact test (rare): exact walk of both segments
+                    const int j = __ffs(redo) - 1;
+                    redo &= redo - 1;
+                    const float4 cbj = sm->cbox[sm->cord[g * kGroupCands + j]];
+                    bool rr = false;
+                    for (int k = lo + lane; k < hi; k += 32) rr = rr || suppress_exact(kbox[k], cbj, thr.up);
+                    if (!all_range)
+                        for (int k = sp_lo + lane; k < sp_hi; k += 32) rr = rr || suppress_exact(kbox[k], cbj, thr.up);
+                    if (__any_sync(0xffffffffu, rr)) confirmed |= 1u << j;
+                }
+                if (lane < kGroupCands && ((confirmed >> lane) & 1u)) {
+                    const int cp = sm->cord[g * kGroupCands + lane];
+                    atomicOr(&sm->acc[par][cp >> 5], 1u << (cp & 31));
                 }
             }
         } else {
@@ -367,11 +386,12 @@ __global__ void __launch_bounds__(kThreads)
                 for (int j = 0; j < kTile; ++j)
                     for (int k = part; k < ns && !sup[j]; k += kParts) sup[j] = suppress_exact(kbox[k], cb[j], thr.up);
             }
-            // warp covers candidates u in [32*(warp&1), +32) + 64 j  ->  word (warp&1) + 2 j
+            // warp covers candidates u in [32 * (warp % kGW), +32) + kGroup j  ->  word (warp % kGW) + kGW j
+            constexpr int kGW = kGroup / 32;
 #pragma unroll
             for (int j = 0; j < kTile; ++j) {
                 const unsigned int wj = __ballot_sync(0xffffffffu, sup[j]);
-                if (lane == 0 && wj != 0u) atomicOr(&sm->acc[par][(warp & 1) + 2 * j], wj);
+                if (lane == 0 && wj != 0u) atomicOr(&sm->acc[par][(warp % kGW) + kGW * j], wj);
             }
         }
         }
@@ -560,10 +580,11 @@ static NmsThr make_thr(double thr) {
     t.fast = (thr >= 1.0e-6) && isfinite(thr) && (t.up < 1.0e30f) ? 1 : 0;
     const double u = (double)t.up;
     t.c2 = t.fast ? (float)(u / (1.0 + u) * (1.0 - 1.9073486328125e-06)) : 0.f;
-    // IoU >= thr needs |cy_a - cy_b| <= max(1 - thr, (1 - thr) / (2 thr)) * h of EITHER box; thr is
-    // lowered by 2^-18 relative to cover the fp32 rounding of the exact IoU
-    const double tl = thr * (1.0 - 3.814697265625e-06);
-    t.fy = t.fast ? (float)(fmax(1.0 - tl, (1.0 - tl) / (2.0 * tl)) * (1.0 + 1.0e-6)) : 0.f;
+    // IoU >= thr needs min(area) / max(area) >= thr; thr is lowered by 2^-17 relative to cover the fp32 roundings of the
+    // exact IoU (<= 2^-20, see strip_of_area) and of the two products below
+    const double tl = thr * (1.0 - 7.62939453125e-06);
+    t.alo = t.fast ? (float)(tl * (1.0 - 1.0e-6)) : 0.f;
+    t.ahi = t.fast ? (float)(1.0 / tl * (1.0 + 1.0e-6)) : 0.f;
     return t;
 }
 
@@ -591,9 +612,10 @@ int nms_launch(const float* boxes, const int32_t* counts, int B, int n, double i
     }
     FRR_CHECK_ARG(S == 1 || S == 2 || S == 4 || S == 8 || S == 16, "frr_nms_sorted: cluster_size %d not in {1,2,4,8,16}", S);
     if (threads == 0) threads = 1024;
+    if (threads < kChunk) threads = kChunk;  // the first kChunk threads own one candidate each
     // grow the cluster until a slice of the kept list fits in shared memory
     const NmsThr thr = make_thr(iou_thr);
-    // The y-strip sorted phase 1 pays ~10 k cycles of bucketing per chunk: it wins once a CTA's slice of the kept
+    // The class-sorted phase 1 pays ~10 k cycles of bucketing per chunk: it wins once a CTA's slice of the kept
     // list is large (batched launches with 1-2 CTAs per image), not for a single image spread over 16 CTAs.
     const bool sorted = thr.fast && unit_boxes && (kcap / S >= 384);
     const size_t limit = 227 * 1024;
@@ -606,7 +628,7 @@ int nms_launch(const float* boxes, const int32_t* counts, int B, int n, double i
                             const int32_t*, int);
     kern_t kern = nullptr;
 #define FRR_NMS_PICK(F, U, SO)                                                                      \
-    (threads == 256 ? nms_keeplist_kernel<256, F, U, SO>                                               \
+    (threads < kChunk * 2 ? nms_keeplist_kernel<kChunk, F, U, SO>                                            \
                     : threads == 512 ? nms_keeplist_kernel<512, F, U, SO> : nms_keeplist_kernel<1024, F, U, SO>)
     if (sorted) kern = FRR_NMS_PICK(true, true, true);
     else if (thr.fast && unit_boxes) kern = FRR_NMS_PICK(true, true, false);

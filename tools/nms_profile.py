@@ -38,9 +38,8 @@ def run(bx, cnt, S, threads, reps=20, dbg=False):
     print(json.dumps(out), flush=True)
 
 
-for threads in (512, 1024):
-    for S in (1, 2):
-        run(tb, tc, S, threads, dbg=True)
+for threads, S in ((1024, 2), (512, 2), (512, 4), (512, 8), (1024, 4)):
+    run(tb, tc, S, threads, dbg=True)
 one, onec = tb[:1].contiguous(), tc[:1].contiguous()
 for threads in (512, 1024):
     for S in (4, 8, 16):
