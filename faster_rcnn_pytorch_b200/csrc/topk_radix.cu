@@ -36,7 +36,7 @@ struct RsLayout {
     int db;  // digit bits of the sort passes (5 when the 2^db x 1024 u16 counters fit, else 4)
 };
 
-static inline size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
+__host__ __device__ static inline size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 static RsLayout rs_layout(int N, int kcap, int nchunks, bool want_stage, int db) {
     RsLayout L;
@@ -77,8 +77,11 @@ __global__ void __launch_bounds__(kRsThreads, 1)
     topk_radix_kernel(const float* __restrict__ scores, const uint8_t* __restrict__ valid,
                       const float4* __restrict__ boxes, int N, int k, int kcap, int nchunks, RsLayout L,
                       float* __restrict__ out_scores, int32_t* __restrict__ out_idx, int32_t* __restrict__ out_cidx,
-                      float4* __restrict__ out_boxes, int32_t* __restrict__ out_count, long long* __restrict__ dbg) {
+                      float4* __restrict__ out_boxes, int32_t* __restrict__ out_count, long long* __restrict__ dbg,
+                      int only_flagged) {
     extern __shared__ __align__(16) unsigned char smem[];
+    // second launch behind topk_bucket_kernel: only the images it handed over (out_count == -1) are redone here
+    if (only_flagged && out_count[blockIdx.x] != -1) return;
     const bool prof = (dbg != nullptr) && blockIdx.x == 0 && threadIdx.x == 0;
     long long t0 = prof ? clock64() : 0;
 #define RS_TICK(slot)                   \
@@ -392,6 +395,236 @@ __global__ void __launch_bounds__(kRsThreads, 1)
 #undef RS_TICK
 }
 
+// ------------------------------------------------------------------------------------------------
+// Bucket version (default): ONE histogram pass replaces both the 4-pass radix select and the 6-pass LSD sort.
+//   The valid scores are mapped monotonically onto 4096 buckets, bucket(s) = floor((smax - s) * 4096 / (smax - smin))
+//   (float arithmetic is monotone under rounding, so a higher score never lands in a later bucket; RPN scores are
+//   sigmoid outputs, nearly uniform in value, ~5 per bucket).  A shared-memory histogram + one block scan give the
+//   bucket b* in which the k-th largest score lies; the (key, index) pairs of buckets <= b* are scattered to their
+//   bucket ranges (unordered, atomic cursors) and every bucket is insertion-sorted by one thread on the EXACT total
+//   order (ordered key descending, index ascending) -- the same order the radix kernel produces, so ties and the cut
+//   inside b* are bit-identical.  Inputs that do not bucket well (non-finite range, a bucket of > kBucketMax, more than
+//   `cap` stored pairs: e.g. all scores equal) are handed to the radix kernel through out_count = -1.
+constexpr int kBuckets = 4096;
+constexpr int kBucketMax = 192;
+constexpr int kBucketSlack = 1024;  // pairs stored beyond k (the rest of bucket b*)
+
+struct BkHdr {
+    unsigned int warp_tmp[kRsWarps];
+    unsigned int red[kRsWarps];
+    unsigned int nvalid, bstar, stored, bad;
+    float smin, smax;
+};
+
+__global__ void __launch_bounds__(kRsThreads, 1)
+    topk_bucket_kernel(const float* __restrict__ scores, const uint8_t* __restrict__ valid,
+                       const float4* __restrict__ boxes, int N, int k, int cap, int nchunks,
+                       float* __restrict__ out_scores, int32_t* __restrict__ out_idx, int32_t* __restrict__ out_cidx,
+                       float4* __restrict__ out_boxes, int32_t* __restrict__ out_count) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    BkHdr* hd = reinterpret_cast<BkHdr*>(smem);
+    size_t o = up16(sizeof(BkHdr));
+    unsigned int* vbits = reinterpret_cast<unsigned int*>(smem + o); o += 4 * (size_t)nchunks;
+    unsigned int* vpre = reinterpret_cast<unsigned int*>(smem + o);  o = up16(o + 4 * (size_t)nchunks);
+    unsigned int* hist = reinterpret_cast<unsigned int*>(smem + o);  o += 4 * (size_t)kBuckets;
+    unsigned int* start = reinterpret_cast<unsigned int*>(smem + o); o = up16(o + 4 * (size_t)(kBuckets + 1));
+    float* sval = reinterpret_cast<float*>(smem + o);                o = up16(o + 4 * (size_t)N);
+    unsigned int* keyA = reinterpret_cast<unsigned int*>(smem + o);  o += 4 * (size_t)cap;
+    unsigned short* idxA = reinterpret_cast<unsigned short*>(smem + o);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x;
+    const float* sc = scores + (size_t)b * N;
+    const uint8_t* va = valid ? valid + (size_t)b * N : nullptr;
+
+    // ---- 0. validity words, staged scores, min / max of the valid scores, zeroed histogram ---------------
+    float lmin = 3.0e38f, lmax = -3.0e38f;
+    bool lbad = false;
+    for (int c0 = warp; c0 < nchunks; c0 += 4 * kRsWarps) {  // 4 chunks per trip: 8 independent loads in flight
+        uint8_t v4[4];
+        float s4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = (c0 + j * kRsWarps) * 32 + lane;
+            v4[j] = (i < N && va) ? va[i] : (uint8_t)1;
+            s4[j] = (i < N) ? sc[i] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + j * kRsWarps;
+            const int i = c * 32 + lane;
+            const bool ok = (i < N) && (v4[j] != 0);
+            const unsigned int w = __ballot_sync(0xffffffffu, ok);
+            if (c < nchunks) {
+                if (lane == 0) vbits[c] = w;
+                if (i < N) sval[i] = s4[j];
+                if (ok) {
+                    lbad |= !(fabsf(s4[j]) <= 3.0e38f);  // NaN / inf: no monotone float bucket map
+                    lmin = fminf(lmin, s4[j]);
+                    lmax = fmaxf(lmax, s4[j]);
+                }
+            }
+        }
+    }
+    for (int i = tid; i < kBuckets; i += kRsThreads) hist[i] = 0u;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, off));
+        lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, off));
+    }
+    const bool wbad = __any_sync(0xffffffffu, lbad);
+    if (lane == 0) { hd->warp_tmp[warp] = __float_as_uint(lmin); hd->red[warp] = __float_as_uint(lmax); }
+    if (tid == 0) hd->bad = 0u;
+    __syncthreads();
+    if (wbad && lane == 0) hd->bad = 1u;
+    if (warp == 0) {
+        float a = __uint_as_float(hd->warp_tmp[lane]), z = __uint_as_float(hd->red[lane]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            a = fminf(a, __shfl_xor_sync(0xffffffffu, a, off));
+            z = fmaxf(z, __shfl_xor_sync(0xffffffffu, z, off));
+        }
+        if (lane == 0) { hd->smin = a; hd->smax = z; }
+    }
+    __syncthreads();
+    {   // exclusive prefix of the valid counts per chunk (compacted indices) and the number of valid scores
+        unsigned int run = 0;
+        for (int base = 0; base < nchunks; base += kRsThreads) {
+            const int c = base + tid;
+            const unsigned int v = (c < nchunks) ? __popc(vbits[c]) : 0u;
+            unsigned int tot;
+            const unsigned int ex = block_exclusive_scan(v, hd->warp_tmp, &tot);
+            if (c < nchunks) vpre[c] = run + ex;
+            run += tot;
+        }
+        if (tid == 0) hd->nvalid = run;
+    }
+    __syncthreads();
+    const int keff = min(k, (int)hd->nvalid);
+    const float smax = hd->smax;
+    const float scale = (float)kBuckets / (smax - hd->smin);
+    bool handover = hd->bad != 0u || (keff > 0 && !(scale <= 3.0e38f));  // empty range (all equal) or overflow
+    auto bucket_of = [&](float s) { return min(kBuckets - 1, (int)((smax - s) * scale)); };
+
+    if (keff > 0 && !handover) {
+        // ---- 1. histogram of the valid scores ------------------------------------------------------------
+        for (int c = warp; c < nchunks; c += kRsWarps) {
+            const int i = c * 32 + lane;
+            if ((vbits[c] >> lane) & 1u) atomicAdd(&hist[bucket_of(sval[i])], 1u);
+        }
+        __syncthreads();
+        // ---- 2. bucket starts, the bucket b* of the k-th largest score, the largest bucket up to b* ----------
+        {
+            unsigned int h4[4], t4 = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { h4[q] = hist[4 * tid + q]; t4 += h4[q]; }
+            unsigned int tot;
+            unsigned int run = block_exclusive_scan(t4, hd->warp_tmp, &tot);
+            unsigned int big = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                start[4 * tid + q] = run;
+                if (run < (unsigned int)keff) {
+                    big = max(big, h4[q]);
+                    if (run + h4[q] >= (unsigned int)keff) { hd->bstar = 4 * tid + q; hd->stored = run + h4[q]; }
+                }
+                run += h4[q];
+            }
+            if (tid == kRsThreads - 1) start[kBuckets] = run;
+            big = __reduce_max_sync(0xffffffffu, big);
+            __syncthreads();
+            if (lane == 0) hd->red[warp] = big;
+            __syncthreads();
+            if (warp == 0) {
+                big = __reduce_max_sync(0xffffffffu, hd->red[lane]);
+                if (lane == 0 && (big > kBucketMax || hd->stored > (unsigned int)cap)) hd->bad = 1u;
+            }
+            for (int i = tid; i < kBuckets; i += kRsThreads) hist[i] = 0u;  // now the scatter cursors
+            __syncthreads();
+            handover = hd->bad != 0u;
+        }
+    }
+    if (handover) {
+        if (tid == 0) out_count[b] = -1;
+        return;
+    }
+    if (tid == 0) out_count[b] = keff;
+    if (keff > 0) {
+        const int bstar = (int)hd->bstar;
+        // ---- 3. scatter the pairs of buckets <= b* into their ranges (unordered inside a bucket) --------------
+        for (int c = warp; c < nchunks; c += kRsWarps) {
+            const int i = c * 32 + lane;
+            if ((vbits[c] >> lane) & 1u) {
+                const float sv = sval[i];
+                const int bk = bucket_of(sv);
+                if (bk <= bstar) {
+                    const unsigned int pos = start[bk] + atomicAdd(&hist[bk], 1u);
+                    keyA[pos] = float_to_ordered(sv);
+                    idxA[pos] = (unsigned short)i;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- 4. every bucket sorted by one thread: ordered key descending, index ascending --------------------
+        for (int bk = tid; bk <= bstar; bk += kRsThreads) {
+            const int s0 = (int)start[bk], s1 = (int)start[bk + 1];
+            for (int a = s0 + 1; a < s1; ++a) {
+                const unsigned int ku = keyA[a];
+                const unsigned short ki = idxA[a];
+                int p2 = a - 1;
+                while (p2 >= s0) {
+                    const unsigned int kp = keyA[p2];
+                    const unsigned short ip = idxA[p2];
+                    if (kp > ku || (kp == ku && ip < ki)) break;
+                    keyA[p2 + 1] = kp;
+                    idxA[p2 + 1] = ip;
+                    --p2;
+                }
+                keyA[p2 + 1] = ku;
+                idxA[p2 + 1] = ki;
+            }
+        }
+        __syncthreads();
+    }
+    // ---- 5. write-out (4 independent gathers in flight per thread) ------------------------------------------
+    for (int j0 = tid; j0 < k; j0 += 4 * kRsThreads) {
+        int ii[4];
+        unsigned int kk[4];
+        float4 bx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * kRsThreads;
+            ii[u] = -1;
+            kk[u] = 0u;
+            if (j < keff) { kk[u] = keyA[j]; ii[u] = (int)idxA[j]; }
+        }
+        if (out_boxes) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                bx[u] = ii[u] >= 0 ? boxes[(size_t)b * N + ii[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * kRsThreads;
+            if (j >= k) continue;
+            const size_t oo = (size_t)b * k + j;
+            const int i = ii[u];
+            if (out_scores) out_scores[oo] = i >= 0 ? ordered_to_float(kk[u]) : __uint_as_float(0xff800000u);  // -inf pad
+            out_idx[oo] = i;
+            if (out_cidx) out_cidx[oo] = i >= 0 ? (int)(vpre[i >> 5] + __popc(vbits[i >> 5] & ((1u << (i & 31)) - 1u))) : -1;
+            if (out_boxes) out_boxes[oo] = bx[u];
+        }
+    }
+}
+
+static size_t bucket_smem(int N, int cap, int nchunks) {
+    size_t o = up16(sizeof(BkHdr));
+    o = up16(o + 8 * (size_t)nchunks);
+    o = up16(o + 4 * (size_t)kBuckets + 4 * (size_t)(kBuckets + 1));
+    o = up16(o + 4 * (size_t)N);
+    return up16(o + 6 * (size_t)cap);
+}
+
 // Returns FRR_OK when the launch was done, 1 when the shape is outside the fast path (caller falls back).
 int topk_radix_launch(const float* scores, const uint8_t* valid, const float* boxes, int B, int N, int k,
                       float* out_scores, int32_t* out_idx, int32_t* out_cidx, float* out_boxes, int32_t* out_count,
@@ -407,8 +640,22 @@ int topk_radix_launch(const float* scores, const uint8_t* valid, const float* bo
     if (L.total > limit) return 1;
     auto kern = L.staged ? topk_radix_kernel<true> : topk_radix_kernel<false>;
     FRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+    // bucket kernel first (unless the per-phase profile of the radix kernel is asked for); the radix kernel then redoes
+    // only the images the bucket kernel handed over (all of its CTAs exit at once in the common case)
+    const int cap = kcap + kBucketSlack;
+    const size_t bsm = bucket_smem(N, cap, nchunks);
+    const bool bucket = dbg == nullptr && bsm <= limit;
+    if (bucket) {
+        FRR_CUDA(cudaFuncSetAttribute(topk_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+        topk_bucket_kernel<<<B, kRsThreads, bsm, (cudaStream_t)stream>>>(scores, valid, (const float4*)boxes, N, k, cap, nchunks,
+                                                                        out_scores, out_idx, out_cidx, (float4*)out_boxes,
+                                                                        out_count);
+        count_launch();
+        FRR_CHECK_LAUNCH("topk_bucket_kernel");
+    }
     kern<<<B, kRsThreads, L.total, (cudaStream_t)stream>>>(scores, valid, (const float4*)boxes, N, k, kcap, nchunks, L,
-                                                            out_scores, out_idx, out_cidx, (float4*)out_boxes, out_count, dbg);
+                                                            out_scores, out_idx, out_cidx, (float4*)out_boxes, out_count, dbg,
+                                                            bucket ? 1 : 0);
     count_launch();
     FRR_CHECK_LAUNCH("topk_radix_kernel");
     return FRR_OK;

@@ -375,3 +375,31 @@ def test_topk_more_than_65536_anchors_takes_the_general_kernel(oracle):
     assert int(r["count"][0]) == k
     assert np.array_equal(r["idx"][0].cpu().numpy(), idx)
     assert np.array_equal(r["cidx"][0].cpu().numpy(), order)
+
+
+def test_topk_bucket_kernel_hands_over_badly_bucketing_inputs(oracle):
+    """The bucket top-k (one histogram pass + per-bucket sorts) hands images whose scores do not bucket well to the radix
+    kernel (out_count = -1 between the two launches): all scores equal (empty range), one value repeated far beyond the
+    bucket capacity, infinities.  Mixed in one batch with a well-behaved image; every row must equal the oracle's
+    order (descending, ties lower index first)."""
+    rs = np.random.RandomState(77)
+    N, k = 9000, 5000
+    rows = [synth.unique_scores(rs, N),                                   # well behaved -> bucket path
+            np.full((N,), 0.25, np.float32),                              # empty range
+            synth.unique_scores(rs, N), synth.unique_scores(rs, N), synth.unique_scores(rs, N)]
+    rows[2][rs.permutation(N)[:3000]] = 0.5                               # 3000 copies of one value (> bucket capacity)
+    rows[3][[5, 17]] = np.inf                                             # non-finite: no float bucket map
+    rows[3][[6]] = -np.inf
+    rows[4] = (rows[4] * 1e-3).astype(np.float32)                          # narrow range, still fine
+    rows[4][::2] = rows[4][1]                                             # ... but half of it is one value
+    scores = np.stack(rows)
+    valid = rs.uniform(size=scores.shape) > 0.05
+    r = ops.topk_desc(dev(scores), k, valid=dev(valid.astype(np.uint8)), want_cidx=True)
+    cnt = r["count"].cpu().numpy()
+    for b in range(len(rows)):
+        cidx, idx = _oracle_topk(oracle, scores[b], valid[b], k)
+        n = len(idx)
+        assert cnt[b] == n
+        assert np.array_equal(r["idx"][b, :n].cpu().numpy(), idx), b
+        assert np.array_equal(r["cidx"][b, :n].cpu().numpy(), cidx), b
+        assert np.array_equal(r["scores"][b, :n].cpu().numpy(), scores[b][idx]), b
