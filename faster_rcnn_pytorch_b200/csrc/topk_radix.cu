@@ -416,6 +416,7 @@ struct BkHdr {
     float smin, smax;
 };
 
+template <bool kStaged>  // scores staged in shared memory (N up to ~27 k) or re-read from global / L2 in the two passes
 __global__ void __launch_bounds__(kRsThreads, 1)
     topk_bucket_kernel(const float* __restrict__ scores, const uint8_t* __restrict__ valid,
                        const float4* __restrict__ boxes, int N, int k, int cap, int nchunks,
@@ -428,7 +429,7 @@ __global__ void __launch_bounds__(kRsThreads, 1)
     unsigned int* vpre = reinterpret_cast<unsigned int*>(smem + o);  o = up16(o + 4 * (size_t)nchunks);
     unsigned int* hist = reinterpret_cast<unsigned int*>(smem + o);  o += 4 * (size_t)kBuckets;
     unsigned int* start = reinterpret_cast<unsigned int*>(smem + o); o = up16(o + 4 * (size_t)(kBuckets + 1));
-    float* sval = reinterpret_cast<float*>(smem + o);                o = up16(o + 4 * (size_t)N);
+    float* sval = reinterpret_cast<float*>(smem + o);                o = up16(o + (kStaged ? 4 * (size_t)N : 0));
     unsigned int* keyA = reinterpret_cast<unsigned int*>(smem + o);  o += 4 * (size_t)cap;
     unsigned short* idxA = reinterpret_cast<unsigned short*>(smem + o);
 
@@ -457,7 +458,7 @@ __global__ void __launch_bounds__(kRsThreads, 1)
             const unsigned int w = __ballot_sync(0xffffffffu, ok);
             if (c < nchunks) {
                 if (lane == 0) vbits[c] = w;
-                if (i < N) sval[i] = s4[j];
+                if (kStaged && i < N) sval[i] = s4[j];
                 if (ok) {
                     lbad |= !(fabsf(s4[j]) <= 3.0e38f);  // NaN / inf: no monotone float bucket map
                     lmin = fminf(lmin, s4[j]);
@@ -505,12 +506,13 @@ __global__ void __launch_bounds__(kRsThreads, 1)
     const float scale = (float)kBuckets / (smax - hd->smin);
     bool handover = hd->bad != 0u || (keff > 0 && !(scale <= 3.0e38f));  // empty range (all equal) or overflow
     auto bucket_of = [&](float s) { return min(kBuckets - 1, (int)((smax - s) * scale)); };
+    auto score_at = [&](int i) -> float { return kStaged ? sval[i] : sc[i]; };
 
     if (keff > 0 && !handover) {
         // ---- 1. histogram of the valid scores ------------------------------------------------------------
         for (int c = warp; c < nchunks; c += kRsWarps) {
             const int i = c * 32 + lane;
-            if ((vbits[c] >> lane) & 1u) atomicAdd(&hist[bucket_of(sval[i])], 1u);
+            if ((vbits[c] >> lane) & 1u) atomicAdd(&hist[bucket_of(score_at(i))], 1u);
         }
         __syncthreads();
         // ---- 2. bucket starts, the bucket b* of the k-th largest score, the largest bucket up to b* ----------
@@ -555,7 +557,7 @@ __global__ void __launch_bounds__(kRsThreads, 1)
         for (int c = warp; c < nchunks; c += kRsWarps) {
             const int i = c * 32 + lane;
             if ((vbits[c] >> lane) & 1u) {
-                const float sv = sval[i];
+                const float sv = score_at(i);
                 const int bk = bucket_of(sv);
                 if (bk <= bstar) {
                     const unsigned int pos = start[bk] + atomicAdd(&hist[bk], 1u);
@@ -617,11 +619,11 @@ __global__ void __launch_bounds__(kRsThreads, 1)
     }
 }
 
-static size_t bucket_smem(int N, int cap, int nchunks) {
+static size_t bucket_smem(int N, int cap, int nchunks, bool staged) {
     size_t o = up16(sizeof(BkHdr));
     o = up16(o + 8 * (size_t)nchunks);
     o = up16(o + 4 * (size_t)kBuckets + 4 * (size_t)(kBuckets + 1));
-    o = up16(o + 4 * (size_t)N);
+    o = up16(o + (staged ? 4 * (size_t)N : 0));
     return up16(o + 6 * (size_t)cap);
 }
 
@@ -643,13 +645,14 @@ int topk_radix_launch(const float* scores, const uint8_t* valid, const float* bo
     // bucket kernel first (unless the per-phase profile of the radix kernel is asked for); the radix kernel then redoes
     // only the images the bucket kernel handed over (all of its CTAs exit at once in the common case)
     const int cap = kcap + kBucketSlack;
-    const size_t bsm = bucket_smem(N, cap, nchunks);
+    const bool bstaged = bucket_smem(N, cap, nchunks, true) <= limit;
+    const size_t bsm = bucket_smem(N, cap, nchunks, bstaged);
     const bool bucket = dbg == nullptr && bsm <= limit;
     if (bucket) {
-        FRR_CUDA(cudaFuncSetAttribute(topk_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
-        topk_bucket_kernel<<<B, kRsThreads, bsm, (cudaStream_t)stream>>>(scores, valid, (const float4*)boxes, N, k, cap, nchunks,
-                                                                        out_scores, out_idx, out_cidx, (float4*)out_boxes,
-                                                                        out_count);
+        auto bkern = bstaged ? topk_bucket_kernel<true> : topk_bucket_kernel<false>;
+        FRR_CUDA(cudaFuncSetAttribute(bkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+        bkern<<<B, kRsThreads, bsm, (cudaStream_t)stream>>>(scores, valid, (const float4*)boxes, N, k, cap, nchunks, out_scores,
+                                                             out_idx, out_cidx, (float4*)out_boxes, out_count);
         count_launch();
         FRR_CHECK_LAUNCH("topk_bucket_kernel");
     }
