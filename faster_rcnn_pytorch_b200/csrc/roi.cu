@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-// 7x7 fast paths (roi_fast.cu): 0 = launched, 1 = shape outside the fast path, < 0 = error
+// 7x7 fast paths (roi_fast.cu): 0 = launched, 1 = shape outside the fast path, 2 = use the direct atomic kernel, < 0 = error
 int roi_fwd_fast(bool align, const float* feat, const float* rois, int K, int B, int C, int H, int W, int PH, int PW,
                  float scale, int sampling, int aligned, int nhwc, float* out, int32_t* argmax, frr_stream_t stream);
 int roi_pool_bwd_fast(const float* grad_out, const int32_t* argmax, const float* rois, int K, int B, int C, int H, int W,
@@ -322,14 +322,16 @@ static int roi_backward(const float* grad_out, const int32_t* argmax, const floa
     FRR_CHECK_ARG(grad_in && (K == 0 || (grad_out && rois)), "roi backward: null pointer");
     FRR_CHECK_ARG(kAlign || K == 0 || argmax, "roi_pool backward: argmax is required");
     FRR_CHECK_ARG(K >= 0 && B > 0 && C > 0 && H > 0 && W > 0 && PH > 0 && PW > 0 && B <= 65535, "roi backward: bad sizes");
+    bool direct = false;
     if (K > 0) {
         const int rc = kAlign ? roi_align_bwd_fast(grad_out, rois, K, B, C, H, W, PH, PW, scale, sampling, aligned, nhwc, grad_in, stream)
                               : roi_pool_bwd_fast(grad_out, argmax, rois, K, B, C, H, W, PH, PW, nhwc, grad_in, stream);
         if (rc <= 0) return rc;
+        direct = rc == 2;  // the fast path asks for the global-atomic kernel
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int HW = H * W;
-    const int cb = pick_cb(B, C, HW);
+    const int cb = direct ? 0 : pick_cb(B, C, HW);
     if (cb > 0) {
         const size_t smem = roi_smem_bytes(cb, HW);
         auto kern = roi_bwd_planes_kernel<kAlign>;

@@ -774,6 +774,10 @@ int roi_pool_bwd_fast(const float* grad_out, const int32_t* argmax, const float*
         if ((long)B * ((C + t - 1) / t) >= (long)num_sms()) break;
     }
     if (cbk == 0) return 1;
+    // When 16 planes do not fit shared memory (maps above ~3400 pixels: the 50x83 map of an 800x1333 image) the
+    // warp-owned plane kernel is left with 8 or 4 warps per SM and is latency bound (measured 520 us against 320 us for
+    // global RED.ADD on the config-4 shape): the caller takes the direct atomic kernel then.
+    if (bwd_fast_smem(16, HW) > kSmemLimit) return 2;
     cudaStream_t st = (cudaStream_t)stream;
     const int rc = cbk == 16 ? launch_pool_bwd<16>(grad_out, argmax, rois, K, B, C, H, W, nhwc, grad_in, st)
                  : cbk == 8  ? launch_pool_bwd<8>(grad_out, argmax, rois, K, B, C, H, W, nhwc, grad_in, st)

@@ -107,6 +107,18 @@ class ProposalPlan:
         return rois, count
 
 
+    def capture(self, cls, reg):
+        """Capture one ``run(cls, reg)`` into a CUDA graph (the call neither allocates nor synchronises) and return the
+        ``torch.cuda.CUDAGraph``; ``graph.replay()`` then re-runs the whole proposal layer on whatever ``cls`` / ``reg``
+        hold at that moment, writing ``self.rois`` / ``self.count``, for one graph launch instead of four kernel launches."""
+        self.run(cls, reg)                                    # warm-up outside the capture (function attributes, tables)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.run(cls, reg)
+        return graph
+
+
 class HostProposalPipeline:
     """Proposal layer for HOST inputs (numpy / CPU tensors), double buffered.
 

@@ -403,3 +403,26 @@ def test_topk_bucket_kernel_hands_over_badly_bucketing_inputs(oracle):
         assert np.array_equal(r["idx"][b, :n].cpu().numpy(), idx), b
         assert np.array_equal(r["cidx"][b, :n].cpu().numpy(), cidx), b
         assert np.array_equal(r["scores"][b, :n].cpu().numpy(), scores[b][idx]), b
+
+
+def test_proposal_plan_is_cuda_graph_capturable(oracle):
+    """frr_rpn_proposals never allocates or synchronises: one call captured into a CUDA graph replays on new inputs and
+    gives the same rois / counts as the eager call."""
+    from faster_rcnn_pytorch_b200 import region
+    hw, B = (320, 480), 3
+    ins = [synth.rpn_head_outputs(300 + i, hw) for i in range(B + B)]
+    n = synth.num_anchors(hw)
+    plan = region.ProposalPlan(B, n, DEV, image_hw=hw, mode="train", logits=False)
+    sc = dev(np.stack([x[2] for x in ins[:B]]))
+    rg = dev(np.stack([x[1] for x in ins[:B]]))
+    graph = plan.capture(sc, rg)
+    # new inputs in the captured buffers
+    sc.copy_(dev(np.stack([x[2] for x in ins[B:]])))
+    rg.copy_(dev(np.stack([x[1] for x in ins[B:]])))
+    graph.replay()
+    torch.cuda.synchronize()
+    got_rois, got_cnt = plan.rois.clone(), plan.count.clone()
+    want_rois, want_cnt = region.rpn_proposals(sc, rg, image_hw=hw, mode="train")
+    assert torch.equal(got_cnt, want_cnt)
+    assert torch.equal(got_rois, want_rois)
+    assert int(got_cnt.min()) > 0
