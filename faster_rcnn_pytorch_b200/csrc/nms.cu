@@ -44,7 +44,6 @@ struct NmsThr {
 };
 
 constexpr int kStrips = 88;         // area classes of the sorted kept slice (4 per octave, 2^-22 .. 1); class kStrips = boxes that must always be tested
-constexpr int kGroupCands = 4;      // candidates per warp pass in the sorted phase 1
 
 __device__ __forceinline__ float box_area(const float4& b) {
     return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
@@ -257,88 +256,42 @@ __global__ void __launch_bounds__(kThreads)
             if (tid < kChunk) sm->cord[atomicAdd(&sm->ccursor[cst], 1u)] = (unsigned short)tid;
             __syncthreads();
             FRR_TICK(10);  // bucketing time (reported separately, not part of the phase-1 slot)
-            // (c) groups of 4 class-adjacent candidates: warp-uniform registers, the LANES walk the admissible kept boxes
-            const int sp_lo = sm->sstart[kStrips], sp_hi = sm->sstart[kStrips + 1];  // always-tested boxes
-            for (int g = warp; g < kChunk / kGroupCands; g += kWarps) {
-                float4 cb[kGroupCands];
-                float ca[kGroupCands];
-                int cpos[kGroupCands];
-                bool has[kGroupCands];
-                bool all_range = false;
-                float alo = 3.0e38f, ahi = -3.0e38f;
-                bool any = false;
-#pragma unroll
-                for (int j = 0; j < kGroupCands; ++j) {
-                    cpos[j] = sm->cord[g * kGroupCands + j];
-                    cb[j] = sm->cbox[cpos[j]];
-                    ca[j] = sm->carea[cpos[j]];
-                    has[j] = base + cpos[j] < cnt;
-                    if (has[j]) {
-                        any = true;
-                        if (ca[j] != ca[j]) {
-                            all_range = true;  // no usable screening area: test against the whole slice
-                        } else {
-                            const float a = box_area(cb[j]);
-                            alo = fminf(alo, a * thr.alo);
-                            ahi = fmaxf(ahi, a * thr.ahi);
-                        }
+            // (c) kSub threads per candidate (candidates in class order, so the lanes of a warp walk ranges of similar
+            //     length): each thread screens its candidate against every kSub-th kept box of the candidate's admissible
+            //     classes and of the always-tested class, remembers one hit, and confirms it with the exact test.  (The
+            //     earlier form -- a warp per 4 candidates, lanes over kept boxes -- spent half of its issue slots on
+            //     warp-uniform bookkeeping: after the area cut a group's range is only ~4 warp trips long.  Dealing
+            //     fixed-size pieces of the ranges to the threads through a prefix sum balances better but was measured
+            //     1.7x slower: the per-item search and the virtual-range indexing cost more than the imbalance.)
+            {
+                constexpr int kSub = kThreads / kChunk;
+                const int sub = tid % kSub;
+                const int cpos = sm->cord[tid / kSub];
+                if (base + cpos < cnt) {
+                    const float4 cbx = sm->cbox[cpos];
+                    const float ca = sm->carea[cpos];
+                    int lo = 0, hi = ns, lo2 = 0, hi2 = 0;
+                    if (ca == ca) {
+                        const float a = box_area(cbx);
+                        lo = sm->sstart[strip_of_area(a * thr.alo)];
+                        hi = sm->sstart[strip_of_area(a * thr.ahi) + 1];
+                        lo2 = sm->sstart[kStrips];
+                        hi2 = sm->sstart[kStrips + 1];
                     }
-                }
-                if (!any) continue;  // warp-uniform
-                int lo = 0, hi = ns;
-                if (!all_range) {
-                    lo = sm->sstart[strip_of_area(alo)];
-                    hi = sm->sstart[strip_of_area(ahi) + 1];
-                }
-                // two segments: the admissible area classes and (unless already covered) the always-tested class
-                int pk[kGroupCands];
-#pragma unroll
-                for (int j = 0; j < kGroupCands; ++j) pk[j] = -1;
-#pragma unroll 1
-                for (int seg = 0; seg < 2; ++seg) {
-                    const int a0 = seg == 0 ? lo : (all_range ? 0 : sp_lo);
-                    const int a1 = seg == 0 ? hi : (all_range ? 0 : sp_hi);
-                    const int trips = (a1 - a0 + 31) >> 5;
-                    // walked from the end: the plain conditional move leaves the smallest passing k
-                    for (int k = a0 + lane + (trips - 1) * 32; k >= a0; k -= 32) {
-                        if (k < a1) {
-                            const float4 kb = kbox[k];
-                            const float ka = karea[k];
-#pragma unroll
-                            for (int j = 0; j < kGroupCands; ++j)
-                                if (suppress_screen<true>(kb, ka, cb[j], ca[j])) pk[j] = k;
+                    int pk = -1;
+#pragma unroll 4
+                    for (int k = lo + sub; k < hi; k += kSub)
+                        if (suppress_screen<true>(kbox[k], karea[k], cbx, ca)) pk = k;
+                    for (int k = lo2 + sub; k < hi2; k += kSub)
+                        if (suppress_screen<true>(kbox[k], karea[k], cbx, ca)) pk = k;
+                    if (pk >= 0) {
+                        bool r = suppress_exact(kbox[pk], cbx, thr.up);
+                        if (!r) {  // the screen hit was not confirmed by the exact test (rare): exact walk of the own share
+                            for (int k = lo + sub; k < hi && !r; k += kSub) r = suppress_exact(kbox[k], cbx, thr.up);
+                            for (int k = lo2 + sub; k < hi2 && !r; k += kSub) r = suppress_exact(kbox[k], cbx, thr.up);
                         }
+                        if (r) atomicOr(&sm->acc[par][cpos >> 5], 1u << (cpos & 31));
                     }
-                }
-                // Verdicts.  The exact test of one screen hit per candidate is enough almost always (the screen is tight to
-                // 2^-19), and the four candidates' tests run side by side in lanes 0..3: ONE call of the division path per
-                // group instead of one per candidate (the sequential form cost twice as many issue slots as the scan).
-                int kj = -1;  // lane j < 4: a kept box that passed the screen against candidate j
-                unsigned int hit_any = 0u;
-#pragma unroll
-                for (int j = 0; j < kGroupCands; ++j) {
-                    const unsigned int m = __ballot_sync(0xffffffffu, has[j] && pk[j] >= 0);
-                    const int v = __shfl_sync(0xffffffffu, pk[j], m ? __ffs(m) - 1 : 0);
-                    if (lane == j && m) kj = v;
-                    hit_any |= m ? (1u << j) : 0u;
-                }
-                bool r = false;
-                if (kj >= 0) r = suppress_exact(kbox[kj], sm->cbox[sm->cord[g * kGroupCands + lane]], thr.up);
-                unsigned int confirmed = __ballot_sync(0xffffffffu, r);
-                unsigned int redo = hit_any & ~confirmed;
-                while (redo) {  // a screen hit was not confirmed by the exact test (rare): exact walk of both segments
-                    const int j = __ffs(redo) - 1;
-                    redo &= redo - 1;
-                    const float4 cbj = sm->cbox[sm->cord[g * kGroupCands + j]];
-                    bool rr = false;
-                    for (int k = lo + lane; k < hi; k += 32) rr = rr || suppress_exact(kbox[k], cbj, thr.up);
-                    if (!all_range)
-                        for (int k = sp_lo + lane; k < sp_hi; k += 32) rr = rr || suppress_exact(kbox[k], cbj, thr.up);
-                    if (__any_sync(0xffffffffu, rr)) confirmed |= 1u << j;
-                }
-                if (lane < kGroupCands && ((confirmed >> lane) & 1u)) {
-                    const int cp = sm->cord[g * kGroupCands + lane];
-                    atomicOr(&sm->acc[par][cp >> 5], 1u << (cp & 31));
                 }
             }
         } else {

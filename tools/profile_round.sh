@@ -11,7 +11,7 @@ python bench.py --workload infer > $O/${R}_bench_infer.json 2> $O/${R}_bench_inf
 python tools/stage_profile.py > $O/${R}_stage_profile.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${R}_bench_launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu > $O/ncu1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"nms_keeplist|rpn_decode|topk_radix" -s 12 -c 3 \
+ncu --set full --clock-control none --import-source on -k regex:"nms_keeplist|rpn_decode|topk_bucket" -s 12 -c 3 \
     -o $O/prof_${R}_proposal -f python bench.py --steps 3 --warmup 3 --no-cpu > $O/ncu2.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"roi_|sample_|region_loss" -c 8 \
     -o $O/prof_${R}_roi -f python tools/roi_one.py > $O/ncu3.log 2>&1
