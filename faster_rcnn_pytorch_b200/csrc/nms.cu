@@ -40,10 +40,15 @@ struct NmsThr {
     float up;  // smallest fp32 with (double)up > thr
     float c2;  // up/(1+up) * (1 - 2^-19): screening constant
     float alo, ahi;  // a box of area A can only be suppressed by boxes with area in [alo * A, ahi * A] (IoU <= min/max area)
+    float fx;        // ... and only by boxes whose x-centre is within fx * (its width) of its own
     int fast;  // screening usable (1e-6 <= thr, finite)
 };
 
-constexpr int kStrips = 88;         // area classes of the sorted kept slice (4 per octave, 2^-22 .. 1); class kStrips = boxes that must always be tested
+constexpr int kStrips = 88;         // area classes of the sorted kept slice (4 per octave, 2^-22 .. 1)
+constexpr int kXBins = 8;           // x-centre bins inside an area class
+constexpr int kKeys = kStrips * kXBins;  // bucket keys; key kKeys = boxes that must always be tested
+constexpr int kKeyPer = ((kKeys + 2 + 31) / 32 + 3) & ~3;  // keys scanned per lane (a multiple of 4: uint4 accesses)
+constexpr int kKeyCap = 32 * kKeyPer;                       // padded length of the per-key arrays
 
 __device__ __forceinline__ float box_area(const float4& b) {
     return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
@@ -94,25 +99,29 @@ struct NmsSmem {
     float sarea[kChunk];
     short ssrc[kChunk];  // survivor -> position inside the chunk
     // sorted phase 1 (kUnit): kept slice bucketed by area class, chunk candidates ordered by area class
-    unsigned int shist[kStrips + 2];
-    unsigned int scursor[kStrips + 2];
-    unsigned int chist[kStrips + 2];
-    unsigned int ccursor[kStrips + 2];
-    unsigned short sstart[kStrips + 2];  // sstart[s] = first sorted position of strip s; [kStrips+1] = total
+    alignas(16) unsigned int shist[kKeyCap];
+    alignas(16) unsigned int scursor[kKeyCap];
+    alignas(16) unsigned int chist[kKeyCap];
+    alignas(16) unsigned int ccursor[kKeyCap];
+    alignas(16) unsigned short sstart[kKeyCap];  // sstart[s] = first sorted position of key s; [kKeys+1] = total
     unsigned short cord[kChunk];         // chunk positions ordered by area class
 };
 
-// Area class of a box: the top bits of the fp32 area (exponent + 2 mantissa bits = 4 classes per octave), an exactly
-// monotone integer function of the area.  IoU <= min(area) / max(area) (in fp32 as well: w <= both widths and RN is
-// monotone, so inter <= both areas), hence only kept boxes whose area lies within [thr, 1/thr] of the candidate's can
-// suppress it: for RPN proposals (three anchor scales, a factor 4 apart in area) that is a far sharper cut than any
-// position strip, because the large boxes overlap every strip.  Boxes without a usable screening area (degenerate /
-// malformed, NaN sa) go to the extra class kStrips and are tested against everything.
+// Bucket key of a box = (area class, x bin).
+// Area class: the top bits of the fp32 area (exponent + 2 mantissa bits = 4 classes per octave), an exactly monotone
+// integer function of the area.  IoU <= min(area) / max(area) (in fp32 as well: w <= both widths and RN is monotone, so
+// inter <= both areas), hence only kept boxes whose area lies within [thr, 1/thr] of the candidate's can suppress it: for
+// RPN proposals (three anchor scales, a factor 4 apart in area) that alone removes 3/4 of the pairs.
+// x bin: kXBins equal strips of the x-centre; IoU >= thr also needs |cx_K - cx_c| <= fx * w_c, which is sharp exactly
+// where the area cut is not -- the many small boxes of the most populated classes.
+// Boxes without a usable screening area (degenerate / malformed, NaN sa) get the extra key kKeys and are tested
+// against everything.
 __device__ __forceinline__ int strip_of_area(float a) {
     return min(kStrips - 1, max(0, (__float_as_int(a) >> 21) - ((127 - 22) << 2)));
 }
+__device__ __forceinline__ int xbin_of(float cx) { return min(kXBins - 1, max(0, (int)(cx * (float)kXBins))); }
 __device__ __forceinline__ int strip_of(const float4& b, float sa) {
-    return (sa != sa) ? kStrips : strip_of_area(box_area(b));
+    return (sa != sa) ? kKeys : strip_of_area(box_area(b)) * kXBins + xbin_of(0.5f * (b.x + b.z));
 }
 
 // barrier over the first `n` threads of the CTA with an OR reduction of `pred`
@@ -179,7 +188,8 @@ __global__ void __launch_bounds__(kThreads)
     float4 nbx = make_float4(0.f, 0.f, 0.f, 0.f);  // prefetched candidate of the next chunk (first kChunk threads)
     if (tid < kChunk && tid < cnt) nbx = cand(tid);
     if (tid < 2 * kChunkWords) (&sm->acc[0][0])[tid] = 0u;
-    if (kSorted && tid < kStrips + 2) sm->sstart[tid] = 0;
+    if (kSorted)
+        for (int e = tid; e < kKeys + 2; e += kThreads) sm->sstart[e] = 0;
     for (int base = 0; base < cnt && nk < max_keep; base += kChunk, par ^= 1) {
         if (prof) { t0 = clock64(); dbg[DBG_CHUNKS] += 1; }
         // ---- phase 0: stage the chunk's candidates in shared memory, prefetch the next chunk ----------
@@ -202,26 +212,26 @@ __global__ void __launch_bounds__(kThreads)
             //     buffer) and (b) order the chunk's candidates by class (counting sort of <= 256 positions; positions
             //     past the end of the list are marked suppressed right away) -- the two sorts share their barriers
             const bool resort = ns > ns_sorted;
-            if (tid < kStrips + 2) { sm->shist[tid] = 0u; sm->chist[tid] = 0u; }
+            for (int e = tid; e < kKeyCap; e += kThreads) { sm->shist[e] = 0u; sm->chist[e] = 0u; }
             __syncthreads();
             if (resort)
                 for (int i = tid; i < ns; i += kThreads) atomicAdd(&sm->shist[strip_of(kbox[i], karea[i])], 1u);
-            int cst = kStrips + 1;
+            int cst = kKeys + 1;
             if (tid < kChunk) {
                 if (base + tid < cnt) cst = strip_of(sm->cbox[tid], sm->carea[tid]);
                 else atomicOr(&sm->acc[par][tid >> 5], 1u << (tid & 31));
                 atomicAdd(&sm->chist[cst], 1u);
             }
             __syncthreads();
-            if (warp < 2 && (warp == 1 || resort)) {  // warp 0: slice strips, warp 1: candidate strips (3 counts per lane)
+            if (warp < 2 && (warp == 1 || resort)) {  // warp 0: slice keys, warp 1: candidate keys (kKeyPer keys per lane)
                 unsigned int* hist = warp == 0 ? sm->shist : sm->chist;
                 unsigned int* cursor = warp == 0 ? sm->scursor : sm->ccursor;
-                unsigned int c3[3], t3 = 0;
+                unsigned int h[kKeyPer], t3 = 0;
 #pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    const int e = lane * 3 + q;
-                    c3[q] = (e <= kStrips + 1) ? hist[e] : 0u;
-                    t3 += c3[q];
+                for (int q = 0; q < kKeyPer; q += 4) {  // independent 16-byte loads (entries past kKeys + 1 are zero)
+                    const uint4 v = *reinterpret_cast<const uint4*>(hist + lane * kKeyPer + q);
+                    h[q] = v.x; h[q + 1] = v.y; h[q + 2] = v.z; h[q + 3] = v.w;
+                    t3 += v.x + v.y + v.z + v.w;
                 }
                 unsigned int inc = t3;
 #pragma unroll
@@ -231,13 +241,24 @@ __global__ void __launch_bounds__(kThreads)
                 }
                 unsigned int run = inc - t3;
 #pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    const int e = lane * 3 + q;
-                    if (e <= kStrips + 1) {
-                        cursor[e] = run;
-                        if (warp == 0) sm->sstart[e] = (unsigned short)run;
+                for (int q = 0; q < kKeyPer; q += 4) {
+                    uint4 v;
+                    v.x = run; run += h[q];
+                    v.y = run; run += h[q + 1];
+                    v.z = run; run += h[q + 2];
+                    v.w = run; run += h[q + 3];
+                    *reinterpret_cast<uint4*>(cursor + lane * kKeyPer + q) = v;
+                    if (warp == 0) {
+                        const int e = lane * kKeyPer + q;
+                        if (e + 3 <= kKeys + 1) {
+                            *reinterpret_cast<uint2*>(sm->sstart + e) =
+                                make_uint2((v.x & 0xffffu) | (v.y << 16), (v.z & 0xffffu) | (v.w << 16));
+                        } else {
+                            if (e <= kKeys + 1) sm->sstart[e] = (unsigned short)v.x;
+                            if (e + 1 <= kKeys + 1) sm->sstart[e + 1] = (unsigned short)v.y;
+                            if (e + 2 <= kKeys + 1) sm->sstart[e + 2] = (unsigned short)v.z;
+                        }
                     }
-                    run += c3[q];
                 }
             }
             __syncthreads();
@@ -270,24 +291,35 @@ __global__ void __launch_bounds__(kThreads)
                 if (base + cpos < cnt) {
                     const float4 cbx = sm->cbox[cpos];
                     const float ca = sm->carea[cpos];
-                    int lo = 0, hi = ns, lo2 = 0, hi2 = 0;
+                    int pk = -1;
+                    int c_lo = 0, c_hi = -1, x_lo = 0, x_hi = 0;  // admissible keys: classes c_lo..c_hi, x bins x_lo..x_hi
+                    int lo2 = 0, hi2 = ns;                        // second segment: everything (NaN area) / always-tested
                     if (ca == ca) {
                         const float a = box_area(cbx);
-                        lo = sm->sstart[strip_of_area(a * thr.alo)];
-                        hi = sm->sstart[strip_of_area(a * thr.ahi) + 1];
-                        lo2 = sm->sstart[kStrips];
-                        hi2 = sm->sstart[kStrips + 1];
+                        c_lo = strip_of_area(a * thr.alo);
+                        c_hi = strip_of_area(a * thr.ahi);
+                        const float cx = 0.5f * (cbx.x + cbx.z);
+                        const float rx = thr.fx * (cbx.z - cbx.x) * 1.0001f + 2.0e-6f;
+                        x_lo = xbin_of(cx - rx);
+                        x_hi = xbin_of(cx + rx);
+                        lo2 = sm->sstart[kKeys];
+                        hi2 = sm->sstart[kKeys + 1];
                     }
-                    int pk = -1;
+                    for (int c = c_lo; c <= c_hi; ++c) {
+                        const int lo = sm->sstart[c * kXBins + x_lo], hi = sm->sstart[c * kXBins + x_hi + 1];
 #pragma unroll 4
-                    for (int k = lo + sub; k < hi; k += kSub)
-                        if (suppress_screen<true>(kbox[k], karea[k], cbx, ca)) pk = k;
+                        for (int k = lo + sub; k < hi; k += kSub)
+                            if (suppress_screen<true>(kbox[k], karea[k], cbx, ca)) pk = k;
+                    }
                     for (int k = lo2 + sub; k < hi2; k += kSub)
                         if (suppress_screen<true>(kbox[k], karea[k], cbx, ca)) pk = k;
                     if (pk >= 0) {
                         bool r = suppress_exact(kbox[pk], cbx, thr.up);
                         if (!r) {  // the screen hit was not confirmed by the exact test (rare): exact walk of the own share
-                            for (int k = lo + sub; k < hi && !r; k += kSub) r = suppress_exact(kbox[k], cbx, thr.up);
+                            for (int c = c_lo; c <= c_hi && !r; ++c) {
+                                const int lo = sm->sstart[c * kXBins + x_lo], hi = sm->sstart[c * kXBins + x_hi + 1];
+                                for (int k = lo + sub; k < hi && !r; k += kSub) r = suppress_exact(kbox[k], cbx, thr.up);
+                            }
                             for (int k = lo2 + sub; k < hi2 && !r; k += kSub) r = suppress_exact(kbox[k], cbx, thr.up);
                         }
                         if (r) atomicOr(&sm->acc[par][cpos >> 5], 1u << (cpos & 31));
@@ -536,6 +568,8 @@ static NmsThr make_thr(double thr) {
     // IoU >= thr needs min(area) / max(area) >= thr; thr is lowered by 2^-17 relative to cover the fp32 roundings of the
     // exact IoU (<= 2^-20, see strip_of_area) and of the two products below
     const double tl = thr * (1.0 - 7.62939453125e-06);
+    // ... and |cx_a - cx_b| <= max(1 - thr, (1 - thr) / (2 thr)) * w of EITHER box
+    t.fx = t.fast ? (float)(fmax(1.0 - tl, (1.0 - tl) / (2.0 * tl)) * (1.0 + 1.0e-6)) : 0.f;
     t.alo = t.fast ? (float)(tl * (1.0 - 1.0e-6)) : 0.f;
     t.ahi = t.fast ? (float)(1.0 / tl * (1.0 + 1.0e-6)) : 0.f;
     return t;
