@@ -190,3 +190,32 @@ def test_joint_training_step_through_autograd():
     assert float(model.reg_head.weight.grad.abs().sum()) > 0               # through the in-kernel class-row gather
     assert not torch.equal(first, model.extractor[0].weight.detach())
     np.testing.assert_allclose(losses[0][:, 0], losses[0][:, 1:].sum(axis=1), rtol=1e-5)
+
+
+def test_torch_library_ops_match_the_module_path_and_pass_opcheck():
+    """torch.ops.frr.{nms, roi_pool, roi_align, rpn_proposals}: same results as the Python wrappers, gradients through
+    the registered autograd formulas, and torch.library.opcheck (schema, fake kernel, autograd registration)."""
+    from faster_rcnn_pytorch_b200 import region, torch_ops  # noqa: F401
+    feat = dev(synth.features(610, 2, 16, 20, 30)).requires_grad_(True)
+    rois5 = dev(synth.random_rois(611, 40, 20, 30, 2))
+    out, arg = torch.ops.frr.roi_pool(feat, rois5, 1.0, 7, 7)
+    want, warg = ops.roi_pool_forward(feat.detach(), rois5)
+    assert torch.equal(out, want) and torch.equal(arg, warg)
+    go = torch.randn_like(out)
+    out.backward(go)
+    assert torch.equal(feat.grad, ops.roi_pool_backward(go, warg, rois5, feat.shape))
+    f2 = feat.detach().clone().requires_grad_(True)
+    oa = torch.ops.frr.roi_align(f2, rois5, 0.5, 7, 7, 2, False)
+    assert torch.equal(oa, ops.roi_align_forward(f2.detach(), rois5, spatial_scale=0.5, sampling_ratio=2))
+    oa.backward(go)
+    assert torch.equal(f2.grad, ops.roi_align_backward(go, rois5, f2.shape, spatial_scale=0.5, sampling_ratio=2))
+    b, s = synth.random_boxes(612, 700)
+    assert torch.equal(torch.ops.frr.nms(dev(b), dev(s), 0.5), modules.nms(dev(b), dev(s), 0.5))
+    hw = (160, 256)
+    _, reg, sc = synth.rpn_head_outputs(613, hw)
+    r1, c1 = torch.ops.frr.rpn_proposals(dev(sc[None]), dev(reg[None]), hw[0], hw[1], 12000, 2000, 0.7, float(np.float32(0.001)))
+    r2, c2 = region.rpn_proposals(dev(sc[None]), dev(reg[None]), image_hw=hw, mode="train")
+    assert torch.equal(r1, r2) and torch.equal(c1, c2)
+    for op, args in ((torch.ops.frr.roi_pool, (feat.detach().requires_grad_(True), rois5, 1.0, 7, 7)),
+                     (torch.ops.frr.roi_align, (feat.detach().requires_grad_(True), rois5, 1.0, 7, 7, 2, False))):
+        torch.library.opcheck(op, args, test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
