@@ -305,9 +305,24 @@ __global__ void __launch_bounds__(kThreads)
                         lo2 = sm->sstart[kKeys];
                         hi2 = sm->sstart[kKeys + 1];
                     }
-                    for (int c = c_lo; c <= c_hi; ++c) {
+                    // the bounds of all admissible classes are fetched before the first walk (independent loads): with one
+                    // dependent sstart -> kbox chain per class the walks were latency bound
+                    constexpr int kMaxCls = 6;  // [alo, ahi] spans 2 * log2(1 / thr) * 4 + 1 classes: 5.1 at thr 0.7
+                    int lo_c[kMaxCls], hi_c[kMaxCls];
+#pragma unroll
+                    for (int q = 0; q < kMaxCls; ++q) {
+                        const int c = min(c_lo + q, kStrips - 1);
+                        lo_c[q] = sm->sstart[c * kXBins + x_lo];
+                        hi_c[q] = (c_lo + q <= c_hi) ? (int)sm->sstart[c * kXBins + x_hi + 1] : 0;
+                    }
+#pragma unroll
+                    for (int q = 0; q < kMaxCls; ++q) {
+#pragma unroll 2
+                        for (int k = lo_c[q] + sub; k < hi_c[q]; k += kSub)
+                            if (suppress_screen<true>(kbox[k], karea[k], cbx, ca)) pk = k;
+                    }
+                    for (int c = c_lo + kMaxCls; c <= c_hi; ++c) {  // thresholds below 0.6: more classes
                         const int lo = sm->sstart[c * kXBins + x_lo], hi = sm->sstart[c * kXBins + x_hi + 1];
-#pragma unroll 4
                         for (int k = lo + sub; k < hi; k += kSub)
                             if (suppress_screen<true>(kbox[k], karea[k], cbx, ca)) pk = k;
                     }
