@@ -1,4 +1,5 @@
-"""Developer tool: times roi_pool_forward (with argmax) at the config-3 shape; FRR_ROI_VARIANT selects the inner loop."""
+"""Developer tool: times roi_pool_forward (with / without argmax) at the config-3 shape on RPN-sized and small rois,
+and prints the per-phase cycles of CTA (0,0)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -26,7 +27,7 @@ def t(fn, reps=20):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps * 1e3
 out0 = ops.roi_pool_forward(feats[0], rois5)
-print("variant", os.environ.get("FRR_ROI_VARIANT", "0"),
+print(
       "rpn-rois us", round(t(lambda i: ops.roi_pool_forward(feats[i % 3], rois5)), 1),
       "small-rois us", round(t(lambda i: ops.roi_pool_forward(feats[i % 3], small)), 1),
       "noarg us", round(t(lambda i: ops.roi_pool_forward(feats[i % 3], rois5, want_argmax=False)), 1),
