@@ -114,7 +114,8 @@ class ProposalPlan:
         self.run(cls, reg)                                    # warm-up outside the capture (function attributes, tables)
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        # thread_local: CUDA calls of other threads (e.g. NCCL's watchdog under torchrun) must not invalidate the capture
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             self.run(cls, reg)
         return graph
 
