@@ -227,8 +227,9 @@ int topk_radix_launch(const float* scores, const uint8_t* valid, const float* bo
 
 }  // namespace frr
 
-// Profiling variant: dbg = int64[8] accumulating clock64() cycles of CTA 0 per phase of the radix kernel
-// (0 load+validity, 1 select, 2 compaction, 3 sort, 4 write-out).  Returns FRR_E_UNSUPPORTED outside the fast path.
+// Profiling variant: dbg = int64[16] accumulating clock64() cycles of CTA 0 per phase: [0..4] radix kernel (load+validity,
+// select, compaction, sort, write-out; only when image 0 was handed over), [8..13] bucket kernel (load + min/max,
+// histogram, scan, scatter, bucket sorts, write-out).  Returns FRR_E_UNSUPPORTED outside the fast path.
 extern "C" int frr_topk_desc_profile(const float* scores, const uint8_t* valid, const float* boxes, int B, int N, int k,
                                      float* out_scores, int32_t* out_idx, int32_t* out_cidx, float* out_boxes,
                                      int32_t* out_count, int64_t* dbg_cycles, frr_stream_t stream) {

@@ -397,15 +397,15 @@ __global__ void __launch_bounds__(kRsThreads, 1)
 
 // ------------------------------------------------------------------------------------------------
 // Bucket version (default): ONE histogram pass replaces both the 4-pass radix select and the 6-pass LSD sort.
-//   The valid scores are mapped monotonically onto 4096 buckets, bucket(s) = floor((smax - s) * 4096 / (smax - smin))
+//   The valid scores are mapped monotonically onto 8192 buckets, bucket(s) = floor((smax - s) * 8192 / (smax - smin))
 //   (float arithmetic is monotone under rounding, so a higher score never lands in a later bucket; RPN scores are
-//   sigmoid outputs, nearly uniform in value, ~5 per bucket).  A shared-memory histogram + one block scan give the
+//   sigmoid outputs, nearly uniform in value, ~2.6 per bucket).  A shared-memory histogram + one block scan give the
 //   bucket b* in which the k-th largest score lies; the (key, index) pairs of buckets <= b* are scattered to their
 //   bucket ranges (unordered, atomic cursors) and every bucket is insertion-sorted by one thread on the EXACT total
 //   order (ordered key descending, index ascending) -- the same order the radix kernel produces, so ties and the cut
 //   inside b* are bit-identical.  Inputs that do not bucket well (non-finite range, a bucket of > kBucketMax, more than
 //   `cap` stored pairs: e.g. all scores equal) are handed to the radix kernel through out_count = -1.
-constexpr int kBuckets = 4096;
+constexpr int kBuckets = 8192;
 constexpr int kBucketMax = 192;
 constexpr int kBucketSlack = 1024;  // pairs stored beyond k (the rest of bucket b*)
 
@@ -421,14 +421,22 @@ __global__ void __launch_bounds__(kRsThreads, 1)
     topk_bucket_kernel(const float* __restrict__ scores, const uint8_t* __restrict__ valid,
                        const float4* __restrict__ boxes, int N, int k, int cap, int nchunks,
                        float* __restrict__ out_scores, int32_t* __restrict__ out_idx, int32_t* __restrict__ out_cidx,
-                       float4* __restrict__ out_boxes, int32_t* __restrict__ out_count) {
+                       float4* __restrict__ out_boxes, int32_t* __restrict__ out_count, long long* __restrict__ dbg) {
     extern __shared__ __align__(16) unsigned char smem[];
+    const bool prof = (dbg != nullptr) && blockIdx.x == 0 && threadIdx.x == 0;
+    long long t0 = prof ? clock64() : 0;
+#define BK_TICK(slot)                   \
+    if (prof) {                         \
+        const long long t1 = clock64(); \
+        dbg[slot] += t1 - t0;           \
+        t0 = t1;                        \
+    }
     BkHdr* hd = reinterpret_cast<BkHdr*>(smem);
     size_t o = up16(sizeof(BkHdr));
     unsigned int* vbits = reinterpret_cast<unsigned int*>(smem + o); o += 4 * (size_t)nchunks;
     unsigned int* vpre = reinterpret_cast<unsigned int*>(smem + o);  o = up16(o + 4 * (size_t)nchunks);
     unsigned int* hist = reinterpret_cast<unsigned int*>(smem + o);  o += 4 * (size_t)kBuckets;
-    unsigned int* start = reinterpret_cast<unsigned int*>(smem + o); o = up16(o + 4 * (size_t)(kBuckets + 1));
+    unsigned short* start = reinterpret_cast<unsigned short*>(smem + o); o = up16(o + 2 * (size_t)(kBuckets + 1));
     float* sval = reinterpret_cast<float*>(smem + o);                o = up16(o + (kStaged ? 4 * (size_t)N : 0));
     unsigned int* keyA = reinterpret_cast<unsigned int*>(smem + o);  o += 4 * (size_t)cap;
     unsigned short* idxA = reinterpret_cast<unsigned short*>(smem + o);
@@ -441,17 +449,18 @@ __global__ void __launch_bounds__(kRsThreads, 1)
     // ---- 0. validity words, staged scores, min / max of the valid scores, zeroed histogram ---------------
     float lmin = 3.0e38f, lmax = -3.0e38f;
     bool lbad = false;
-    for (int c0 = warp; c0 < nchunks; c0 += 4 * kRsWarps) {  // 4 chunks per trip: 8 independent loads in flight
-        uint8_t v4[4];
-        float s4[4];
+    constexpr int kLd = 4;  // chunks per trip: 8 independent loads in flight per thread (16 measured slower)
+    for (int c0 = warp; c0 < nchunks; c0 += kLd * kRsWarps) {
+        uint8_t v4[kLd];
+        float s4[kLd];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < kLd; ++j) {
             const int i = (c0 + j * kRsWarps) * 32 + lane;
             v4[j] = (i < N && va) ? va[i] : (uint8_t)1;
             s4[j] = (i < N) ? sc[i] : 0.f;
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < kLd; ++j) {
             const int c = c0 + j * kRsWarps;
             const int i = c * 32 + lane;
             const bool ok = (i < N) && (v4[j] != 0);
@@ -501,6 +510,7 @@ __global__ void __launch_bounds__(kRsThreads, 1)
         if (tid == 0) hd->nvalid = run;
     }
     __syncthreads();
+    BK_TICK(0);
     const int keff = min(k, (int)hd->nvalid);
     const float smax = hd->smax;
     const float scale = (float)kBuckets / (smax - hd->smin);
@@ -515,24 +525,27 @@ __global__ void __launch_bounds__(kRsThreads, 1)
             if ((vbits[c] >> lane) & 1u) atomicAdd(&hist[bucket_of(score_at(i))], 1u);
         }
         __syncthreads();
+        BK_TICK(1);
         // ---- 2. bucket starts, the bucket b* of the k-th largest score, the largest bucket up to b* ----------
         {
-            unsigned int h4[4], t4 = 0;
+            constexpr int kPerT = kBuckets / kRsThreads;
+            unsigned int h4[kPerT], t4 = 0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { h4[q] = hist[4 * tid + q]; t4 += h4[q]; }
+            for (int q = 0; q < kPerT; ++q) { h4[q] = hist[kPerT * tid + q]; t4 += h4[q]; }
             unsigned int tot;
             unsigned int run = block_exclusive_scan(t4, hd->warp_tmp, &tot);
             unsigned int big = 0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                start[4 * tid + q] = run;
+            for (int q = 0; q < kPerT; ++q) {
+                // only the buckets up to b* are ever looked at: positions beyond 65535 (N > 65535 never gets here) are moot
+                start[kPerT * tid + q] = (unsigned short)min(run, 65535u);
                 if (run < (unsigned int)keff) {
                     big = max(big, h4[q]);
-                    if (run + h4[q] >= (unsigned int)keff) { hd->bstar = 4 * tid + q; hd->stored = run + h4[q]; }
+                    if (run + h4[q] >= (unsigned int)keff) { hd->bstar = kPerT * tid + q; hd->stored = run + h4[q]; }
                 }
                 run += h4[q];
             }
-            if (tid == kRsThreads - 1) start[kBuckets] = run;
+            if (tid == kRsThreads - 1) start[kBuckets] = (unsigned short)min(run, 65535u);
             big = __reduce_max_sync(0xffffffffu, big);
             __syncthreads();
             if (lane == 0) hd->red[warp] = big;
@@ -546,6 +559,7 @@ __global__ void __launch_bounds__(kRsThreads, 1)
             handover = hd->bad != 0u;
         }
     }
+    BK_TICK(2);
     if (handover) {
         if (tid == 0) out_count[b] = -1;
         return;
@@ -567,6 +581,7 @@ __global__ void __launch_bounds__(kRsThreads, 1)
             }
         }
         __syncthreads();
+        BK_TICK(3);
         // ---- 4. every bucket sorted by one thread: ordered key descending, index ascending --------------------
         for (int bk = tid; bk <= bstar; bk += kRsThreads) {
             const int s0 = (int)start[bk], s1 = (int)start[bk + 1];
@@ -587,6 +602,7 @@ __global__ void __launch_bounds__(kRsThreads, 1)
             }
         }
         __syncthreads();
+        BK_TICK(4);
     }
     // ---- 5. write-out (4 independent gathers in flight per thread) ------------------------------------------
     for (int j0 = tid; j0 < k; j0 += 4 * kRsThreads) {
@@ -617,12 +633,16 @@ __global__ void __launch_bounds__(kRsThreads, 1)
             if (out_boxes) out_boxes[oo] = bx[u];
         }
     }
+    __syncthreads();
+    BK_TICK(5);
+#undef BK_TICK
 }
 
 static size_t bucket_smem(int N, int cap, int nchunks, bool staged) {
     size_t o = up16(sizeof(BkHdr));
     o = up16(o + 8 * (size_t)nchunks);
-    o = up16(o + 4 * (size_t)kBuckets + 4 * (size_t)(kBuckets + 1));
+    o = up16(o + 4 * (size_t)kBuckets);
+    o = up16(o + 2 * (size_t)(kBuckets + 1));
     o = up16(o + (staged ? 4 * (size_t)N : 0));
     return up16(o + 6 * (size_t)cap);
 }
@@ -642,17 +662,18 @@ int topk_radix_launch(const float* scores, const uint8_t* valid, const float* bo
     if (L.total > limit) return 1;
     auto kern = L.staged ? topk_radix_kernel<true> : topk_radix_kernel<false>;
     FRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
-    // bucket kernel first (unless the per-phase profile of the radix kernel is asked for); the radix kernel then redoes
+    // bucket kernel first; the radix kernel then redoes
     // only the images the bucket kernel handed over (all of its CTAs exit at once in the common case)
     const int cap = kcap + kBucketSlack;
     const bool bstaged = bucket_smem(N, cap, nchunks, true) <= limit;
     const size_t bsm = bucket_smem(N, cap, nchunks, bstaged);
-    const bool bucket = dbg == nullptr && bsm <= limit;
+    const bool bucket = bsm <= limit;
     if (bucket) {
         auto bkern = bstaged ? topk_bucket_kernel<true> : topk_bucket_kernel<false>;
         FRR_CUDA(cudaFuncSetAttribute(bkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
         bkern<<<B, kRsThreads, bsm, (cudaStream_t)stream>>>(scores, valid, (const float4*)boxes, N, k, cap, nchunks, out_scores,
-                                                             out_idx, out_cidx, (float4*)out_boxes, out_count);
+                                                             out_idx, out_cidx, (float4*)out_boxes, out_count,
+                                                             dbg ? dbg + 8 : nullptr);
         count_launch();
         FRR_CHECK_LAUNCH("topk_bucket_kernel");
     }

@@ -78,8 +78,9 @@ int frr_topk_desc(const float* scores /* [B,N] */, const uint8_t* valid /* [B,N]
                   float* out_scores /* [B,k] or NULL */, int32_t* out_idx /* [B,k] */,
                   int32_t* out_cidx /* [B,k] or NULL */, float* out_boxes /* [B,k,4] or NULL */,
                   int32_t* out_count /* [B] */, frr_stream_t stream);
-/* Profiling variant of the shared-memory radix path: dbg_cycles = int64[8] accumulating clock64() cycles of
- * CTA 0 per phase (0 load+validity, 1 select, 2 compaction, 3 sort, 4 write-out). */
+/* Profiling variant: dbg_cycles = int64[16] accumulating clock64() cycles of CTA 0 per phase: [0..4] radix kernel
+ * (load+validity, select, compaction, sort, write-out; only when image 0 was handed over), [8..13] bucket kernel
+ * (load + min/max, histogram, scan, scatter, bucket sorts, write-out). */
 int frr_topk_desc_profile(const float* scores, const uint8_t* valid, const float* boxes, int B, int N, int k,
                           float* out_scores, int32_t* out_idx, int32_t* out_cidx, float* out_boxes,
                           int32_t* out_count, int64_t* dbg_cycles, frr_stream_t stream);

@@ -13,12 +13,12 @@ sc = torch.from_numpy(np.stack([x[2] for x in ins])).to(dev)
 boxes, scores, valid = ops.rpn_decode(reg, sc, image_hw=HW)
 lib = _lib.load()
 N = scores.shape[1]
-names = ["load", "select", "compact", "sort", "write"]
+names = ["r_load", "r_select", "r_compact", "r_sort", "r_write", "-", "-", "-", "load", "hist", "scan", "scatter", "sort", "write"]
 for k in (12000, 6000):
     oi = torch.empty((B, k), dtype=torch.int32, device=dev)
     ob = torch.empty((B, k, 4), dtype=torch.float32, device=dev)
     oc = torch.empty((B,), dtype=torch.int32, device=dev)
-    d = torch.zeros(8, dtype=torch.int64, device=dev)
+    d = torch.zeros(16, dtype=torch.int64, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     def run(dbg):
         _lib.check(lib.frr_topk_desc_profile(scores.data_ptr(), valid.data_ptr(), boxes.data_ptr(), B, N, k, None, oi.data_ptr(),
@@ -34,5 +34,5 @@ for k in (12000, 6000):
     e1.record()
     torch.cuda.synchronize()
     out = {"k": k, "B": B, "us": round(e0.elapsed_time(e1) / 20 * 1e3, 1)}
-    out.update({n: int(v) // 20 for n, v in zip(names, d.cpu().tolist())})
+    out.update({n: int(v) // 20 for n, v in zip(names, d.cpu().tolist()) if n != "-"})
     print(json.dumps(out), flush=True)
