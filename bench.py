@@ -383,7 +383,7 @@ def run_ours(args):
                     "serialized_value": world * B * e2e_steps / (ms_e2e_serial * 1e-3)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            # dominant kernel by time is the NMS keep-list kernel: ALU/FP32 issue-bound, not HBM- or tensor-bound
+            # dominant kernel by time is the NMS keep-list kernel: latency / issue bound, not HBM- or tensor-bound
             # (see DESIGN.md); its HBM traffic is ~0.2 MB/image.  The HBM roofline entry is the decode kernel.
             "roofline": {"kernel": "rpn_decode_kernel", "bound": "hbm", "achieved": dec_bytes / (ms_dec * 1e-3) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": dec_bytes / (ms_dec * 1e-3) / 1e9 / peak,
@@ -391,7 +391,7 @@ def run_ours(args):
                          "traffic_note": "ncu dram read+write of one launch; below the algorithmic bytes because the "
                                          "28 MB of outputs stay in the 126 MB L2 for the top-k / NMS kernels"},
             "dominant_kernel": {"kernel": "nms_keeplist_kernel", "share_of_step": ms_nms / (ms / args.steps),
-                                "bound": "ALU-pipe issue (pair screening), not HBM or tensor: see profiles/ and DESIGN.md"},
+                                "bound": "latency of the per-chunk phase chain + issue of the pair screen (not HBM or tensor): see profiles/ and DESIGN.md 4.3"},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))
