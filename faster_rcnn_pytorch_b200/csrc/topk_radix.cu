@@ -72,16 +72,15 @@ __device__ __forceinline__ unsigned int match_digit8(unsigned int d, bool act) {
     return m;
 }
 
+// The whole radix top-k of image blockIdx.x in the CTA's dynamic shared memory: the body of topk_radix_kernel, and the
+// path topk_bucket_kernel falls into for inputs that do not bucket.
 template <bool kStaged>
-__global__ void __launch_bounds__(kRsThreads, 1)
-    topk_radix_kernel(const float* __restrict__ scores, const uint8_t* __restrict__ valid,
-                      const float4* __restrict__ boxes, int N, int k, int kcap, int nchunks, RsLayout L,
-                      float* __restrict__ out_scores, int32_t* __restrict__ out_idx, int32_t* __restrict__ out_cidx,
-                      float4* __restrict__ out_boxes, int32_t* __restrict__ out_count, long long* __restrict__ dbg,
-                      int only_flagged) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    // second launch behind topk_bucket_kernel: only the images it handed over (out_count == -1) are redone here
-    if (only_flagged && out_count[blockIdx.x] != -1) return;
+__device__ __forceinline__ void topk_radix_body(unsigned char* smem, const float* __restrict__ scores,
+                                                const uint8_t* __restrict__ valid, const float4* __restrict__ boxes, int N,
+                                                int k, int kcap, int nchunks, const RsLayout& L,
+                                                float* __restrict__ out_scores, int32_t* __restrict__ out_idx,
+                                                int32_t* __restrict__ out_cidx, float4* __restrict__ out_boxes,
+                                                int32_t* __restrict__ out_count, long long* __restrict__ dbg) {
     const bool prof = (dbg != nullptr) && blockIdx.x == 0 && threadIdx.x == 0;
     long long t0 = prof ? clock64() : 0;
 #define RS_TICK(slot)                   \
@@ -395,6 +394,17 @@ __global__ void __launch_bounds__(kRsThreads, 1)
 #undef RS_TICK
 }
 
+template <bool kStaged>
+__global__ void __launch_bounds__(kRsThreads, 1)
+    topk_radix_kernel(const float* __restrict__ scores, const uint8_t* __restrict__ valid,
+                      const float4* __restrict__ boxes, int N, int k, int kcap, int nchunks, RsLayout L,
+                      float* __restrict__ out_scores, int32_t* __restrict__ out_idx, int32_t* __restrict__ out_cidx,
+                      float4* __restrict__ out_boxes, int32_t* __restrict__ out_count, long long* __restrict__ dbg) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    topk_radix_body<kStaged>(smem, scores, valid, boxes, N, k, kcap, nchunks, L, out_scores, out_idx, out_cidx, out_boxes,
+                             out_count, dbg);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Bucket version (default): ONE histogram pass replaces both the 4-pass radix select and the 6-pass LSD sort.
 //   The valid scores are mapped monotonically onto 8192 buckets, bucket(s) = floor((smax - s) * 8192 / (smax - smin))
@@ -421,7 +431,8 @@ __global__ void __launch_bounds__(kRsThreads, 1)
     topk_bucket_kernel(const float* __restrict__ scores, const uint8_t* __restrict__ valid,
                        const float4* __restrict__ boxes, int N, int k, int cap, int nchunks,
                        float* __restrict__ out_scores, int32_t* __restrict__ out_idx, int32_t* __restrict__ out_cidx,
-                       float4* __restrict__ out_boxes, int32_t* __restrict__ out_count, long long* __restrict__ dbg) {
+                       float4* __restrict__ out_boxes, int32_t* __restrict__ out_count, long long* __restrict__ dbg,
+                       RsLayout L, int kcap) {
     extern __shared__ __align__(16) unsigned char smem[];
     const bool prof = (dbg != nullptr) && blockIdx.x == 0 && threadIdx.x == 0;
     long long t0 = prof ? clock64() : 0;
@@ -560,8 +571,12 @@ __global__ void __launch_bounds__(kRsThreads, 1)
         }
     }
     BK_TICK(2);
-    if (handover) {
-        if (tid == 0) out_count[b] = -1;
+    if (handover) {  // block-uniform: the radix path redoes this image from scratch in the same shared memory
+        __syncthreads();
+        if (L.staged) topk_radix_body<true>(smem, scores, valid, boxes, N, k, kcap, nchunks, L, out_scores, out_idx, out_cidx,
+                                            out_boxes, out_count, dbg ? dbg - 8 : nullptr);
+        else topk_radix_body<false>(smem, scores, valid, boxes, N, k, kcap, nchunks, L, out_scores, out_idx, out_cidx,
+                                    out_boxes, out_count, dbg ? dbg - 8 : nullptr);
         return;
     }
     if (tid == 0) out_count[b] = keff;
@@ -660,26 +675,25 @@ int topk_radix_launch(const float* scores, const uint8_t* valid, const float* bo
     if (L.total > limit) L = rs_layout(N, kcap, nchunks, false, 5);
     if (L.total > limit) L = rs_layout(N, kcap, nchunks, false, 4);
     if (L.total > limit) return 1;
-    auto kern = L.staged ? topk_radix_kernel<true> : topk_radix_kernel<false>;
-    FRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
-    // bucket kernel first; the radix kernel then redoes
-    // only the images the bucket kernel handed over (all of its CTAs exit at once in the common case)
+    // bucket kernel (with the radix path compiled in as its hand-over) when its shared memory fits, else the radix
+    // kernel alone
     const int cap = kcap + kBucketSlack;
     const bool bstaged = bucket_smem(N, cap, nchunks, true) <= limit;
     const size_t bsm = bucket_smem(N, cap, nchunks, bstaged);
-    const bool bucket = bsm <= limit;
-    if (bucket) {
+    if (bsm <= limit) {
         auto bkern = bstaged ? topk_bucket_kernel<true> : topk_bucket_kernel<false>;
         FRR_CUDA(cudaFuncSetAttribute(bkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
-        bkern<<<B, kRsThreads, bsm, (cudaStream_t)stream>>>(scores, valid, (const float4*)boxes, N, k, cap, nchunks, out_scores,
-                                                             out_idx, out_cidx, (float4*)out_boxes, out_count,
-                                                             dbg ? dbg + 8 : nullptr);
+        bkern<<<B, kRsThreads, bsm > L.total ? bsm : L.total, (cudaStream_t)stream>>>(
+            scores, valid, (const float4*)boxes, N, k, cap, nchunks, out_scores, out_idx, out_cidx, (float4*)out_boxes,
+            out_count, dbg ? dbg + 8 : nullptr, L, kcap);
         count_launch();
         FRR_CHECK_LAUNCH("topk_bucket_kernel");
+        return FRR_OK;
     }
+    auto kern = L.staged ? topk_radix_kernel<true> : topk_radix_kernel<false>;
+    FRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
     kern<<<B, kRsThreads, L.total, (cudaStream_t)stream>>>(scores, valid, (const float4*)boxes, N, k, kcap, nchunks, L,
-                                                            out_scores, out_idx, out_cidx, (float4*)out_boxes, out_count, dbg,
-                                                            bucket ? 1 : 0);
+                                                            out_scores, out_idx, out_cidx, (float4*)out_boxes, out_count, dbg);
     count_launch();
     FRR_CHECK_LAUNCH("topk_radix_kernel");
     return FRR_OK;
