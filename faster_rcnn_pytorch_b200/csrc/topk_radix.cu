@@ -597,56 +597,40 @@ __global__ void __launch_bounds__(kRsThreads, 1)
         }
         __syncthreads();
         BK_TICK(3);
-        // ---- 4. every bucket sorted by one thread: ordered key descending, index ascending --------------------
-        for (int bk = tid; bk <= bstar; bk += kRsThreads) {
+        BK_TICK(4);
+        // ---- 4. rank and write: every stored pair counts the pairs of ITS bucket that precede it in the exact total order
+        //         (ordered key descending, index ascending); start[bucket] + that count is its final rank, and it goes
+        //         straight to the output row -- no sorted copy in shared memory, no separate write-out pass.  One thread
+        //         per pair: ~2.6 pairs per bucket, so the loops are a few iterations long and every lane is busy (a
+        //         thread sorting whole buckets left the warp waiting for its largest bucket: 19 k of 59 k cycles).
+        const int stored = (int)hd->stored;
+        for (int p2 = tid; p2 < stored; p2 += kRsThreads) {
+            const unsigned int ku = keyA[p2];
+            const unsigned int ki = idxA[p2];
+            const int bk = bucket_of(ordered_to_float(ku));
             const int s0 = (int)start[bk], s1 = (int)start[bk + 1];
-            for (int a = s0 + 1; a < s1; ++a) {
-                const unsigned int ku = keyA[a];
-                const unsigned short ki = idxA[a];
-                int p2 = a - 1;
-                while (p2 >= s0) {
-                    const unsigned int kp = keyA[p2];
-                    const unsigned short ip = idxA[p2];
-                    if (kp > ku || (kp == ku && ip < ki)) break;
-                    keyA[p2 + 1] = kp;
-                    idxA[p2 + 1] = ip;
-                    --p2;
-                }
-                keyA[p2 + 1] = ku;
-                idxA[p2 + 1] = ki;
+            int rank = s0;
+            for (int a = s0; a < s1; ++a) {
+                const unsigned int ka = keyA[a];
+                rank += (ka > ku || (ka == ku && (unsigned int)idxA[a] < ki)) ? 1 : 0;
+            }
+            if (rank < keff) {
+                const size_t oo = (size_t)b * k + rank;
+                const int i = (int)ki;
+                out_idx[oo] = i;
+                if (out_scores) out_scores[oo] = ordered_to_float(ku);
+                if (out_cidx) out_cidx[oo] = (int)(vpre[i >> 5] + __popc(vbits[i >> 5] & ((1u << (i & 31)) - 1u)));
+                if (out_boxes) out_boxes[oo] = boxes[(size_t)b * N + i];
             }
         }
-        __syncthreads();
-        BK_TICK(4);
     }
-    // ---- 5. write-out (4 independent gathers in flight per thread) ------------------------------------------
-    for (int j0 = tid; j0 < k; j0 += 4 * kRsThreads) {
-        int ii[4];
-        unsigned int kk[4];
-        float4 bx[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int j = j0 + u * kRsThreads;
-            ii[u] = -1;
-            kk[u] = 0u;
-            if (j < keff) { kk[u] = keyA[j]; ii[u] = (int)idxA[j]; }
-        }
-        if (out_boxes) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                bx[u] = ii[u] >= 0 ? boxes[(size_t)b * N + ii[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int j = j0 + u * kRsThreads;
-            if (j >= k) continue;
-            const size_t oo = (size_t)b * k + j;
-            const int i = ii[u];
-            if (out_scores) out_scores[oo] = i >= 0 ? ordered_to_float(kk[u]) : __uint_as_float(0xff800000u);  // -inf pad
-            out_idx[oo] = i;
-            if (out_cidx) out_cidx[oo] = i >= 0 ? (int)(vpre[i >> 5] + __popc(vbits[i >> 5] & ((1u << (i & 31)) - 1u))) : -1;
-            if (out_boxes) out_boxes[oo] = bx[u];
-        }
+    // ---- 5. padding past the count ----------------------------------------------------------------------
+    for (int j2 = keff + tid; j2 < k; j2 += kRsThreads) {
+        const size_t oo = (size_t)b * k + j2;
+        out_idx[oo] = -1;
+        if (out_scores) out_scores[oo] = __uint_as_float(0xff800000u);  // -inf
+        if (out_cidx) out_cidx[oo] = -1;
+        if (out_boxes) out_boxes[oo] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
     BK_TICK(5);
