@@ -9,6 +9,9 @@ python bench.py > $O/${R}_bench_rpn.json 2> $O/${R}_bench_rpn.err || exit 1
 python bench.py --workload train > $O/${R}_bench_train.json 2> $O/${R}_bench_train.err || exit 1
 python bench.py --workload infer > $O/${R}_bench_infer.json 2> $O/${R}_bench_infer.err || exit 1
 python tools/stage_profile.py > $O/${R}_stage_profile.log 2>&1
+python tools/nms_profile.py > $O/${R}_nms_phases.log 2>&1
+python tools/topk_profile.py > $O/${R}_topk_phases.log 2>&1
+python tools/msroialign_profile.py > $O/${R}_msroialign.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${R}_bench_launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu > $O/ncu1.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"nms_keeplist|rpn_decode|topk_bucket" -s 12 -c 3 \
