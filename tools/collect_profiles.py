@@ -17,7 +17,7 @@ for name in (f"{R}_bench_launches.csv", f"{R}_stage_profile.log", f"{R}_nms_phas
 open(os.path.join(P, f"{R}_bench_launches_summary.txt"), "w").write(
     run(sys.executable, os.path.join(REPO, "tools", "launch_summary.py"), os.path.join(G, f"{R}_bench_launches.csv")))
 lines = []
-for w in ("rpn", "train", "infer"):
+for w in ("rpn", "train", "infer", "joint", "rpn_n2", "rpn_n8"):   # the multi-GPU lines come from separate gpurun --gpus N calls
     f = os.path.join(G, f"{R}_bench_{w}.json")
     if os.path.exists(f):
         lines.append(open(f).read().strip())
