@@ -613,7 +613,9 @@ int nms_launch(const float* boxes, const int32_t* counts, int B, int n, double i
         while (S * 2 <= per && S < 16) S *= 2;
     }
     FRR_CHECK_ARG(S == 1 || S == 2 || S == 4 || S == 8 || S == 16, "frr_nms_sorted: cluster_size %d not in {1,2,4,8,16}", S);
-    if (threads == 0) threads = 1024;
+    // a CTA whose slice of the kept list is short (one image spread over 16 CTAs) is bound by its per-chunk barriers:
+    // 16 warps resolve them faster than 32 (130 vs 134 us for 12000 -> 2000 boxes)
+    if (threads == 0) threads = (kcap / S < 192) ? 512 : 1024;
     if (threads < kChunk) threads = kChunk;  // the first kChunk threads own one candidate each
     // grow the cluster until a slice of the kept list fits in shared memory
     const NmsThr thr = make_thr(iou_thr);
