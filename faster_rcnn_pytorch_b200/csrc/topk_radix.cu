@@ -1,6 +1,8 @@
 // P4 (fast path): pre-NMS top-k, sorted descending, ties lower-index-first (models/model.py:44-49).
+// Two algorithms in one launch: topk_bucket_kernel (below, the default) and the radix path described here, which it falls
+// into for inputs that do not bucket and which also runs alone when the bucket kernel's shared memory does not fit.
 //
-// One CTA (1024 threads) per image, everything after the first read of the scores stays in shared memory:
+// Radix path: one CTA (1024 threads) per image, everything after the first read of the scores stays in shared memory:
 //   0. validity words (ballot) + the order-preserving uint32 keys of all N scores staged in shared memory;
 //   1. MSB-first radix select (4 x 8-bit digits, warp-aggregated histogram atomics) -> T = k-th largest key
 //      and how many keys == T to take;

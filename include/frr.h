@@ -68,8 +68,9 @@ int frr_rpn_decode(const float* reg /* [B,N,4] */, const float* cls /* [B,N,2] l
                    frr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
- * P4  pre-NMS top-k, sorted descending -- models/model.py:44-49.  Radix select + in-smem
- *     sort, one CTA per image.  Ties: lower index first.  Entries past count[b] are padded
+ * P4  pre-NMS top-k, sorted descending -- models/model.py:44-49.  One CTA per image, in shared
+ *     memory: monotone bucketing of the scores + exact ranking inside the buckets (radix select + radix
+ *     sort for inputs that do not bucket).  Ties: lower index first.  Entries past count[b] are padded
  *     (idx -1, score -inf, box 0).  out_cidx = index into the min-size-compacted array (what
  *     the reference's sort returns), out_idx = index into the full N.  k <= 16384.
  * ------------------------------------------------------------------------------------- */
@@ -80,7 +81,7 @@ int frr_topk_desc(const float* scores /* [B,N] */, const uint8_t* valid /* [B,N]
                   int32_t* out_count /* [B] */, frr_stream_t stream);
 /* Profiling variant: dbg_cycles = int64[16] accumulating clock64() cycles of CTA 0 per phase: [0..4] radix kernel
  * (load+validity, select, compaction, sort, write-out; only when image 0 was handed over), [8..13] bucket kernel
- * (load + min/max, histogram, scan, scatter, bucket sorts, write-out). */
+ * (load + min/max, histogram, scan, scatter, -, rank + write-out). */
 int frr_topk_desc_profile(const float* scores, const uint8_t* valid, const float* boxes, int B, int N, int k,
                           float* out_scores, int32_t* out_idx, int32_t* out_cidx, float* out_boxes,
                           int32_t* out_count, int64_t* dbg_cycles, frr_stream_t stream);
