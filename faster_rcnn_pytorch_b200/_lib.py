@@ -33,6 +33,8 @@ SIGNATURES = {
     "frr_nms_sorted": (_i, [_p, _p, _i, _i, _d, _i, _p, _p, _p, _i, _p]),
     "frr_rpn_proposals_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i]),
     "frr_rpn_proposals": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _i, _f, _i, _i, _i, _i, _d, _p, _p, _p, C.c_size_t, _p]),
+    "frr_nms_variant": (_i, [_i, _i, _d, _i, _i, _i, _i, _p]),
+    "frr_rpn_proposals_workspace_layout": (_i, [_i, _i, _i, _i, _p]),
     "frr_nms_sorted_indirect": (_i, [_p, _i, _p, _p, _i, _i, _d, _i, _p, _p, _p, _i, _i, _p]),
     "frr_roi_pool_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p, _p]),
     "frr_roi_pool_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p]),
@@ -77,6 +79,9 @@ def load():
             raise FrrError(
                 f"{LIB_PATH} is missing: build it with `python -m faster_rcnn_pytorch_b200.build` "
                 "(there is no CPU fallback for the region stage)")
+        # libfrr.so links the CUDA runtime dynamically (no second, static copy inside the library): torch has already
+        # loaded its libcudart.so.12 into the process, and the loader resolves the NEEDED entry to that copy
+        import torch  # noqa: F401
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)

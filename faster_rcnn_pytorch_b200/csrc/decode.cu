@@ -34,8 +34,11 @@ __global__ void __launch_bounds__(256) anchors_kernel(float4* __restrict__ out, 
 // issued back to back (memory-level parallelism) before any arithmetic.
 //   score = 1 / (1 + exp(l0 - l1))           (== softmax(l)[1]; one ex2 + one reciprocal)
 //   box   = sat(c -/+ exp(t_wh) * a_wh / 2)  (add.sat == clamp(0,1) of the rounded sum)
-// exp() is ex2.approx(x * log2 e): <= 2 ulp + |x| * 2^-23 relative, inside the 1e-5 contract for decoded boxes
-// and scores; every index-valued stage downstream is evaluated on the fp32 values written here.
+// exp() is CUDA's accurate expf (<= 1 ulp; the kernel is HBM-bound, the extra instructions are free), well inside the
+// 1e-5 contract for decoded boxes and scores; every index-valued stage downstream is evaluated on the fp32 values
+// written here.  A NaN regression output stays out of the proposals exactly as in the reference: torch.clamp
+// propagates NaN and `NaN - y1 >= min_size` is false (models/model.py:34,39), whereas add.sat maps NaN to 0 -- so the
+// box is marked invalid when any pre-clamp coordinate is NaN.
 template <bool kLogits, bool kGenAnchors, int kImgs>
 __global__ void __launch_bounds__(256)
     rpn_decode_kernel(const float4* __restrict__ reg, const float* __restrict__ cls, const float4* __restrict__ anchors,
@@ -73,17 +76,19 @@ __global__ void __launch_bounds__(256)
         if (b0 + j < B) {
             const size_t g = (size_t)(b0 + j) * N + i;
             float s = l[j].y;
-            if (kLogits) s = __frcp_rn(__fadd_rn(1.0f, __expf(__fsub_rn(l[j].x, l[j].y))));
+            if (kLogits) s = __frcp_rn(__fadd_rn(1.0f, expf(__fsub_rn(l[j].x, l[j].y))));
             // decode: c = t_xy * a_wh + a_c ; wh/2 = exp(t_wh) * a_wh / 2 ; cxcy_to_xy ; clamp(0,1)
             const float cx = __fadd_rn(__fmul_rn(t[j].x, aw), acx), cy = __fadd_rn(__fmul_rn(t[j].y, ah), acy);
-            const float hw = __fmul_rn(__fmul_rn(__expf(t[j].z), aw), 0.5f);
-            const float hh = __fmul_rn(__fmul_rn(__expf(t[j].w), ah), 0.5f);
+            const float hw = __fmul_rn(__fmul_rn(expf(t[j].z), aw), 0.5f);
+            const float hh = __fmul_rn(__fmul_rn(expf(t[j].w), ah), 0.5f);
+            const float r0 = __fsub_rn(cx, hw), r1 = __fsub_rn(cy, hh), r2 = __fadd_rn(cx, hw), r3 = __fadd_rn(cy, hh);
             float4 bx;
-            bx.x = __saturatef(__fsub_rn(cx, hw));
-            bx.y = __saturatef(__fsub_rn(cy, hh));
-            bx.z = __saturatef(__fadd_rn(cx, hw));
-            bx.w = __saturatef(__fadd_rn(cy, hh));
-            const bool ok = (__fsub_rn(bx.w, bx.y) >= min_size) && (__fsub_rn(bx.z, bx.x) >= min_size);
+            bx.x = __saturatef(r0);
+            bx.y = __saturatef(r1);
+            bx.z = __saturatef(r2);
+            bx.w = __saturatef(r3);
+            const bool finite = (r0 == r0) && (r1 == r1) && (r2 == r2) && (r3 == r3);
+            const bool ok = finite && (__fsub_rn(bx.w, bx.y) >= min_size) && (__fsub_rn(bx.z, bx.x) >= min_size);
             st_stream(boxes + g, bx);
             scores[g] = s;
             valid[g] = ok ? 1 : 0;

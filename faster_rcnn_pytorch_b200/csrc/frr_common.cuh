@@ -41,13 +41,16 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::mem
     } while (0)
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-inline int num_sms() {
-    static int n = 0;
+inline int num_sms() {  // of the CURRENT device (cached per device id: a process may drive several GPUs)
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int slot = (dev >= 0 && dev < 64) ? dev : 0;
+    int n = cache[slot].load(std::memory_order_relaxed);
     if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
+        cache[slot].store(n, std::memory_order_relaxed);
     }
     return n;
 }

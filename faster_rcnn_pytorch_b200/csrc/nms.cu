@@ -594,16 +594,18 @@ static size_t nms_smem_bytes(int slice_cap, bool sorted) {
     return ((sizeof(NmsSmem) + 15) & ~(size_t)15) + (size_t)slice_cap * (sizeof(float4) + sizeof(float)) * (sorted ? 2 : 1);
 }
 
-int nms_launch(const float* boxes, const int32_t* counts, int B, int n, double iou_thr, int max_keep,
-                      int32_t* keep, int32_t* keep_count, float* out_boxes, int cluster_size, int threads,
-                      long long* dbg, int unit_boxes, frr_stream_t stream, const int32_t* gather_idx, int src_n) {
-    FRR_CHECK_ARG(keep && keep_count, "frr_nms_sorted: null output");
+// Launch geometry and kernel variant for a problem: shared by nms_launch and frr_nms_variant (tests / bench assert
+// through the latter that the variant they mean to exercise is the one that runs).
+struct NmsPick {
+    int S, threads, slice_cap, sorted;
+    size_t smem;
+    NmsThr thr;
+};
+
+static int nms_pick(int B, int n, double iou_thr, int max_keep, int cluster_size, int threads, int unit_boxes, NmsPick* out) {
     FRR_CHECK_ARG(B >= 0 && n >= 0 && max_keep >= 0, "frr_nms_sorted: bad sizes B=%d n=%d max_keep=%d", B, n, max_keep);
-    FRR_CHECK_ARG(n == 0 || (boxes && aligned16(boxes)), "frr_nms_sorted: boxes must be non-null, 16-byte aligned");
-    FRR_CHECK_ARG(out_boxes == nullptr || aligned16(out_boxes), "frr_nms_sorted: out_boxes must be 16-byte aligned");
     FRR_CHECK_ARG(threads == 0 || threads == 256 || threads == 512 || threads == 1024,
                   "frr_nms_sorted: threads %d not in {0,256,512,1024}", threads);
-    if (B == 0) return FRR_OK;
     const int kcap = max_keep < n ? max_keep : n;  // most boxes that can ever be kept
     int S = cluster_size;
     if (S == 0) {
@@ -617,16 +619,42 @@ int nms_launch(const float* boxes, const int32_t* counts, int B, int n, double i
     // 16 warps resolve them faster than 32 (130 vs 134 us for 12000 -> 2000 boxes)
     if (threads == 0) threads = (kcap / S < 192) ? 512 : 1024;
     if (threads < kChunk) threads = kChunk;  // the first kChunk threads own one candidate each
-    // grow the cluster until a slice of the kept list fits in shared memory
     const NmsThr thr = make_thr(iou_thr);
     // The class-sorted phase 1 pays ~10 k cycles of bucketing per chunk: it wins once a CTA's slice of the kept
     // list is large (batched launches with 1-2 CTAs per image), not for a single image spread over 16 CTAs.
     const bool sorted = thr.fast && unit_boxes && (kcap / S >= 384);
+    // grow the cluster until a slice of the kept list fits in shared memory
     const size_t limit = 227 * 1024;
     while (nms_smem_bytes((kcap + S - 1) / S + 1, sorted) > limit && S < 16) S *= 2;
     const int slice_cap = (kcap + S - 1) / S + 1;
     const size_t smem = nms_smem_bytes(slice_cap, sorted);
     FRR_CHECK_ARG(smem <= limit, "frr_nms_sorted: max_keep=%d does not fit the kept list in shared memory", max_keep);
+    out->S = S;
+    out->threads = threads;
+    out->slice_cap = slice_cap;
+    out->sorted = sorted ? 1 : 0;
+    out->smem = smem;
+    out->thr = thr;
+    return FRR_OK;
+}
+
+int nms_launch(const float* boxes, const int32_t* counts, int B, int n, double iou_thr, int max_keep,
+                      int32_t* keep, int32_t* keep_count, float* out_boxes, int cluster_size, int threads,
+                      long long* dbg, int unit_boxes, frr_stream_t stream, const int32_t* gather_idx, int src_n) {
+    FRR_CHECK_ARG(keep && keep_count, "frr_nms_sorted: null output");
+    FRR_CHECK_ARG(n == 0 || (boxes && aligned16(boxes)), "frr_nms_sorted: boxes must be non-null, 16-byte aligned");
+    FRR_CHECK_ARG(out_boxes == nullptr || aligned16(out_boxes), "frr_nms_sorted: out_boxes must be 16-byte aligned");
+    NmsPick pk;
+    {
+        const int rc = nms_pick(B, n, iou_thr, max_keep, cluster_size, threads, unit_boxes, &pk);
+        if (rc) return rc;
+    }
+    if (B == 0) return FRR_OK;
+    const int S = pk.S, slice_cap = pk.slice_cap;
+    threads = pk.threads;
+    const bool sorted = pk.sorted != 0;
+    const size_t smem = pk.smem, limit = 227 * 1024;
+    const NmsThr thr = pk.thr;
 
     using kern_t = void (*)(const float4*, const int32_t*, int, int, int, NmsThr, int32_t*, int32_t*, float4*, long long*,
                             const int32_t*, int);
@@ -675,6 +703,22 @@ extern "C" int frr_nms_sorted_tuned(const float* boxes, const int32_t* counts, i
                                     int64_t* dbg_cycles, int unit_boxes, frr_stream_t stream) {
     return frr::nms_launch(boxes, counts, B, n, iou_thr, max_keep, keep, keep_count, out_boxes, cluster_size, threads,
                            (long long*)dbg_cycles, unit_boxes, stream, nullptr, 0);
+}
+
+// Which kernel variant / launch geometry frr_nms_sorted* picks for a problem (host only, launches nothing):
+// out[0] = CTAs per image (cluster size), out[1] = threads per CTA, out[2] = variant (0 exact only, 1 screened,
+// 2 screened + unit range, 3 unit range + class / x-bin bucketed kept slice), out[3] = dynamic shared memory bytes.
+extern "C" int frr_nms_variant(int B, int n, double iou_thr, int max_keep, int cluster_size, int threads, int unit_boxes,
+                               int32_t* out4) {
+    FRR_CHECK_ARG(out4 != nullptr, "frr_nms_variant: null output");
+    frr::NmsPick pk;
+    const int rc = frr::nms_pick(B, n, iou_thr, max_keep, cluster_size, threads, unit_boxes, &pk);
+    if (rc) return rc;
+    out4[0] = pk.S;
+    out4[1] = pk.threads;
+    out4[2] = pk.sorted ? 3 : (pk.thr.fast ? (unit_boxes ? 2 : 1) : 0);
+    out4[3] = (int32_t)pk.smem;
+    return FRR_OK;
 }
 
 // Same as frr_nms_sorted_tuned, but the score order is given as indices: candidate i of image b is

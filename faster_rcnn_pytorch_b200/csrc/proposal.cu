@@ -10,7 +10,7 @@ int nms_launch(const float* boxes, const int32_t* counts, int B, int n, double i
                frr_stream_t stream, const int32_t* gather_idx = nullptr, int src_n = 0);
 
 struct ProposalWs {
-    size_t boxes, scores, valid, top_boxes, top_idx, top_count, keep, total;
+    size_t boxes, scores, valid, top_idx, top_count, keep, total;
 };
 
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -21,7 +21,6 @@ static ProposalWs proposal_ws(int B, int N, int k, int post) {
     w.boxes = o;     o += al256((size_t)B * N * 16);
     w.scores = o;    o += al256((size_t)B * N * 4);
     w.valid = o;     o += al256((size_t)B * N);
-    w.top_boxes = o; o += al256((size_t)B * k * 16);
     w.top_idx = o;   o += al256((size_t)B * k * 4);
     w.top_count = o; o += al256((size_t)B * 4);
     w.keep = o;      o += al256((size_t)B * post * 4);
@@ -37,6 +36,21 @@ size_t frr_rpn_proposals_workspace_bytes(int B, int N, int pre_nms_top_k, int po
     if (B < 0 || N < 0 || pre_nms_top_k < 0 || post_nms_top_k < 0) return 0;
     const int k = pre_nms_top_k < N ? pre_nms_top_k : N;
     return frr::proposal_ws(B, N, k, post_nms_top_k).total;
+}
+
+int frr_rpn_proposals_workspace_layout(int B, int N, int pre_nms_top_k, int post_nms_top_k, size_t* offsets6) {
+    using namespace frr;
+    FRR_CHECK_ARG(offsets6 && B >= 0 && N >= 0 && pre_nms_top_k >= 0 && post_nms_top_k >= 0,
+                  "frr_rpn_proposals_workspace_layout: bad arguments");
+    const int k = pre_nms_top_k < N ? pre_nms_top_k : N;
+    const ProposalWs w = proposal_ws(B, N, k, post_nms_top_k);
+    offsets6[0] = w.boxes;
+    offsets6[1] = w.scores;
+    offsets6[2] = w.valid;
+    offsets6[3] = w.top_idx;
+    offsets6[4] = w.top_count;
+    offsets6[5] = w.keep;
+    return FRR_OK;
 }
 
 int frr_rpn_proposals(const float* reg, const float* cls, int cls_is_logits, const float* anchors,

@@ -260,11 +260,8 @@ extern "C" int frr_topk_desc(const float* scores, const uint8_t* valid, const fl
     const int nchunks = (N + 31) / 32;
     const size_t smem = topk_smem_bytes(nchunks, P);
     FRR_CHECK_ARG(smem <= 227 * 1024, "frr_topk_desc: N=%d k=%d needs %zu B shared memory (> 227 KB)", N, k, smem);
-    static std::atomic<size_t> configured{0};
-    if (configured.load() < smem) {
-        FRR_CUDA(cudaFuncSetAttribute(topk_bitonic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured.store(227 * 1024);
-    }
+    // per device attribute: set before every launch (a process may drive several GPUs)
+    FRR_CUDA(cudaFuncSetAttribute(topk_bitonic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     topk_bitonic_kernel<<<B, kTopkThreads, smem, (cudaStream_t)stream>>>(scores, valid, (const float4*)boxes, N, k, P,
                                                                        nchunks, out_scores, out_idx, out_cidx,
                                                                        (float4*)out_boxes, out_count);

@@ -138,6 +138,21 @@ def nms_sorted(boxes, iou_threshold: float, max_keep: int | None = None, counts=
     return keep, cnt, rois
 
 
+NMS_VARIANTS = {0: "exact", 1: "screened", 2: "screened+unit", 3: "bucketed"}
+
+
+def nms_variant(B: int, n: int, iou_threshold: float, max_keep: int | None = None, cluster_size: int = 0,
+                threads: int = 0, unit_boxes: bool = False, device=None) -> dict:
+    """Kernel variant / launch geometry ``nms_sorted`` picks for this problem (host query, launches nothing)."""
+    import ctypes
+    out = (ctypes.c_int32 * 4)()
+    mk = n if max_keep is None else int(max_keep)
+    with torch.cuda.device(device if device is not None else torch.cuda.current_device()):
+        _lib.check(_lib.load().frr_nms_variant(int(B), int(n), float(iou_threshold), mk, int(cluster_size), int(threads),
+                                               int(bool(unit_boxes)), out), "frr_nms_variant")
+    return dict(cluster_size=out[0], threads=out[1], variant=NMS_VARIANTS[out[2]], smem=out[3])
+
+
 # ------------------------------------------------------------------------------------------------
 # RoIPool / RoIAlign (R1-R4): raw kernels + autograd functions
 # ------------------------------------------------------------------------------------------------

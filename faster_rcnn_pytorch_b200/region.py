@@ -107,6 +107,28 @@ class ProposalPlan:
         return rois, count
 
 
+    def intermediates(self):
+        """Views of the workspace regions the last ``run`` / graph replay left behind (no copies): decoded ``boxes``
+        [B,N,4], ``scores`` [B,N], ``valid`` u8 [B,N], ``top_idx`` int32 [B,k] (indices into N, score descending),
+        ``top_count`` int32 [B], ``keep`` int32 [B,post] (positions in the top-k order, -1 padded)."""
+        import ctypes
+        off = (ctypes.c_size_t * 6)()
+        _lib.check(self.lib.frr_rpn_proposals_workspace_layout(self.B, self.N, self.pre_k, self.post_k, off),
+                   "frr_rpn_proposals_workspace_layout")
+        base = self._ws_ptr - self._ws.data_ptr()
+        k = min(self.pre_k, self.N)
+        B, N = self.B, self.N
+
+        def view(o, nbytes, dtype, shape):
+            return self._ws[base + o: base + o + nbytes].view(dtype).view(shape)
+
+        return dict(boxes=view(off[0], B * N * 16, torch.float32, (B, N, 4)),
+                    scores=view(off[1], B * N * 4, torch.float32, (B, N)),
+                    valid=view(off[2], B * N, torch.uint8, (B, N)),
+                    top_idx=view(off[3], B * k * 4, torch.int32, (B, k)),
+                    top_count=view(off[4], B * 4, torch.int32, (B,)),
+                    keep=view(off[5], B * self.post_k * 4, torch.int32, (B, self.post_k)))
+
     def capture(self, cls, reg):
         """Capture one ``run(cls, reg)`` into a CUDA graph (the call neither allocates nor synchronises) and return the
         ``torch.cuda.CUDAGraph``; ``graph.replay()`` then re-runs the whole proposal layer on whatever ``cls`` / ``reg``

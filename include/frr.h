@@ -106,6 +106,13 @@ int frr_nms_sorted_tuned(const float* boxes, const int32_t* counts, int B, int n
                          int32_t* keep, int32_t* keep_count, float* out_boxes, int cluster_size, int threads,
                          int64_t* dbg_cycles, int unit_boxes, frr_stream_t stream);
 
+/* Which kernel variant and launch geometry the NMS entry points pick for a problem (host only, launches nothing;
+ * tests and bench.py assert through it that the variant they mean to exercise is the one that runs):
+ * out4[0] = CTAs per image, out4[1] = threads per CTA, out4[2] = variant (0 exact test only, 1 screened,
+ * 2 screened + unit range, 3 unit range + area-class / x-bin bucketed lists), out4[3] = dynamic shared memory.   */
+int frr_nms_variant(int B, int n, double iou_thr, int max_keep, int cluster_size, int threads, int unit_boxes,
+                    int32_t* out4);
+
 /* Same, with the score order given as indices into an unsorted array: candidate i of image b is
  * boxes_src[b][order[b][i]] (boxes_src [B,src_n,4]; order int32 [B,n] = out_idx of frr_topk_desc).  Only the
  * candidates NMS visits are gathered; the top-k kernel then need not write sorted boxes at all.          */
@@ -121,6 +128,10 @@ int frr_nms_sorted_indirect(const float* boxes_src, int src_n, const int32_t* or
  * frr_rpn_proposals_workspace_bytes.
  * ------------------------------------------------------------------------------------- */
 size_t frr_rpn_proposals_workspace_bytes(int B, int N, int pre_nms_top_k, int post_nms_top_k);
+/* Byte offsets of the intermediates inside that workspace (for callers / tests that inspect them after a call):
+ * offsets[0..5] = decoded boxes [B,N,4] f32, scores [B,N] f32, valid [B,N] u8, top-k order [B,k] i32 (indices into
+ * N), top-k count [B] i32, NMS keep list [B,post] i32 (positions in the top-k order, -1 padded).                */
+int frr_rpn_proposals_workspace_layout(int B, int N, int pre_nms_top_k, int post_nms_top_k, size_t* offsets6);
 int frr_rpn_proposals(const float* reg /* [B,N,4] */, const float* cls /* [B,N,2] logits or [B,N] scores */,
                       int cls_is_logits, const float* anchors /* [N,4] or NULL */, const float* base_table_host, int A,
                       int img_h, int img_w, int stride, float min_size, int B, int N, int pre_nms_top_k,

@@ -49,10 +49,73 @@ def report(name, us, nbytes=None, **kw):
     print(json.dumps(d), flush=True)
 
 
+def nms_race(flush):
+    """torchvision's sm_100 CUDA `nms` (IoU bitmask [n, n/64] + gather_keep_from_mask) against
+    frr_nms_sorted on the same score-sorted RPN boxes (models/model.py:53: 12000 -> 2000 train, 6000 -> 300 test) and
+    torchvision `batched_nms` against frr_class_nms for the 300 x 80 per-class case (models/model.py:394); also
+    where the keep lists differ (torchvision's CUDA kernel narrows the threshold to fp32 and contracts Sa + Sb)."""
+    import torchvision
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    import nms_cases
+    for tag, n, post, B in [("train_12000_2000", 12000, 2000, 64), ("test_6000_300", 6000, 300, 8)]:
+        boxes = np.stack([nms_cases.rpn_like(2000 + i, n) for i in range(B)])
+        d = torch.from_numpy(boxes).to(dev)
+        sc = torch.arange(n, 0, -1, device=dev, dtype=torch.float32)
+        tv1 = timeit(lambda: torchvision.ops.nms(d[0], sc, 0.7)[:post], flush=flush)
+        report(f"nms/{tag}/torchvision_cuda_nms_one_image", tv1, n=n)
+
+        def tv_loop():
+            return [torchvision.ops.nms(d[i], sc, 0.7)[:post] for i in range(B)]
+        tvB = timeit(tv_loop, reps=5, warm=2, flush=flush)
+        report(f"nms/{tag}/torchvision_cuda_nms_loop_over_{B}_images", tvB, per_image_us=round(tvB / B, 2))
+        idxs = torch.arange(B, device=dev).repeat_interleave(n)
+
+        def tv_batched():
+            return torchvision.ops.batched_nms(d.reshape(-1, 4), sc.repeat(B), idxs, 0.7)
+        tvb = timeit(tv_batched, reps=5, warm=2, flush=flush)
+        report(f"nms/{tag}/torchvision_cuda_batched_nms_{B}_images", tvb, per_image_us=round(tvb / B, 2))
+        one = d[:1].contiguous()
+        us1 = timeit(lambda: ops.nms_sorted(one, 0.7, max_keep=post, unit_boxes=True), flush=flush)
+        report(f"nms/{tag}/frr_nms_sorted_one_image", us1, variant=ops.nms_variant(1, n, 0.7, post, unit_boxes=True))
+        usB = timeit(lambda: ops.nms_sorted(d, 0.7, max_keep=post, unit_boxes=True), flush=flush)
+        report(f"nms/{tag}/frr_nms_sorted_{B}_images", usB, per_image_us=round(usB / B, 2),
+               variant=ops.nms_variant(B, n, 0.7, post, unit_boxes=True),
+               speedup_vs_torchvision_loop=round(tvB / usB, 1))
+        keep, cnt, _ = ops.nms_sorted(d, 0.7, max_keep=post, unit_boxes=True)
+        diff = 0
+        for i in range(B):
+            a = torchvision.ops.nms(d[i], sc, 0.7)[:post].cpu().numpy()
+            b = keep[i, :int(cnt[i])].cpu().numpy()
+            diff += int(len(a) != len(b) or not np.array_equal(a, b))
+        report(f"nms/{tag}/images_where_torchvision_cuda_keep_list_differs_from_cpu_exact", 0.0, images=B, differing=diff)
+    # per-class NMS: 8 images x 300 rois x 80 classes, thres 0.05 / IoU 0.3
+    B, R, C = 8, 300, 81
+    cls = torch.from_numpy(np.stack([synth.head_outputs(600 + i, R, C)[0] for i in range(B)])).to(dev)
+    reg = torch.from_numpy(np.stack([synth.head_outputs(600 + i, R, C)[1] for i in range(B)])).to(dev)
+    rr = torch.from_numpy(np.stack([synth.random_boxes(700 + i, R)[0] for i in range(B)])).to(dev)
+    prob, boxes = ops.decode_classwise(cls.reshape(B * R, C), reg.reshape(B * R, 4 * C), rr.reshape(B * R, 4), C)
+    prob = prob.reshape(B, R, C)
+    boxes = boxes.reshape(B, R, C, 4)
+
+    def tv_class():
+        # the reference's loop (models/model.py:386-398) collapsed into ONE batched_nms over (image, class) groups
+        m = prob[:, :, 1:] > 0.05
+        bi, ri, ci = torch.nonzero(m, as_tuple=True)
+        return torchvision.ops.batched_nms(boxes[bi, ri, ci + 1], prob[bi, ri, ci + 1], bi * C + ci, 0.3)
+    us_tv = timeit(tv_class, reps=10, flush=flush)
+    us = timeit(lambda: ops.class_nms(prob, boxes.reshape(B, R, 4 * C), C, score_thres=0.05), flush=flush)
+    report("nms/class_300x80x8/torchvision_cuda_batched_nms(mask+nonzero+gather+nms)", us_tv)
+    report("nms/class_300x80x8/frr_class_nms", us, speedup=round(us_tv / us, 1))
+
+
 def main():
     quick = "--quick" in sys.argv
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     import torchvision
+    if "--skip-nms" not in sys.argv:
+        nms_race(flush)
+    if "--only-nms" in sys.argv:
+        return
     for tag, B, C, fh, fw, per_img, real in [("cfg3_train", 16, 512, 37, 62, 128, False), ("cfg3_train_rpnrois", 16, 512, 37, 62, 128, True),
                                               ("cfg4_infer", 8, 512, 50, 83, 300, False), ("cfg4_infer_rpnrois", 8, 512, 50, 83, 300, True)]:
         K = B * per_img
