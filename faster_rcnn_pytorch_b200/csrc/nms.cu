@@ -24,7 +24,7 @@
 #include <cooperative_groups.h>
 #include <math.h>
 
-#include "frr_common.cuh"
+#include "nms_common.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -32,59 +32,8 @@ namespace frr {
 
 constexpr int kChunk = 256;  // candidates per chunk
 constexpr int kChunkWords = kChunk / 32;
-constexpr int kMaxCluster = 16;
 constexpr int kTile = 4;                // candidates per thread in phase 1
 constexpr int kGroup = kChunk / kTile;  // threads that together cover one chunk (64)
-
-struct NmsThr {
-    float up;  // smallest fp32 with (double)up > thr
-    float c2;  // up/(1+up) * (1 - 2^-19): screening constant
-    float alo, ahi;  // a box of area A can only be suppressed by boxes with area in [alo * A, ahi * A] (IoU <= min/max area)
-    float fx;        // ... and only by boxes whose x-centre is within fx * (its width) of its own
-    int fast;  // screening usable (1e-6 <= thr, finite)
-};
-
-constexpr int kStrips = 88;         // area classes of the sorted kept slice (4 per octave, 2^-22 .. 1)
-constexpr int kXBins = 8;           // x-centre bins inside an area class
-constexpr int kKeys = kStrips * kXBins;  // bucket keys; key kKeys = boxes that must always be tested
-constexpr int kKeyPer = ((kKeys + 2 + 31) / 32 + 3) & ~3;  // keys scanned per lane (a multiple of 4: uint4 accesses)
-constexpr int kKeyCap = 32 * kKeyPer;                       // padded length of the per-key arrays
-
-__device__ __forceinline__ float box_area(const float4& b) {
-    return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
-}
-// c2-scaled area used by the screen: NaN for boxes that are not well formed or tiny (forces the exact path)
-__device__ __forceinline__ float screen_area(const float4& b, float c2) {
-    const float a = box_area(b);
-    const bool ok = (b.z >= b.x) && (b.w >= b.y) && (a <= 3.0e38f) && (a >= 1.0e-30f);
-    return ok ? __fmul_rn(c2, a) : __int_as_float(0x7fc00000);
-}
-
-// The exact torchvision CPU decision for one pair (a = earlier box).  Rare path.
-__device__ __noinline__ bool suppress_exact(float4 a, float4 b, float up) {
-    const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
-    const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
-    const float inter = __fmul_rn(w, h);
-    const float uni = __fsub_rn(__fadd_rn(box_area(a), box_area(b)), inter);
-    const float ovr = __fdiv_rn(inter, uni);
-    return ovr >= up;  // false for NaN, as (double)NaN > thr
-}
-
-// Screen: returns false only when the pair is certainly NOT suppressed.
-//   exact:  ovr = RN(I / U),  U = RN(RN(Aa+Ab) - I) = (Aa+Ab-I)(1+e), |e| <= 2^-22 (I <= (Aa+Ab)/2)
-//   ovr < up  <=  I/U < up(1-2^-23)  <=  I < u'(Aa+Ab-I), u' = up(1-2^-21)  <=>  I < u'/(1+u') (Aa+Ab)
-//   screen:  T = RN(RN(c2 Aa) + RN(c2 Ab)) <= c2 (Aa+Ab)(1+2^-22), and c2 (1+2^-22) < u'/(1+u').
-// Only one of w/h is clamped: if w < 0 then I <= 0 < T (the true intersection is 0: not suppressed).
-// sa/sb are the c2-scaled areas (NaN if degenerate -> T is NaN -> the screen reports "maybe").
-// kUnit: all coordinates lie in [0,1] (RPN / detection boxes are clamped there), so |h| <= 1 and the clamp of h at 0
-// is the free .sat modifier of the subtraction (FMA pipe) instead of an FMNMX on the half-rate ALU pipe.
-template <bool kUnit>
-__device__ __forceinline__ bool suppress_screen(const float4& a, float sa, const float4& b, float sb) {
-    const float w = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
-    const float hd = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
-    const float h = kUnit ? __saturatef(hd) : fmaxf(0.f, hd);
-    return !(__fmul_rn(w, h) < __fadd_rn(sa, sb));
-}
 
 struct NmsSmem {
     unsigned int supp[2][kMaxCluster][kChunkWords];  // [parity][src rank][word]: suppressed-by-slice words
@@ -98,31 +47,7 @@ struct NmsSmem {
     float4 sbox[kChunk];  // survivor boxes (compacted)
     float sarea[kChunk];
     short ssrc[kChunk];  // survivor -> position inside the chunk
-    // sorted phase 1 (kUnit): kept slice bucketed by area class, chunk candidates ordered by area class
-    alignas(16) unsigned int shist[kKeyCap];
-    alignas(16) unsigned int scursor[kKeyCap];
-    alignas(16) unsigned int chist[kKeyCap];
-    alignas(16) unsigned int ccursor[kKeyCap];
-    alignas(16) unsigned short sstart[kKeyCap];  // sstart[s] = first sorted position of key s; [kKeys+1] = total
-    unsigned short cord[kChunk];         // chunk positions ordered by area class
 };
-
-// Bucket key of a box = (area class, x bin).
-// Area class: the top bits of the fp32 area (exponent + 2 mantissa bits = 4 classes per octave), an exactly monotone
-// integer function of the area.  IoU <= min(area) / max(area) (in fp32 as well: w <= both widths and RN is monotone, so
-// inter <= both areas), hence only kept boxes whose area lies within [thr, 1/thr] of the candidate's can suppress it: for
-// RPN proposals (three anchor scales, a factor 4 apart in area) that alone removes 3/4 of the pairs.
-// x bin: kXBins equal strips of the x-centre; IoU >= thr also needs |cx_K - cx_c| <= fx * w_c, which is sharp exactly
-// where the area cut is not -- the many small boxes of the most populated classes.
-// Boxes without a usable screening area (degenerate / malformed, NaN sa) get the extra key kKeys and are tested
-// against everything.
-__device__ __forceinline__ int strip_of_area(float a) {
-    return min(kStrips - 1, max(0, (__float_as_int(a) >> 21) - ((127 - 22) << 2)));
-}
-__device__ __forceinline__ int xbin_of(float cx) { return min(kXBins - 1, max(0, (int)(cx * (float)kXBins))); }
-__device__ __forceinline__ int strip_of(const float4& b, float sa) {
-    return (sa != sa) ? kKeys : strip_of_area(box_area(b)) * kXBins + xbin_of(0.5f * (b.x + b.z));
-}
 
 // barrier over the first `n` threads of the CTA with an OR reduction of `pred`
 __device__ __forceinline__ bool bar_or(int id, int n, bool pred) {
@@ -137,7 +62,7 @@ __device__ __forceinline__ bool bar_or(int id, int n, bool pred) {
 
 enum { DBG_CHUNKS = 0, DBG_LOAD, DBG_P1, DBG_SYNC, DBG_P2, DBG_P3, DBG_P4, DBG_P5, DBG_SURV, DBG_ITERS, DBG_N };
 
-template <int kThreads, bool kFast, bool kUnit, bool kSort>
+template <int kThreads, bool kFast, bool kUnit>
 __global__ void __launch_bounds__(kThreads)
     nms_keeplist_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ counts, int n, int max_keep,
                         int slice_cap, NmsThr thr, int32_t* __restrict__ keep, int32_t* __restrict__ keep_count,
@@ -158,12 +83,6 @@ __global__ void __launch_bounds__(kThreads)
     NmsSmem* sm = reinterpret_cast<NmsSmem*>(smem_raw);
     float4* kbox = reinterpret_cast<float4*>(smem_raw + ((sizeof(NmsSmem) + 15) & ~(size_t)15));  // [slice_cap]
     float* karea = reinterpret_cast<float*>(kbox + slice_cap);                                      // [slice_cap]
-    // kUnit: second buffer for the per-chunk re-bucketing of the slice (layout: boxA | boxB | areaA | areaB)
-    constexpr bool kSorted = kFast && kUnit && kSort;
-    float4* kbox_alt = kbox + slice_cap;
-    if (kSorted) karea = reinterpret_cast<float*>(kbox + 2 * slice_cap);
-    float* karea_alt = karea + slice_cap;
-    int ns_sorted = 0;  // slice entries already bucketed in the current buffer
 
     const int cnt = counts ? min(counts[img], n) : n;
     // candidate i of the image: boxes[img][i], or boxes[img][gather_idx[img][i]] when the sorted order is given as
@@ -188,8 +107,6 @@ __global__ void __launch_bounds__(kThreads)
     float4 nbx = make_float4(0.f, 0.f, 0.f, 0.f);  // prefetched candidate of the next chunk (first kChunk threads)
     if (tid < kChunk && tid < cnt) nbx = cand(tid);
     if (tid < 2 * kChunkWords) (&sm->acc[0][0])[tid] = 0u;
-    if (kSorted)
-        for (int e = tid; e < kKeys + 2; e += kThreads) sm->sstart[e] = 0;
     for (int base = 0; base < cnt && nk < max_keep; base += kChunk, par ^= 1) {
         if (prof) { t0 = clock64(); dbg[DBG_CHUNKS] += 1; }
         // ---- phase 0: stage the chunk's candidates in shared memory, prefetch the next chunk ----------
@@ -203,145 +120,6 @@ __global__ void __launch_bounds__(kThreads)
         FRR_TICK(DBG_LOAD);
 
         const int ns = (nk - rank + S - 1) / S;  // kept ordinals o with o % S == rank
-        if (kSorted) {
-            // ---- phase 1 (sorted): the slice is bucketed by area class, the chunk's candidates are ordered by area class;
-            //      a warp takes 4 class-adjacent candidates (warp-uniform registers) and its LANES walk only the kept
-            //      boxes whose area can reach them: min(area) / max(area) >= thr is necessary for IoU >= thr, so
-            //      everything outside that range of classes is skipped exactly.
-            // (a) re-bucket the slice when boxes were appended by the previous chunk (counting sort into the other
-            //     buffer) and (b) order the chunk's candidates by class (counting sort of <= 256 positions; positions
-            //     past the end of the list are marked suppressed right away) -- the two sorts share their barriers
-            const bool resort = ns > ns_sorted;
-            for (int e = tid; e < kKeyCap; e += kThreads) { sm->shist[e] = 0u; sm->chist[e] = 0u; }
-            __syncthreads();
-            if (resort)
-                for (int i = tid; i < ns; i += kThreads) atomicAdd(&sm->shist[strip_of(kbox[i], karea[i])], 1u);
-            int cst = kKeys + 1;
-            if (tid < kChunk) {
-                if (base + tid < cnt) cst = strip_of(sm->cbox[tid], sm->carea[tid]);
-                else atomicOr(&sm->acc[par][tid >> 5], 1u << (tid & 31));
-                atomicAdd(&sm->chist[cst], 1u);
-            }
-            __syncthreads();
-            if (warp < 2 && (warp == 1 || resort)) {  // warp 0: slice keys, warp 1: candidate keys (kKeyPer keys per lane)
-                unsigned int* hist = warp == 0 ? sm->shist : sm->chist;
-                unsigned int* cursor = warp == 0 ? sm->scursor : sm->ccursor;
-                unsigned int h[kKeyPer], t3 = 0;
-#pragma unroll
-                for (int q = 0; q < kKeyPer; q += 4) {  // independent 16-byte loads (entries past kKeys + 1 are zero)
-                    const uint4 v = *reinterpret_cast<const uint4*>(hist + lane * kKeyPer + q);
-                    h[q] = v.x; h[q + 1] = v.y; h[q + 2] = v.z; h[q + 3] = v.w;
-                    t3 += v.x + v.y + v.z + v.w;
-                }
-                unsigned int inc = t3;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += t;
-                }
-                unsigned int run = inc - t3;
-#pragma unroll
-                for (int q = 0; q < kKeyPer; q += 4) {
-                    uint4 v;
-                    v.x = run; run += h[q];
-                    v.y = run; run += h[q + 1];
-                    v.z = run; run += h[q + 2];
-                    v.w = run; run += h[q + 3];
-                    *reinterpret_cast<uint4*>(cursor + lane * kKeyPer + q) = v;
-                    if (warp == 0) {
-                        const int e = lane * kKeyPer + q;
-                        if (e + 3 <= kKeys + 1) {
-                            *reinterpret_cast<uint2*>(sm->sstart + e) =
-                                make_uint2((v.x & 0xffffu) | (v.y << 16), (v.z & 0xffffu) | (v.w << 16));
-                        } else {
-                            if (e <= kKeys + 1) sm->sstart[e] = (unsigned short)v.x;
-                            if (e + 1 <= kKeys + 1) sm->sstart[e + 1] = (unsigned short)v.y;
-                            if (e + 2 <= kKeys + 1) sm->sstart[e + 2] = (unsigned short)v.z;
-                        }
-                    }
-                }
-            }
-            __syncthreads();
-            if (resort) {
-                for (int i = tid; i < ns; i += kThreads) {
-                    const float4 b = kbox[i];
-                    const float a = karea[i];
-                    const unsigned int pos = atomicAdd(&sm->scursor[strip_of(b, a)], 1u);
-                    kbox_alt[pos] = b;
-                    karea_alt[pos] = a;
-                }
-                float4* tb = kbox; kbox = kbox_alt; kbox_alt = tb;
-                float* ta = karea; karea = karea_alt; karea_alt = ta;
-                ns_sorted = ns;
-            }
-            if (tid < kChunk) sm->cord[atomicAdd(&sm->ccursor[cst], 1u)] = (unsigned short)tid;
-            __syncthreads();
-            FRR_TICK(10);  // bucketing time (reported separately, not part of the phase-1 slot)
-            // (c) kSub threads per candidate (candidates in class order, so the lanes of a warp walk ranges of similar
-            //     length): each thread screens its candidate against every kSub-th kept box of the candidate's admissible
-            //     classes and of the always-tested class, remembers one hit, and confirms it with the exact test.  (The
-            //     earlier form -- a warp per 4 candidates, lanes over kept boxes -- spent half of its issue slots on
-            //     warp-uniform bookkeeping: after the area cut a group's range is only ~4 warp trips long.  Dealing
-            //     fixed-size pieces of the ranges to the threads through a prefix sum balances better but was measured
-            //     1.7x slower: the per-item search and the virtual-range indexing cost more than the imbalance.)
-            {
-                constexpr int kSub = kThreads / kChunk;
-                const int sub = tid % kSub;
-                const int cpos = sm->cord[tid / kSub];
-                if (base + cpos < cnt) {
-                    const float4 cbx = sm->cbox[cpos];
-                    const float ca = sm->carea[cpos];
-                    int pk = -1;
-                    int c_lo = 0, c_hi = -1, x_lo = 0, x_hi = 0;  // admissible keys: classes c_lo..c_hi, x bins x_lo..x_hi
-                    int lo2 = 0, hi2 = ns;                        // second segment: everything (NaN area) / always-tested
-                    if (ca == ca) {
-                        const float a = box_area(cbx);
-                        c_lo = strip_of_area(a * thr.alo);
-                        c_hi = strip_of_area(a * thr.ahi);
-                        const float cx = 0.5f * (cbx.x + cbx.z);
-                        const float rx = thr.fx * (cbx.z - cbx.x) * 1.0001f + 2.0e-6f;
-                        x_lo = xbin_of(cx - rx);
-                        x_hi = xbin_of(cx + rx);
-                        lo2 = sm->sstart[kKeys];
-                        hi2 = sm->sstart[kKeys + 1];
-                    }
-                    // the bounds of all admissible classes are fetched before the first walk (independent loads): with one
-                    // dependent sstart -> kbox chain per class the walks were latency bound
-                    constexpr int kMaxCls = 6;  // [alo, ahi] spans 2 * log2(1 / thr) * 4 + 1 classes: 5.1 at thr 0.7
-                    int lo_c[kMaxCls], hi_c[kMaxCls];
-#pragma unroll
-                    for (int q = 0; q < kMaxCls; ++q) {
-                        const int c = min(c_lo + q, kStrips - 1);
-                        lo_c[q] = sm->sstart[c * kXBins + x_lo];
-                        hi_c[q] = (c_lo + q <= c_hi) ? (int)sm->sstart[c * kXBins + x_hi + 1] : 0;
-                    }
-#pragma unroll
-                    for (int q = 0; q < kMaxCls; ++q) {
-#pragma unroll 2
-                        for (int k = lo_c[q] + sub; k < hi_c[q]; k += kSub)
-                            if (suppress_screen<true>(kbox[k], karea[k], cbx, ca)) pk = k;
-                    }
-                    for (int c = c_lo + kMaxCls; c <= c_hi; ++c) {  // thresholds below 0.6: more classes
-                        const int lo = sm->sstart[c * kXBins + x_lo], hi = sm->sstart[c * kXBins + x_hi + 1];
-                        for (int k = lo + sub; k < hi; k += kSub)
-                            if (suppress_screen<true>(kbox[k], karea[k], cbx, ca)) pk = k;
-                    }
-                    for (int k = lo2 + sub; k < hi2; k += kSub)
-                        if (suppress_screen<true>(kbox[k], karea[k], cbx, ca)) pk = k;
-                    if (pk >= 0) {
-                        bool r = suppress_exact(kbox[pk], cbx, thr.up);
-                        if (!r) {  // the screen hit was not confirmed by the exact test (rare): exact walk of the own share
-                            for (int c = c_lo; c <= c_hi && !r; ++c) {
-                                const int lo = sm->sstart[c * kXBins + x_lo], hi = sm->sstart[c * kXBins + x_hi + 1];
-                                for (int k = lo + sub; k < hi && !r; k += kSub) r = suppress_exact(kbox[k], cbx, thr.up);
-                            }
-                            for (int k = lo2 + sub; k < hi2 && !r; k += kSub) r = suppress_exact(kbox[k], cbx, thr.up);
-                        }
-                        if (r) atomicOr(&sm->acc[par][cpos >> 5], 1u << (cpos & 31));
-                    }
-                }
-            }
-        } else {
         // ---- phase 1: 4 candidates per thread vs this CTA's slice of the kept list ----------------------
         {
             float4 cb[kTile];
@@ -393,7 +171,6 @@ __global__ void __launch_bounds__(kThreads)
                 const unsigned int wj = __ballot_sync(0xffffffffu, sup[j]);
                 if (lane == 0 && wj != 0u) atomicOr(&sm->acc[par][(warp % kGW) + kGW * j], wj);
             }
-        }
         }
         __syncthreads();
         // publish this CTA's 8 words to every CTA of the cluster (distributed shared memory)
@@ -568,36 +345,14 @@ __global__ void __launch_bounds__(kThreads)
     }
 }
 
-static NmsThr make_thr(double thr) {
-    NmsThr t;
-    float f = (float)thr;
-    if (isnan(thr)) {
-        t.up = NAN;  // nothing is ever > NaN
-    } else {
-        if (!((double)f > thr)) f = nextafterf(f, INFINITY);
-        t.up = f;
-    }
-    t.fast = (thr >= 1.0e-6) && isfinite(thr) && (t.up < 1.0e30f) ? 1 : 0;
-    const double u = (double)t.up;
-    t.c2 = t.fast ? (float)(u / (1.0 + u) * (1.0 - 1.9073486328125e-06)) : 0.f;
-    // IoU >= thr needs min(area) / max(area) >= thr; thr is lowered by 2^-17 relative to cover the fp32 roundings of the
-    // exact IoU (<= 2^-20, see strip_of_area) and of the two products below
-    const double tl = thr * (1.0 - 7.62939453125e-06);
-    // ... and |cx_a - cx_b| <= max(1 - thr, (1 - thr) / (2 thr)) * w of EITHER box
-    t.fx = t.fast ? (float)(fmax(1.0 - tl, (1.0 - tl) / (2.0 * tl)) * (1.0 + 1.0e-6)) : 0.f;
-    t.alo = t.fast ? (float)(tl * (1.0 - 1.0e-6)) : 0.f;
-    t.ahi = t.fast ? (float)(1.0 / tl * (1.0 + 1.0e-6)) : 0.f;
-    return t;
-}
-
-static size_t nms_smem_bytes(int slice_cap, bool sorted) {
-    return ((sizeof(NmsSmem) + 15) & ~(size_t)15) + (size_t)slice_cap * (sizeof(float4) + sizeof(float)) * (sorted ? 2 : 1);
+static size_t nms_smem_bytes(int slice_cap) {
+    return ((sizeof(NmsSmem) + 15) & ~(size_t)15) + (size_t)slice_cap * (sizeof(float4) + sizeof(float));
 }
 
 // Launch geometry and kernel variant for a problem: shared by nms_launch and frr_nms_variant (tests / bench assert
 // through the latter that the variant they mean to exercise is the one that runs).
 struct NmsPick {
-    int S, threads, slice_cap, sorted;
+    int S, threads, slice_cap, bucketed;
     size_t smem;
     NmsThr thr;
 };
@@ -615,26 +370,33 @@ static int nms_pick(int B, int n, double iou_thr, int max_keep, int cluster_size
         while (S * 2 <= per && S < 16) S *= 2;
     }
     FRR_CHECK_ARG(S == 1 || S == 2 || S == 4 || S == 8 || S == 16, "frr_nms_sorted: cluster_size %d not in {1,2,4,8,16}", S);
+    const NmsThr thr = make_thr(iou_thr);
+    out->thr = thr;
+    // Unit-range boxes with a screenable threshold (the RPN proposal layer, models/model.py:53): the bucketed
+    // large-chunk kernel of nms_bucket.cu, every CTA of the cluster holds the whole kept list.
+    if (nms_bucket_eligible(n, max_keep, thr, unit_boxes)) {
+        out->S = S;
+        out->threads = threads == 0 ? 1024 : threads;
+        out->slice_cap = 0;
+        out->bucketed = 1;
+        out->smem = nms_bucket_smem_bytes();
+        return FRR_OK;
+    }
     // a CTA whose slice of the kept list is short (one image spread over 16 CTAs) is bound by its per-chunk barriers:
     // 16 warps resolve them faster than 32 (130 vs 134 us for 12000 -> 2000 boxes)
     if (threads == 0) threads = (kcap / S < 192) ? 512 : 1024;
     if (threads < kChunk) threads = kChunk;  // the first kChunk threads own one candidate each
-    const NmsThr thr = make_thr(iou_thr);
-    // The class-sorted phase 1 pays ~10 k cycles of bucketing per chunk: it wins once a CTA's slice of the kept
-    // list is large (batched launches with 1-2 CTAs per image), not for a single image spread over 16 CTAs.
-    const bool sorted = thr.fast && unit_boxes && (kcap / S >= 384);
     // grow the cluster until a slice of the kept list fits in shared memory
     const size_t limit = 227 * 1024;
-    while (nms_smem_bytes((kcap + S - 1) / S + 1, sorted) > limit && S < 16) S *= 2;
+    while (nms_smem_bytes((kcap + S - 1) / S + 1) > limit && S < 16) S *= 2;
     const int slice_cap = (kcap + S - 1) / S + 1;
-    const size_t smem = nms_smem_bytes(slice_cap, sorted);
+    const size_t smem = nms_smem_bytes(slice_cap);
     FRR_CHECK_ARG(smem <= limit, "frr_nms_sorted: max_keep=%d does not fit the kept list in shared memory", max_keep);
     out->S = S;
     out->threads = threads;
     out->slice_cap = slice_cap;
-    out->sorted = sorted ? 1 : 0;
+    out->bucketed = 0;
     out->smem = smem;
-    out->thr = thr;
     return FRR_OK;
 }
 
@@ -650,22 +412,23 @@ int nms_launch(const float* boxes, const int32_t* counts, int B, int n, double i
         if (rc) return rc;
     }
     if (B == 0) return FRR_OK;
+    if (pk.bucketed)
+        return nms_bucket_launch(boxes, counts, B, n, pk.thr, max_keep, keep, keep_count, out_boxes, pk.S, pk.threads, dbg,
+                                 stream, gather_idx, src_n);
     const int S = pk.S, slice_cap = pk.slice_cap;
     threads = pk.threads;
-    const bool sorted = pk.sorted != 0;
     const size_t smem = pk.smem, limit = 227 * 1024;
     const NmsThr thr = pk.thr;
 
     using kern_t = void (*)(const float4*, const int32_t*, int, int, int, NmsThr, int32_t*, int32_t*, float4*, long long*,
                             const int32_t*, int);
     kern_t kern = nullptr;
-#define FRR_NMS_PICK(F, U, SO)                                                                      \
-    (threads < kChunk * 2 ? nms_keeplist_kernel<kChunk, F, U, SO>                                            \
-                    : threads == 512 ? nms_keeplist_kernel<512, F, U, SO> : nms_keeplist_kernel<1024, F, U, SO>)
-    if (sorted) kern = FRR_NMS_PICK(true, true, true);
-    else if (thr.fast && unit_boxes) kern = FRR_NMS_PICK(true, true, false);
-    else if (thr.fast) kern = FRR_NMS_PICK(true, false, false);
-    else kern = FRR_NMS_PICK(false, false, false);
+#define FRR_NMS_PICK(F, U)                                                                      \
+    (threads < kChunk * 2 ? nms_keeplist_kernel<kChunk, F, U>                                            \
+                    : threads == 512 ? nms_keeplist_kernel<512, F, U> : nms_keeplist_kernel<1024, F, U>)
+    if (thr.fast && unit_boxes) kern = FRR_NMS_PICK(true, true);
+    else if (thr.fast) kern = FRR_NMS_PICK(true, false);
+    else kern = FRR_NMS_PICK(false, false);
 #undef FRR_NMS_PICK
     FRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
     if (S > 8) FRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -716,7 +479,7 @@ extern "C" int frr_nms_variant(int B, int n, double iou_thr, int max_keep, int c
     if (rc) return rc;
     out4[0] = pk.S;
     out4[1] = pk.threads;
-    out4[2] = pk.sorted ? 3 : (pk.thr.fast ? (unit_boxes ? 2 : 1) : 0);
+    out4[2] = pk.bucketed ? 3 : (pk.thr.fast ? (unit_boxes ? 2 : 1) : 0);
     out4[3] = (int32_t)pk.smem;
     return FRR_OK;
 }

@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kRoiThreads)
 // ---------------------------------------------------------------------------------------------
 template <bool kAlign>
 __global__ void __launch_bounds__(256)
-    roi_fwd_direct_kernel(const float* __restrict__ feat, const float* __restrict__ rois, size_t total, int C, int H, int W,
+    roi_fwd_direct_kernel(const float* __restrict__ feat, const float* __restrict__ rois, size_t total, int B, int C, int H, int W,
                           int PH, int PW, float scale, int sampling, int aligned, int nhwc, float* __restrict__ out,
                           int32_t* __restrict__ argmax) {
     const int bins = PH * PW;
@@ -177,7 +177,9 @@ __global__ void __launch_bounds__(256)
         const int ph = bin / PW, pw = bin - ph * PW;
         const float* r = rois + 5 * k;
         const int b = (int)r[0];
-        if (b < 0) continue;  // masked roi (belongs to another pyramid level): its output row is written elsewhere
+        // masked roi (index -1: belongs to another pyramid level / padding row, its output row is written elsewhere);
+        // an index >= B is malformed input and is skipped the same way instead of reading out of bounds
+        if (b < 0 || b >= B) continue;
         const float* base = nhwc ? feat + (size_t)b * H * W * C + c : feat + ((size_t)b * C + c) * H * W;
         const size_t ps = nhwc ? (size_t)C : 1;  // pixel stride
         if (!kAlign) {
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(256)
 template <bool kAlign>
 __global__ void __launch_bounds__(256)
     roi_bwd_direct_kernel(const float* __restrict__ grad_out, const int32_t* __restrict__ argmax,
-                          const float* __restrict__ rois, size_t total, int C, int H, int W, int PH, int PW, float scale,
+                          const float* __restrict__ rois, size_t total, int B, int C, int H, int W, int PH, int PW, float scale,
                           int sampling, int aligned, int nhwc, float* __restrict__ grad_in /* zeroed */) {
     const int bins = PH * PW;
     for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(256)
         const size_t k = o / ((size_t)bins * C);
         const float* r = rois + 5 * k;
         const int b = (int)r[0];
-        if (b < 0) continue;  // masked roi
+        if (b < 0 || b >= B) continue;  // masked / malformed roi: contributes nothing
         float* base = nhwc ? grad_in + (size_t)b * H * W * C + c : grad_in + ((size_t)b * C + c) * H * W;
         const size_t ps = nhwc ? (size_t)C : 1;
         const float go = grad_out[o];
@@ -307,7 +309,7 @@ static int roi_forward(const float* feat, const float* rois, int K, int B, int C
     } else {
         const size_t total = (size_t)K * C * PH * PW;
         const int blocks = (int)((total + 255) / 256 < (size_t)num_sms() * 16 ? (total + 255) / 256 : (size_t)num_sms() * 16);
-        roi_fwd_direct_kernel<kAlign><<<blocks, 256, 0, st>>>(feat, rois, total, C, H, W, PH, PW, scale, sampling, aligned,
+        roi_fwd_direct_kernel<kAlign><<<blocks, 256, 0, st>>>(feat, rois, total, B, C, H, W, PH, PW, scale, sampling, aligned,
                                                               nhwc, out, argmax);
     }
     count_launch();
@@ -346,7 +348,7 @@ static int roi_backward(const float* grad_out, const int32_t* argmax, const floa
             const size_t total = (size_t)K * C * PH * PW;
             const int blocks =
                 (int)((total + 255) / 256 < (size_t)num_sms() * 16 ? (total + 255) / 256 : (size_t)num_sms() * 16);
-            roi_bwd_direct_kernel<kAlign><<<blocks, 256, 0, st>>>(grad_out, argmax, rois, total, C, H, W, PH, PW, scale,
+            roi_bwd_direct_kernel<kAlign><<<blocks, 256, 0, st>>>(grad_out, argmax, rois, total, B, C, H, W, PH, PW, scale,
                                                                   sampling, aligned, nhwc, grad_in);
             count_launch();
         }
@@ -378,9 +380,37 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// R1 glue (models/model.py:104-110 + TV ops/_utils.py:18-25): normalised rois [B,R,4] -> feature-map rois [B*R,5] with
+// the batch index in column 0; rows past count[b] get index -1 (masked: the RoI kernels skip them).
+__global__ void __launch_bounds__(256)
+    rois5_kernel(const float4* __restrict__ rois, const int32_t* __restrict__ count, int B, int R, float fw, float fh,
+                 float* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= B * R) return;
+    const int b = k / R, r = k - b * R;
+    const float4 v = rois[k];
+    float* o = out + 5 * (size_t)k;
+    o[0] = (count == nullptr || r < count[b]) ? (float)b : -1.0f;
+    o[1] = __fmul_rn(v.x, fw);
+    o[2] = __fmul_rn(v.y, fh);
+    o[3] = __fmul_rn(v.z, fw);
+    o[4] = __fmul_rn(v.w, fh);
+}
+
 }  // namespace frr
 
 extern "C" {
+
+int frr_rois5(const float* rois, const int32_t* count, int B, int R, float fw, float fh, float* rois5, frr_stream_t stream) {
+    using namespace frr;
+    FRR_CHECK_ARG(B >= 0 && R >= 0, "frr_rois5: bad sizes");
+    if (B == 0 || R == 0) return FRR_OK;
+    FRR_CHECK_ARG(rois && rois5 && aligned16(rois), "frr_rois5: rois must be non-null and 16-byte aligned");
+    rois5_kernel<<<(B * R + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float4*)rois, count, B, R, fw, fh, rois5);
+    count_launch();
+    FRR_CHECK_LAUNCH("rois5_kernel");
+    return FRR_OK;
+}
 
 int frr_fpn_level_rois(const float* rois5, int K, int k_min, int k_max, int canonical_level, float canonical_scale, int L,
                        int32_t* levels, float* rois_per_level, frr_stream_t stream) {

@@ -181,6 +181,24 @@ def convert_rois(rois, device=None) -> torch.Tensor:
     return rois
 
 
+def rois5(rois, count, feat_hw, out=None):
+    """models/model.py:104-110 for a batch: normalised rois [B,R,4] (+ int32 count [B] or None) -> [B*R,5] feature-map
+    rois with the batch index; rows past count[b] are masked (index -1).  One kernel, no host synchronisation."""
+    lib = _lib.load()
+    rois = _req(rois, "rois")
+    if rois.dim() != 3 or rois.shape[-1] != 4:
+        raise ValueError("rois must be [B,R,4]")
+    B, R = rois.shape[0], rois.shape[1]
+    if count is not None:
+        count = _req(count, "count", torch.int32)
+    with torch.cuda.device(rois.device):
+        if out is None:
+            out = torch.empty((B * R, 5), dtype=torch.float32, device=rois.device)
+        _lib.check(lib.frr_rois5(rois.data_ptr(), _ptr(count), B, R, float(feat_hw[1]), float(feat_hw[0]), out.data_ptr(),
+                                 _stream()), "frr_rois5")
+    return out
+
+
 def roi_pool_forward(feat, rois5, output_size=(7, 7), spatial_scale: float = 1.0, want_argmax: bool = True):
     lib = _lib.load()
     feat = _req(feat, "features") if feat.is_contiguous() else feat

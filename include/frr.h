@@ -113,6 +113,10 @@ int frr_nms_sorted_tuned(const float* boxes, const int32_t* counts, int B, int n
 int frr_nms_variant(int B, int n, double iou_thr, int max_keep, int cluster_size, int threads, int unit_boxes,
                     int32_t* out4);
 
+/* Developer knob for the profiling tools: sizes of the first and of the largest chunk of the bucketed variant
+ * (multiples of 256 in [256, 2048]; process-wide; results never depend on them). */
+int frr_nms_bucket_tune(int first_chunk, int max_chunk);
+
 /* Same, with the score order given as indices into an unsorted array: candidate i of image b is
  * boxes_src[b][order[b][i]] (boxes_src [B,src_n,4]; order int32 [B,n] = out_idx of frr_topk_desc).  Only the
  * candidates NMS visits are gathered; the top-k kernel then need not write sorted boxes at all.          */
@@ -147,6 +151,12 @@ int frr_rpn_proposals(const float* reg /* [B,N,4] */, const float* cls /* [B,N,2
  *        (argmax int32 = h*W+w, -1 for empty bins; may be NULL in inference).
  *        Forward max/argmax bit-exact vs torchvision CPU; backward within 1e-5 (fp32 sum order).
  * ------------------------------------------------------------------------------------- */
+/* R1 glue -- models/model.py:104-110 (roi * [fw,fh,fw,fh]) + TV ops/_utils.py:18-25 (list of per-image rois ->
+ * Tensor[K,5] with the batch index): rois [B,R,4] normalised (e.g. the output of frr_rpn_proposals), count [B] or
+ * NULL -> rois5 [B*R,5]; rows r >= count[b] get batch index -1 = masked: the RoI kernels skip masked rois (their
+ * output rows are not written) and rois whose index is >= B. */
+int frr_rois5(const float* rois, const int32_t* count, int B, int R, float fw, float fh, float* rois5,
+              frr_stream_t stream);
 int frr_roi_pool_fwd(const float* feat, const float* rois, int K, int B, int C, int H, int W, int PH, int PW,
                      float spatial_scale, int channels_last, float* out, int32_t* argmax, frr_stream_t stream);
 /* grad_in [B,C,H,W] (same memory format as feat) is fully written (no pre-zeroing needed). */

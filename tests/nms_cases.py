@@ -169,6 +169,21 @@ def dense_duplicates(seed: int, n: int):
     return _clip(np.concatenate([c - w / 2, c + w / 2], axis=1))
 
 
+def staircase(seed: int, n: int):
+    """Rows of boxes, each shifted by 1/7 of its width against its left neighbour (IoU 0.75 with the neighbour, 0.56
+    with the next one): at thr 0.7 the decision of a box depends on the decision of its neighbour, chains of ~25
+    dependent decisions -- the fix-point needs as many rounds.  Scores run along a row, rows are interleaved."""
+    rs = np.random.RandomState(seed)
+    per = 25
+    rows = (n + per - 1) // per
+    w, h = 0.2, 0.9 / rows
+    r = np.arange(n) % rows
+    k = np.arange(n) // rows
+    x1 = 0.01 + k * (w / 7.0) + rs.uniform(0, 1e-4, n)
+    y1 = 0.02 + r * h
+    return _clip(np.stack([x1, y1, x1 + w, y1 + h * 0.9], axis=1))
+
+
 def sparse(seed: int, n: int):
     """Small boxes that hardly overlap: (almost) everything is kept -- the walk ends by count, not by max_keep."""
     rs = np.random.RandomState(seed)
@@ -184,6 +199,7 @@ CASES = {
     "one_class": one_class,
     "dense_duplicates": dense_duplicates,
     "sparse": sparse,
+    "staircase": staircase,
 }
 THR_CASES = {
     "nested_at_threshold": nested_at_threshold,

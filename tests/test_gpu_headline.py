@@ -118,21 +118,13 @@ def test_bucketed_nms_adversarial_sets(oracle, name, thr):
     n = len(b)
     for max_keep in (2000, 700):
         want = oracle.nms(b, -np.arange(n, dtype=np.float32), thr)[:max_keep]
-        plain = _run_nms(b, thr, max_keep, cluster_size=8, threads=512)             # screened, no buckets
+        plain = _run_nms(b, thr, max_keep, cluster_size=8, threads=512)             # keep-list kernel, no buckets
         assert np.array_equal(plain, want), (name, thr, "plain")
-        for cs in (1, 2, 4):
-            for threads in (256, 512, 1024):
-                v = ops.nms_variant(1, n, thr, max_keep, cluster_size=cs, threads=threads, unit_boxes=True)
-                if v["variant"] != "bucketed":
-                    continue
-                got = _run_nms(b, thr, max_keep, cluster_size=cs, threads=threads, unit_boxes=True)
-                assert np.array_equal(got, want), (name, thr, max_keep, cs, threads)
-
-
-def test_bucketed_variant_is_reached_by_the_adversarial_test():
-    hit = [ops.nms_variant(1, 6000, 0.7, mk, cluster_size=cs, threads=t, unit_boxes=True)["variant"]
-           for mk in (2000, 700) for cs in (1, 2, 4) for t in (256, 512, 1024)]
-    assert hit.count("bucketed") >= 6, hit
+        for cs, threads in [(1, 1024), (2, 1024), (4, 1024), (16, 1024), (1, 256), (2, 512), (8, 512), (16, 256)]:
+            v = ops.nms_variant(1, n, thr, max_keep, cluster_size=cs, threads=threads, unit_boxes=True)
+            assert v["variant"] == "bucketed" and v["cluster_size"] == cs and v["threads"] == threads, v
+            got = _run_nms(b, thr, max_keep, cluster_size=cs, threads=threads, unit_boxes=True)
+            assert np.array_equal(got, want), (name, thr, max_keep, cs, threads)
 
 
 @pytest.mark.parametrize("cs", [1, 2, 4])
@@ -155,14 +147,29 @@ def test_bucketed_nms_batched_ragged_counts(oracle, cs):
         assert np.array_equal(rois[i, :len(got)].cpu().numpy(), bs[i][got]), i
 
 
-def test_bucketed_nms_full_walk_keeps_everything_up_to_n(oracle):
-    """max_keep never reached: the walk must visit all 12 000 candidates (last, partial chunk included)."""
-    b = nms_cases.rpn_like(2003, 11999)
-    for cs in (2, 4):
+def test_bucketed_nms_walk_ends_by_count_with_a_partial_last_chunk(oracle):
+    """max_keep never reached: every candidate is visited, the last chunk is partial."""
+    for n in (2900, 1025, 255):
+        b = nms_cases.rpn_like(2003, n)
         want = oracle.nms(b, -np.arange(len(b), dtype=np.float32), 0.7)
-        assert len(want) > 2000
-        mk = 3000
-        if ops.nms_variant(1, len(b), 0.7, mk, cluster_size=cs, unit_boxes=True)["variant"] != "bucketed":
-            continue
-        got = _run_nms(b, 0.7, mk, cluster_size=cs, unit_boxes=True)
-        assert np.array_equal(got, want[:mk])
+        assert len(want) < 2000
+        for cs in (1, 2, 16):
+            assert ops.nms_variant(1, len(b), 0.7, 2000, cluster_size=cs, unit_boxes=True)["variant"] == "bucketed"
+            got = _run_nms(b, 0.7, 2000, cluster_size=cs, unit_boxes=True)
+            assert np.array_equal(got, want), (n, cs)
+
+
+@pytest.mark.parametrize("first,largest", [(256, 256), (256, 2048), (2048, 2048), (512, 1024)])
+def test_bucketed_nms_result_does_not_depend_on_chunk_sizes(oracle, first, largest):
+    from faster_rcnn_pytorch_b200 import _lib
+    lib = _lib.load()
+    try:
+        _lib.check(lib.frr_nms_bucket_tune(first, largest), "frr_nms_bucket_tune")
+        for name in ("rpn_like", "dense_duplicates", "staircase"):
+            b = nms_cases.make(name, 5, 7000)
+            want = oracle.nms(b, -np.arange(len(b), dtype=np.float32), 0.7)[:2000]
+            for cs in (1, 2, 8):
+                got = _run_nms(b, 0.7, 2000, cluster_size=cs, unit_boxes=True)
+                assert np.array_equal(got, want), (name, cs)
+    finally:
+        _lib.check(lib.frr_nms_bucket_tune(1024, 2048), "frr_nms_bucket_tune")

@@ -13,7 +13,11 @@ sc = torch.from_numpy(np.stack([x[2] for x in ins])).to(dev)
 boxes, scores, valid = ops.rpn_decode(reg, sc, image_hw=HW)
 top = ops.topk_desc(scores, 12000, valid=valid, boxes=boxes)
 tb, tc = top["boxes"], top["count"]
-names = ["chunks", "load", "p1", "sync", "p2", "p3", "p4", "p5", "surv", "iters", "bucket"]
+# slots of nms_bucket_kernel (csrc/nms_bucket.cu, enum BK_*): cycles of CTA 0 per phase, then counters
+names = ["chunks", "load", "scan", "scatter", "screen", "sync1", "surv_sort", "pred", "sync2", "fix", "append",
+         "rounds", "survivors", "edges", "visited", "ovf"]
+from faster_rcnn_pytorch_b200 import _lib
+lib = _lib.load()
 
 
 def run(bx, cnt, S, threads, reps=20, dbg=False):
@@ -38,9 +42,12 @@ def run(bx, cnt, S, threads, reps=20, dbg=False):
     print(json.dumps(out), flush=True)
 
 
-for threads, S in ((1024, 2), (512, 2), (512, 4), (512, 8), (1024, 4)):
-    run(tb, tc, S, threads, dbg=True)
 one, onec = tb[:1].contiguous(), tc[:1].contiguous()
-for threads in (512, 1024):
-    for S in (4, 8, 16):
+for first, largest in ((1024, 2048), (512, 2048), (2048, 2048), (1024, 1024), (512, 1024), (768, 1536)):
+    _lib.check(lib.frr_nms_bucket_tune(first, largest), "tune")
+    print(json.dumps({"first_chunk": first, "largest_chunk": largest}), flush=True)
+    for threads, S in ((1024, 2), (512, 2), (1024, 1), (1024, 4)):
+        run(tb, tc, S, threads, dbg=True)
+    for threads, S in ((1024, 16), (512, 16), (1024, 8), (512, 8)):
         run(one, onec, S, threads, reps=50, dbg=True)
+_lib.check(lib.frr_nms_bucket_tune(1024, 2048), "tune")
