@@ -1,12 +1,18 @@
 #!/usr/bin/env python
 """Region-stage benchmark (BASELINE.json metric: region-stage images/sec; NMS us @12k boxes).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload rpn|...]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload all|rpn|voc1|train|infer|joint]
 
-Default workload = BASELINE.json configs[1]: RPN proposal layer, 9 anchors x 38x63 map (608x1008 image,
-N = 21546), 12000 pre-NMS -> 2000 post-NMS at IoU 0.7, batch 64 images per GPU.  One "step" = one
-pass of decode + top-k + NMS over one batch of 64 synthetic images.  Under torchrun every rank
-processes its own 64 images (weak scaling, no data-path collective); rank 0 prints ONE JSON line.
+The line's headline (`value`, `e2e`, `roofline`, `cpu_baseline`) is BASELINE.json configs[1]: RPN proposal layer, 9 anchors x
+38x63 map (608x1008 image, N = 21546), 12000 pre-NMS -> 2000 post-NMS at IoU 0.7, batch 64 images per GPU; one "step" = one
+pass of decode + top-k + NMS over one batch of 64 synthetic images.  With the default `--workload all` the same line carries
+`sub_results` for the other single-GPU configurations of the metric, measured by the same process under the same clock:
+    voc1  = configs[0]: one 600x1000 VOC image, FRCNN.predict's region path (6000 -> 300, RoIPool 300, D1, 21-class NMS), latency
+    train = configs[2]: target makers + RoIPool 7x7 fwd/bwd, 16 images/GPU
+    infer = configs[3]: COCO-shaped 800x1333 inference, 81 classes, 8 images/GPU, detections all-gathered over NCCL
+Under torchrun every rank processes its own images (weak scaling; the only collective is the detection all-gather of
+`infer`); rank 0 prints ONE JSON line.  `--impl reference` times the CPU restatement of the reference (oracle/) on the
+host cores for the same configurations.
 """
 from __future__ import annotations
 
@@ -30,14 +36,32 @@ N_ROTATE = 8           # resident input batches cycled through so that every ste
 METRIC = "region-stage images/sec (RPN+NMS+RoIPool) at 1/2/4/8 B200; NMS us @12k boxes"
 WORKLOAD = ("configs[1]: RPN proposal layer, 9 anchors x 38x63 map (608x1008), 12000 pre-NMS -> 2000 post-NMS "
             "@ IoU 0.7, batch 64 images/GPU")
+W_VOC1 = ("configs[0]: VOC VGG16 inference region path, 1 image 600x1000: proposals 6000 -> 300 @0.7, RoIPool 300 x 512 x 7x7, "
+          "per-class decode, 21-class NMS @0.3 (thres 0.05)")
+W_TRAIN = ("configs[2]: training targets (256 anchor / 128 RoI sampling, G=8) + RoIPool 7x7 fwd/bwd on 512-ch stride-16 "
+           "features (37x62), batch 16 images/GPU, RoIs sampled from the RPN proposals")
+W_INFER = ("configs[3]: COCO-shaped 800x1333 inference, 81 classes, 6000 -> 300 proposals, RoIPool of 300 RoIs x 512 ch, "
+           "80-class NMS @0.3 (thres 0.05), 8 images/GPU, detections [8,100,6] all-gathered")
+
+
+def config_of(workload: str, batch: int) -> dict:
+    """Identical in both arms (`--impl ours` / `--impl reference`)."""
+    return {"workload": workload, "images_per_gpu_per_step": batch}
+
+
+def profile_counters(kernel: str) -> dict:
+    """Per-launch counters of `kernel` from the committed ncu --set full capture (profiles/traffic.json)."""
+    try:
+        return json.load(open(os.path.join(REPO, "profiles", "traffic.json")))[kernel]
+    except (OSError, KeyError, ValueError):
+        return {}
 
 
 def ncu_traffic(kernel: str):
-    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json), or None."""
+    t = profile_counters(kernel)
     try:
-        t = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))[kernel]
         return t["dram_bytes_read"] + t["dram_bytes_write"]
-    except (OSError, KeyError, ValueError):
+    except KeyError:
         return None
 
 
@@ -45,39 +69,108 @@ def peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as fh:
-            return float(json.load(fh)["hbm_gbs"]), "measured"
-    return 6650.0, "fallback"
+            d = json.load(fh)
+            return float(d["hbm_gbs"]), "measured", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback", 1965.0
 
 
-def make_inputs(seed0: int, batch: int):
+def make_inputs(seed0: int, batch: int, hw=HW):
     from faster_rcnn_pytorch_b200 import synth
-    n = synth.num_anchors(HW)
+    n = synth.num_anchors(hw)
     rs = np.random.RandomState(seed0)
     logits = rs.standard_normal((batch, n, 2)).astype(np.float32)
     reg = (rs.standard_normal((batch, n, 4)) * 0.2).astype(np.float32)
     return logits, reg
 
 
-# ------------------------------------------------------------------------------------------ CPU arm
-def cpu_images_per_s(n_images: int, threads: int, seed0: int = 2000):
-    """The oracle port of the reference's proposal layer on the host cores: images are independent
-    (the reference is batch-1), one image per worker thread; numpy + the C NMS release the GIL."""
+# ------------------------------------------------------------------------------------------ CPU arm (oracle port)
+def _cpu_pool(fn, n_images: int, threads: int):
+    """Images are independent (the reference is batch-1): one image per worker thread; numpy and the C helpers of the
+    oracle release the GIL."""
     from concurrent.futures import ThreadPoolExecutor
+    fn(0)  # warm-up
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(fn, range(n_images)))
+    dt = time.perf_counter() - t0
+    return n_images / dt, dt
+
+
+def cpu_rpn(n_images: int, threads: int, seed0: int = 2000):
+    """configs[1] on the host: RegionProposal.forward (models/model.py:17-58) per image."""
     from oracle import region_oracle as orc, _cbridge
     _cbridge.load(required=True)
     from faster_rcnn_pytorch_b200 import synth
     anchor = orc.enumerate_anchors(HW)
     ins = [synth.rpn_head_outputs(seed0 + i, HW)[:2] for i in range(n_images)]
+    return _cpu_pool(lambda i: orc.region_proposal(ins[i][0], ins[i][1], anchor, "train")["rois"].shape[0], n_images, threads)
+
+
+def cpu_predict(n_images: int, threads: int, hw, num_classes: int, seed0: int):
+    """configs[0] / configs[3] on the host: FRCNN.predict's region path (models/model.py:346-402) per image: proposal layer
+    in test mode, RoIPool of the 300 rois, per-class decode, per-class NMS."""
+    from oracle import region_oracle as orc, _cbridge
+    _cbridge.load(required=True)
+    from faster_rcnn_pytorch_b200 import synth
+    anchor = orc.enumerate_anchors(hw)
+    fh, fw = hw[0] // 16, hw[1] // 16
+    rs = np.random.RandomState(seed0)
+    feat = rs.standard_normal((1, 512, fh, fw)).astype(np.float32)
+    ins = [synth.rpn_head_outputs(seed0 + i, hw)[:2] for i in range(n_images)]
+    heads = [synth.head_outputs(seed0 + 50 + i, 300, num_classes) for i in range(n_images)]
 
     def one(i):
-        return orc.region_proposal(ins[i][0], ins[i][1], anchor, "train")["rois"].shape[0]
+        rois = orc.region_proposal(ins[i][0], ins[i][1], anchor, "test")["rois"]
+        pooled, _ = orc.roi_pool_forward(feat, orc.scale_rois(rois, fh, fw))
+        r = rois.shape[0]
+        prob, boxes = orc.decode_classwise(heads[i][0][:r], heads[i][1][:r], rois, num_classes)
+        return orc.suppress(boxes, prob, num_classes, 0.05)[0].shape[0] + int(pooled.shape[0])
 
-    one(0)  # warm-up
-    t0 = time.perf_counter()
-    with ThreadPoolExecutor(max_workers=threads) as ex:
-        list(ex.map(one, range(n_images)))
-    dt = time.perf_counter() - t0
-    return n_images / dt, dt
+    return _cpu_pool(one, n_images, threads)
+
+
+def cpu_train(n_images: int, threads: int, seed0: int = 3000):
+    """configs[2] on the host: RPNTargetMaker + FastRcnnTargetMaker (models/model.py:123-266) + RoIPool 7x7 forward and
+    backward of the 128 sampled rois, per image (proposals precomputed, as on the GPU arm)."""
+    from oracle import region_oracle as orc, _cbridge
+    _cbridge.load(required=True)
+    from faster_rcnn_pytorch_b200 import synth
+    hw = (600, 1000)
+    fh, fw = hw[0] // 16, hw[1] // 16
+    anchor = orc.enumerate_anchors(hw)
+    rs = np.random.RandomState(seed0)
+    feat = rs.standard_normal((1, 512, fh, fw)).astype(np.float32)
+    gout = rs.standard_normal((128, 512, 7, 7)).astype(np.float32)
+    props = [synth.random_boxes(seed0 + 100 + i, 2000)[0] for i in range(n_images)]
+    gts = [synth.gt_boxes(seed0 + i, 8) for i in range(n_images)]
+
+    def one(i):
+        rp = orc.HostRandperm(seed0 + i)
+        orc.rpn_targets(gts[i][0], anchor, rp)
+        f = orc.frcnn_targets(gts[i][0], gts[i][1], props[i], rp)
+        rois5 = orc.scale_rois(f["sample_rois"], fh, fw)
+        out, arg = orc.roi_pool_forward(feat, rois5)
+        gin = orc.roi_pool_backward(gout[:rois5.shape[0]], arg, rois5, feat.shape)
+        return float(gin[0, 0, 0, 0])
+
+    return _cpu_pool(one, n_images, threads)
+
+
+CPU_ARMS = {
+    "rpn": (lambda n, t: cpu_rpn(n, t), WORKLOAD, BATCH, "numpy decode/sort + C NMS"),
+    "voc1": (lambda n, t: cpu_predict(n, t, (600, 1000), 21, 1000), W_VOC1, 1, "numpy decode/sort + C NMS + C RoIPool + numpy per-class decode / NMS loop"),
+    "train": (lambda n, t: cpu_train(n, t), W_TRAIN, 16, "numpy target makers (mt19937 randperm replay) + C RoIPool fwd/bwd"),
+    "infer": (lambda n, t: cpu_predict(n, t, (800, 1333), 81, 4000), W_INFER, 8, "numpy decode/sort + C NMS + C RoIPool + numpy per-class decode / NMS loop"),
+}
+
+
+def cpu_baseline(name: str, threads: int, per_thread: int = 2) -> dict:
+    fn, _, _, how = CPU_ARMS[name]
+    sample = max(threads, 8) * per_thread
+    v, dt = fn(sample, threads)
+    return {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
+            "sample": f"{sample} images of the same workload, oracle port ({how}), one image per thread on {threads} "
+                      f"threads, {dt:.1f} s wall"}
 
 
 def run_reference(args):
@@ -86,25 +179,31 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     sample = max(threads, 8) * 4
-    vals = []
     for _ in range(args.warmup):
-        cpu_images_per_s(min(sample, threads), threads)
+        cpu_rpn(min(sample, threads), threads)
     t_tot = 0.0
     for _ in range(args.steps):
-        v, dt = cpu_images_per_s(sample, threads)
-        vals.append(v)
+        _, dt = cpu_rpn(sample, threads)
         t_tot += dt
     value = sample * args.steps / t_tot
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_images_per_step": sample},
+        "config": config_of(WORKLOAD, BATCH),
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
                          "sample": f"{sample} images/step of the same workload, oracle port (numpy decode/sort + C NMS), "
                                    f"one image per thread on {threads} threads"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if args.workload == "all":
+        sub = {}
+        for name in ("voc1", "train", "infer"):
+            cb = cpu_baseline(name, threads)
+            _, wl, batch, _ = CPU_ARMS[name]
+            sub[name] = {"value": cb["value"], "unit": "images/s", "config": config_of(wl, batch), "cpu_baseline": cb,
+                         "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        line["sub_results"] = sub
     print(json.dumps(line))
 
 
@@ -159,23 +258,160 @@ class ClockSampler:
         return out
 
 
-def run_ours(args):
-    import ctypes
-    import torch
-    import torch.distributed as dist
-    from faster_rcnn_pytorch_b200 import _lib, ops, region, synth
+class Ctx:
+    """Process-wide plumbing of the GPU arm: device, NCCL group, device-side timing (max over ranks)."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the region stage has no CPU path; use --impl reference)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    lib = _lib.load()
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (the region stage has no CPU path; use --impl reference)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        from faster_rcnn_pytorch_b200 import _lib
+        self._lib = _lib
+        self.lib = _lib.load()
+        self.peak, self.peak_how, self.sm_mhz = peaks()
 
+    def sync_all(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def maxms(self, ms: float) -> float:
+        if self.world > 1:
+            t = self.torch.tensor([ms], device=self.dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    def timed(self, fn, steps: int, tail=None) -> float:
+        """ms for `steps` calls of fn(i): barrier + synchronize on both sides, CUDA events, max over ranks."""
+        torch = self.torch
+        self.sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        if tail is not None:
+            tail()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = self.maxms(e0.elapsed_time(e1))
+        self.sync_all()
+        return ms
+
+    def median_ms(self, fn, steps: int, runs: int = 5, tail=None) -> float:
+        return float(np.median([self.timed(fn, steps, tail) for _ in range(runs)]))
+
+    def graph_of(self, fn):
+        """Capture fn() (kernels + torch allocations from the graph's private pool) into a CUDA graph, or None."""
+        torch = self.torch
+        try:
+            fn()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                out = fn()
+            return g, out
+        except RuntimeError:
+            torch.cuda.synchronize()
+            return None, None
+
+    def kernel_ms(self, fn, reps: int) -> float:
+        """Average device time of one launch of fn(i, stream): `reps` launches captured into a CUDA graph, the replay
+        bracketed by events on the launching stream -- the kernel's duration plus the device-side launch gap, not the
+        interval at which Python can issue ctypes calls."""
+        torch = self.torch
+        st = torch.cuda.current_stream().cuda_stream
+        for i in range(N_ROTATE):
+            fn(i, st)
+        self.sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                cs = torch.cuda.current_stream().cuda_stream
+                for i in range(reps):
+                    fn(i, cs)
+            g.replay()
+            torch.cuda.synchronize()
+            e0.record()
+            g.replay()
+            e1.record()
+        except RuntimeError:
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(reps):
+                fn(i, st)
+            e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def _issue_roofline(ctx, kernel: str, ms: float) -> dict:
+    """Instruction-issue roofline of a latency / ALU-bound kernel: executed warp instructions per launch (ncu
+    smsp__inst_executed.sum of the committed capture: same kernel, same inputs, deterministic) / live duration, against
+    148 SMs x 4 schedulers x SM clock."""
+    c = profile_counters(kernel)
+    inst = c.get("inst_executed")
+    peak = 148 * 4 * ctx.sm_mhz * 1e6 / 1e9      # G warp-instructions / s
+    ach = inst / (ms * 1e-3) / 1e9 if inst else None
+    return {"kernel": kernel, "bound": "issue", "achieved": ach, "peak": peak, "unit": "Gwarp-inst/s",
+            "frac": (ach / peak) if ach else None, "traffic": ncu_traffic(kernel),
+            "inst_executed_per_launch": inst, "peak_source": f"148 SM x 4 schedulers x {ctx.sm_mhz:.0f} MHz",
+            "note": "neither HBM- nor tensor-bound: ~0.2 MB of boxes per image; see DESIGN.md 4.3"}
+
+
+def _hbm_roofline(ctx, kernel: str, nbytes: float, ms: float, **extra) -> dict:
+    ach = nbytes / (ms * 1e-3) / 1e9
+    d = {"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": ctx.peak, "unit": "GB/s", "frac": ach / ctx.peak,
+         "traffic": ncu_traffic(kernel), "peak_source": ctx.peak_how, "bytes_per_launch": nbytes}
+    d.update(extra)
+    return d
+
+
+# ------------------------------------------------------------------------------------------ configs[1]
+def verify_proposals(plan, rois, count, images) -> bool:
+    """Outside every timed region: the given images of the plan's last run against the oracle fed the GPU's own decoded
+    boxes / scores (index-valued stages from identical fp32 inputs)."""
+    from oracle import region_oracle as orc, _cbridge
+    _cbridge.load(required=True)
+    it = plan.intermediates()
+    rois_h, count_h = rois.cpu().numpy(), count.cpu().numpy()
+    ok = True
+    for i in images:
+        boxes = it["boxes"][i].cpu().numpy()
+        valid = it["valid"][i].cpu().numpy().astype(bool)
+        sc = it["scores"][i].cpu().numpy()
+        ok &= bool(np.array_equal(valid, orc.min_size_mask(boxes)))
+        src = np.nonzero(valid)[0]
+        order = src[orc.sort_desc(sc[valid])[:plan.pre_k]]
+        n = len(order)
+        ok &= int(it["top_count"][i]) == n and bool(np.array_equal(it["top_idx"][i, :n].cpu().numpy(), order))
+        tb = boxes[order]
+        want = orc.nms(tb, -np.arange(n, dtype=np.float32), plan.thr)[:plan.post_k]
+        c = int(count_h[i])
+        ok &= c == len(want) and bool(np.array_equal(it["keep"][i, :c].cpu().numpy(), want))
+        ok &= bool(np.array_equal(rois_h[i, :c], tb[want]))
+    return bool(ok)
+
+
+def run_rpn(ctx, args) -> dict:
+    torch = ctx.torch
+    from faster_rcnn_pytorch_b200 import ops, region, synth
+    _lib, lib, dev, world, rank = ctx._lib, ctx.lib, ctx.dev, ctx.world, ctx.rank
     n = synth.num_anchors(HW)
     B = args.batch
     # resident inputs: N_ROTATE different batches, cycled, so each step's 33 MB of inputs is cold in L2
@@ -189,37 +425,13 @@ def run_ours(args):
         lg, rg = sets[i % N_ROTATE]
         return plan.run(lg, rg)
 
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def timed(fn, steps, tail=None):
-        sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            fn(i)
-        if tail is not None:
-            tail()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        sync_all()
-        return ms
-
     for i in range(max(args.warmup, 3)):
         step(i)
     l0 = _lib.launch_count()
     step(0)
     launches_per_step = _lib.launch_count() - l0          # kernels of one frr_rpn_proposals call
     # the step as the library is meant to be driven: the one C-ABI call (it neither allocates nor synchronises) is
-    # captured once per resident input set and replayed -- one graph launch per step instead of four kernel launches
+    # captured once per resident input set and replayed -- one graph launch per step instead of three kernel launches
     graphs = None
     if not args.eager:
         try:
@@ -233,11 +445,16 @@ def run_ours(args):
     run_step = step_graph if graphs else step
     for i in range(max(args.warmup, 3)):
         run_step(i)
-    sampler = ClockSampler(local) if rank == 0 else None
-    ms = timed(run_step, args.steps)
+    ms = ctx.timed(run_step, args.steps)
     launches = launches_per_step * args.steps
     value = world * B * args.steps / (ms * 1e-3)
-    ms_eager = timed(step, args.steps) if graphs else ms
+    ms_eager = ctx.timed(step, args.steps) if graphs else ms
+
+    # ---- parity of the timed path, outside the timed region: first and last image of one batch vs the oracle
+    run_step(0)
+    torch.cuda.synchronize()
+    verified = verify_proposals(plan, plan.rois, plan.count, (0, B - 1)) if rank == 0 else None
+    variant = ops.nms_variant(B, PRE_K, THR, POST_K, unit_boxes=True, device=dev)
 
     # ---- end to end through the public host-buffer API: pinned host inputs -> H2D -> proposal layer -> D2H of
     #      rois + counts, EVERY step; double buffered (copies of step i+1 overlap the kernels of step i) and,
@@ -265,17 +482,32 @@ def run_ours(args):
     e2e_steps = max(3, min(args.steps, 30))
     for i in range(3):
         e2e_serial(i)
-    ms_e2e_serial = timed(e2e_serial, e2e_steps)
+    ms_e2e_serial = ctx.median_ms(e2e_serial, e2e_steps, runs=3)
     for i in range(3):
         e2e_pipelined(i)
     e2e_drain()
-    # two runs, the faster one is reported: a run is ~20 ms of PCIe traffic and one descheduled host thread shows
-    ms_e2e = min(timed(e2e_pipelined, e2e_steps, tail=e2e_drain), timed(e2e_pipelined, e2e_steps, tail=e2e_drain))
+    ms_e2e = ctx.median_ms(e2e_pipelined, e2e_steps, runs=5, tail=e2e_drain)
     e2e_value = world * B * e2e_steps / (ms_e2e * 1e-3)
+
+    # the host-side ceiling of that pipeline: the same pinned H2D / D2H traffic on the same streams with no kernel between
+    d_l = torch.empty_like(sets[0][0]); d_r = torch.empty_like(sets[0][1])
+    h_out = torch.empty((B, POST_K, 4), dtype=torch.float32).pin_memory()
+    cstream = torch.cuda.Stream(device=dev)
+
+    def copy_only(i):
+        with torch.cuda.stream(cstream):
+            d_l.copy_(h_in[i % 2][0], non_blocking=True)
+            d_r.copy_(h_in[i % 2][1], non_blocking=True)
+            h_out.copy_(plan.rois, non_blocking=True)
+
+    def copy_tail():
+        cstream.synchronize()
+
+    ms_copy = ctx.median_ms(copy_only, e2e_steps, runs=3, tail=copy_tail)
+    copy_value = world * B * e2e_steps / (ms_copy * 1e-3)
 
     # ---- per-kernel timing on the launching stream (live, CUDA events): raw C-ABI launches into preallocated
     #      buffers (no allocator in the timed loop), inputs rotated as above
-    st = torch.cuda.current_stream().cuda_stream
     d_boxes = [torch.empty((B, n, 4), dtype=torch.float32, device=dev) for _ in range(N_ROTATE)]
     d_scores = [torch.empty((B, n), dtype=torch.float32, device=dev) for _ in range(N_ROTATE)]
     d_valid = [torch.empty((B, n), dtype=torch.uint8, device=dev) for _ in range(N_ROTATE)]
@@ -286,321 +518,464 @@ def run_ours(args):
     rois = torch.empty((B, POST_K, 4), dtype=torch.float32, device=dev)
     minsz = float(np.float32(1.0 / 1000.0))
 
-    def k_decode(i, st=st):
+    def k_decode(i, st):
         r = i % N_ROTATE
         _lib.check(lib.frr_rpn_decode(sets[r][1].data_ptr(), sets[r][0].data_ptr(), 1, None, None, 9, HW[0], HW[1], 16,
                                       minsz, d_boxes[r].data_ptr(), d_scores[r].data_ptr(), d_valid[r].data_ptr(), B, n,
                                       st), "frr_rpn_decode")
 
-    def k_topk(i, st=st):
+    def k_topk(i, st):
         r = i % N_ROTATE
         _lib.check(lib.frr_topk_desc(d_scores[r].data_ptr(), d_valid[r].data_ptr(), None, B, n, PRE_K,
                                      None, t_idx[r].data_ptr(), None, None, t_cnt[r].data_ptr(), st),
                    "frr_topk_desc")
 
-    def k_nms(i, st=st):
+    def k_nms(i, st):
         r = i % N_ROTATE
         _lib.check(lib.frr_nms_sorted_indirect(d_boxes[r].data_ptr(), n, t_idx[r].data_ptr(), t_cnt[r].data_ptr(), B, PRE_K,
                                                THR, POST_K, keep.data_ptr(), kcnt.data_ptr(), rois.data_ptr(), 0, 1, st),
                    "frr_nms_sorted_indirect")
 
-    def time_kernel(fn, reps):
-        """Average device time of one launch: `reps` launches over the rotated inputs are captured into a CUDA graph and
-        the replay is bracketed by events on the launching stream, so the figure is the kernel's duration (plus the
-        device-side launch gap), not the interval at which Python can issue ctypes calls (~10 us, close to the
-        duration of the decode kernel itself)."""
-        for i in range(N_ROTATE):
-            fn(i)
-        sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        try:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                cs = torch.cuda.current_stream().cuda_stream
-                for i in range(reps):
-                    fn(i, cs)
-            g.replay()
-            torch.cuda.synchronize()
-            e0.record()
-            g.replay()
-            e1.record()
-        except RuntimeError:
-            torch.cuda.synchronize()
-            e0.record()
-            for i in range(reps):
-                fn(i)
-            e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / reps
-
     reps = max(16, min(args.steps, 64))
-    ms_dec = time_kernel(k_decode, reps)
-    ms_topk = time_kernel(k_topk, reps)
-    ms_nms = time_kernel(k_nms, reps)
+    ms_dec = ctx.kernel_ms(k_decode, reps)
+    ms_topk = ctx.kernel_ms(k_topk, reps)
+    ms_nms = ctx.kernel_ms(k_nms, reps)
     # single-image NMS latency (whole GPU available to one image: clusters of 8 / 16 CTAs)
     one_src = d_boxes[0][:1].contiguous()
     one_idx = t_idx[0][:1].contiguous()
     one_c = t_cnt[0][:1].contiguous()
     ms_nms1 = {}
     for cs in (8, 16):
-        def k_one(i, st=st, cs=cs):
+        def k_one(i, st, cs=cs):
             _lib.check(lib.frr_nms_sorted_indirect(one_src.data_ptr(), n, one_idx.data_ptr(), one_c.data_ptr(), 1, PRE_K, THR,
                                                    POST_K, keep.data_ptr(), kcnt.data_ptr(), rois.data_ptr(), cs, 1, st),
                        "frr_nms_sorted_indirect")
-        ms_nms1[cs] = time_kernel(k_one, 50)
-    clocks = sampler.stop() if sampler else None
+        ms_nms1[cs] = ctx.kernel_ms(k_one, 50)
 
-    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        threads = os.cpu_count() or 1
-        sample = max(threads, 8) * 4        # ~20 CPU-seconds of work
-        v, dt = cpu_images_per_s(sample, threads)
-        cpu = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
-               "sample": f"{sample} images of the same workload (seeds 2000..), oracle port: numpy decode/sort + C NMS, "
-                         f"one image per thread, {dt:.1f} s wall"}
-
-    if rank == 0:
-        peak, how = peaks()
-        dec_bytes = B * n * 44.0                      # SURVEY §8d: reg 16 + logits 8 + box 16 + score 4 per anchor
-        topk_bytes = B * (n * 5.0 + PRE_K * 4.0)      # scores 4 + valid 1 per anchor; sorted index 4 per pick (NMS gathers)
-        line = {
-            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "images_per_gpu_per_step": B, "anchors_per_image": n,
-                       "l2": f"inputs rotated over {N_ROTATE} resident batches ({N_ROTATE * B * n * 24 / 1e6:.0f} MB > 126 MB L2)"},
-            "launch_mode": "cuda-graph replay of one frr_rpn_proposals call per step" if graphs else "eager C-ABI call per step",
-            "value_eager": world * B * args.steps / (ms_eager * 1e-3),
-            "nms_us_per_image": 1e3 * ms_nms / B,
-            "nms_single_image_latency_us": {f"cluster{cs}": 1e3 * v for cs, v in ms_nms1.items()},
-            "kernels_ms_per_batch": {"rpn_decode": ms_dec, "topk_desc": ms_topk, "nms_keeplist": ms_nms},
-            "kernels_hbm_frac": {"rpn_decode": dec_bytes / (ms_dec * 1e-3) / 1e9 / peak,
-                                 "topk_desc": topk_bytes / (ms_topk * 1e-3) / 1e9 / peak},
-            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": pipe.h2d_bytes,
-                    "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": ms_e2e / e2e_steps,
-                    "mode": "double-buffered host pipeline (H2D of step i+1 overlaps kernels of step i), best of 2 runs",
-                    "serialized_value": world * B * e2e_steps / (ms_e2e_serial * 1e-3)},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            # dominant kernel by time is the NMS keep-list kernel: latency / issue bound, not HBM- or tensor-bound
-            # (see DESIGN.md); its HBM traffic is ~0.2 MB/image.  The HBM roofline entry is the decode kernel.
-            "roofline": {"kernel": "rpn_decode_kernel", "bound": "hbm", "achieved": dec_bytes / (ms_dec * 1e-3) / 1e9,
-                         "peak": peak, "unit": "GB/s", "frac": dec_bytes / (ms_dec * 1e-3) / 1e9 / peak,
-                         "traffic": ncu_traffic("rpn_decode_kernel"), "peak_source": how, "bytes_per_launch": dec_bytes,
-                         "traffic_note": "ncu dram read+write of one launch; below the algorithmic bytes because the "
-                                         "28 MB of outputs stay in the 126 MB L2 for the top-k / NMS kernels"},
-            "dominant_kernel": {"kernel": "nms_keeplist_kernel", "share_of_step": ms_nms / (ms / args.steps),
-                                "bound": "latency of the per-chunk phase chain + issue of the pair screen (not HBM or tensor): see profiles/ and DESIGN.md 4.3"},
-            "cpu_baseline": cpu,
-        }
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    dec_bytes = B * n * 44.0                      # reg 16 + logits 8 + box 16 + score 4 per anchor
+    topk_bytes = B * (n * 5.0 + PRE_K * 4.0)      # scores 4 + valid 1 per anchor; sorted index 4 per pick (NMS gathers)
+    kern = {"rpn_decode_kernel": ms_dec, "topk_bucket_kernel": ms_topk, "nms_bucket_kernel": ms_nms}
+    dominant = max(kern, key=kern.get)
+    roof = {
+        "rpn_decode_kernel": _hbm_roofline(ctx, "rpn_decode_kernel", dec_bytes, ms_dec,
+                                           traffic_note="ncu dram read+write of one launch; below the algorithmic bytes because "
+                                                        "the 28 MB of outputs stay in the 126 MB L2 for the top-k / NMS kernels"),
+        "topk_bucket_kernel": _hbm_roofline(ctx, "topk_bucket_kernel", topk_bytes, ms_topk),
+        "nms_bucket_kernel": _issue_roofline(ctx, "nms_bucket_kernel", ms_nms),
+    }
+    step_ms = ms / args.steps
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(config_of(WORKLOAD, B), anchors_per_image=n,
+                       l2=f"inputs rotated over {N_ROTATE} resident batches ({N_ROTATE * B * n * 24 / 1e6:.0f} MB > 126 MB L2)"),
+        "launch_mode": "cuda-graph replay of one frr_rpn_proposals call per step" if graphs else "eager C-ABI call per step",
+        "value_eager": world * B * args.steps / (ms_eager * 1e-3),
+        "verified": verified,
+        "verified_how": "images 0 and 63 of a timed batch: valid mask, top-k order, NMS keep list, count and rois bit-exact vs "
+                        "the CPU oracle fed the GPU's decoded boxes (outside the timed region)",
+        "nms_variant": variant,
+        "nms_us_per_image": 1e3 * ms_nms / B,
+        "nms_single_image_latency_us": {f"cluster{cs}": 1e3 * v for cs, v in ms_nms1.items()},
+        "kernels_ms_per_batch": kern,
+        "kernels_share_of_step": {k: v / step_ms for k, v in kern.items()},
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": pipe.h2d_bytes,
+                "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": ms_e2e / e2e_steps,
+                "mode": "double-buffered host pipeline (H2D of step i+1 overlaps kernels of step i), median of 5 runs",
+                "serialized_value": world * B * e2e_steps / (ms_e2e_serial * 1e-3),
+                "host_copy_ceiling": copy_value, "frac_of_host_copy_ceiling": e2e_value / copy_value,
+                "host_copy_ceiling_how": "the same pinned H2D (33 MB) + D2H (2 MB) per step on a copy stream, no kernels"},
+        "gpu_launches": int(launches),
+        "roofline": roof[dominant],
+        "roofline_other": {k: v for k, v in roof.items() if k != dominant},
+        "dominant_kernel": {"kernel": dominant, "share_of_step": kern[dominant] / step_ms},
+    }
+    return line
 
 
-# ------------------------------------------------------------------------------------------ other workloads
-def _events_ms(torch, fn, steps, sync):
-    sync()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        fn(i)
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1)
-
-
-def run_extra(args):
-    """configs[2] (--workload train): target makers + RoIPool 7x7 fwd/bwd, batch 16 @600x1000, 128 RoIs/image;
-    configs[3] (--workload infer): COCO-shaped 800x1333 inference, 8 images/GPU: proposals (6000 -> 300), RoIPool of
-    300 RoIs, per-class decode, 80-class NMS, detections all-gathered over NCCL when N > 1.
-    Prints one JSON line in the same format (these are not the driver's default line)."""
-    import torch
-    import torch.distributed as dist
-    from faster_rcnn_pytorch_b200 import _lib, ops, region, synth, targets, dist as fdist
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    _lib.load()
-    peak, how = peaks()
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def maxms(ms):
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        return ms
-
-    rs = np.random.RandomState(9000 + rank)
+# ------------------------------------------------------------------------------------------ configs[0] / configs[3]
+def _predict_setup(ctx, hw, B, R, NC, seed, n_sets):
+    torch = ctx.torch
+    from faster_rcnn_pytorch_b200 import region, synth
+    dev = ctx.dev
+    fh, fw = hw[0] // 16, hw[1] // 16
+    n = synth.num_anchors(hw)
+    rs = np.random.RandomState(seed + ctx.rank)
     C = 512
+    h = dict(
+        feats=[rs.standard_normal((B, C, fh, fw)).astype(np.float32) for _ in range(n_sets)],
+        lgs=[rs.standard_normal((B, n, 2)).astype(np.float32) for _ in range(n_sets)],
+        rgs=[(rs.standard_normal((B, n, 4)) * 0.2).astype(np.float32) for _ in range(n_sets)],
+        hcls=rs.standard_normal((B * R, NC)).astype(np.float32),          # head outputs (the FC head is cuBLAS,
+        hreg=rs.standard_normal((B * R, 4 * NC)).astype(np.float32))      # not the product)
+    d = {k: ([torch.from_numpy(x).to(dev) for x in v] if isinstance(v, list) else torch.from_numpy(v).to(dev))
+         for k, v in h.items()}
+    plan = region.ProposalPlan(B, n, dev, image_hw=hw, mode="test")
+    return h, d, plan, (fh, fw), n
+
+
+def _predict_step(ops, fdist, plan, feat, lg, rg, hcls, hreg, fhw, B, R, NC, ids=None, gather=False):
+    """FRCNN.predict's region path for a batch (models/model.py:346-402): proposals -> rois5 -> RoIPool -> per-class decode
+    -> per-class NMS -> packed detections [B,100,6] (+ NCCL all-gather)."""
+    rois, cnt = plan.run(lg, rg)
+    rois5 = ops.rois5(rois, cnt, fhw)
+    pooled, _ = ops.roi_pool_forward(feat, rois5, want_argmax=False)
+    prob, boxes = ops.decode_classwise(hcls, hreg, rois.reshape(-1, 4), NC)
+    db, dl, ds, dc = ops.class_nms(prob.reshape(B, R, NC), boxes.reshape(B, R, 4 * NC), NC, score_thres=0.05, roi_count=cnt)
+    packed, pc = fdist.pack_detections(db, dl, ds, dc, 100)
+    if gather:
+        packed, pc, _ = fdist.gather_detections(packed, pc, ids, equal_batch=True)
+    return dict(rois=rois, cnt=cnt, rois5=rois5, pooled=pooled, prob=prob, boxes=boxes, det=(db, dl, ds, dc), packed=packed, pc=pc)
+
+
+def verify_predict(out, feat, image: int, R: int, NC: int, fhw) -> bool:
+    """One image of the last step against the oracle, stage by stage on the GPU's own inputs: RoIPool max bit-exact on
+    the GPU's rois, per-class NMS detections bit-exact on the GPU's probabilities / decoded boxes."""
+    from oracle import region_oracle as orc, _cbridge
+    _cbridge.load(required=True)
+    c = int(out["cnt"][image])
+    rois = out["rois"][image, :c].cpu().numpy()
+    f = feat[image:image + 1, :32].contiguous().cpu().numpy()                 # 32 of the 512 channels
+    want, _ = orc.roi_pool_forward(f, orc.scale_rois(rois, fhw[0], fhw[1]))
+    got = out["pooled"][image * R:image * R + c, :32].cpu().numpy()
+    ok = bool(np.array_equal(got, want))
+    prob = out["prob"].reshape(-1, R, NC)[image, :c].cpu().numpy()
+    boxes = out["boxes"].reshape(-1, R, 4 * NC)[image, :c].cpu().numpy()
+    wb, wl, ws = orc.suppress(boxes, prob, NC, 0.05)
+    db, dl, ds, dc = out["det"]
+    k = int(dc[image])
+    ok &= k == len(wl) and bool(np.array_equal(db[image, :k].cpu().numpy(), wb)) and \
+        bool(np.array_equal(dl[image, :k].cpu().numpy(), wl)) and bool(np.array_equal(ds[image, :k].cpu().numpy(), ws))
+    return bool(ok)
+
+
+def run_predict(ctx, args, which: str) -> dict:
+    """configs[0] (`voc1`: 1 image 600x1000, 21 classes, latency) and configs[3] (`infer`: 8 images 800x1333, 81 classes,
+    detections all-gathered over NCCL)."""
+    torch = ctx.torch
+    from faster_rcnn_pytorch_b200 import ops, dist as fdist
+    voc = which == "voc1"
+    hw, B, R, NC = ((600, 1000), 1, 300, 21) if voc else ((800, 1333), 8, 300, 81)
+    NR = 4
+    h, d, plan, fhw, n = _predict_setup(ctx, hw, B, R, NC, 9100 if voc else 9000, NR)
+    ids = torch.arange(ctx.rank * B, (ctx.rank + 1) * B, dtype=torch.int64, device=ctx.dev)
+    keep = {}
+    steps = max(5, min(args.steps, 50))
+    gather = (not voc) and ctx.world > 1
+
+    def step(i, gather=gather):
+        r = i % NR
+        keep["out"] = _predict_step(ops, fdist, plan, d["feats"][r], d["lgs"][r], d["rgs"][r], d["hcls"], d["hreg"], fhw, B, R, NC,
+                                    ids, gather)
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    l0 = ctx._lib.launch_count()
+    step(0)
+    launches_per_step = ctx._lib.launch_count() - l0
+    ms = ctx.timed(step, steps)
+    ms_nogather = ctx.timed(lambda i: step(i, False), steps) if gather else ms
+    torch.cuda.synchronize()
+    verified = verify_predict(keep["out"], d["feats"][(steps - 1) % NR], B - 1, R, NC, fhw) if ctx.rank == 0 else None
+
+    # graph-replayed step (the kernels + torch's allocations are captured once per input set; NCCL stays outside)
+    graphs = []
+    if not args.eager:
+        for r in range(NR):
+            g, out = ctx.graph_of(lambda r=r: _predict_step(ops, fdist, plan, d["feats"][r], d["lgs"][r], d["rgs"][r], d["hcls"],
+                                                            d["hreg"], fhw, B, R, NC))
+            if g is None:
+                graphs = []
+                break
+            graphs.append((g, out))
+
+    def step_graph(i):
+        g, out = graphs[i % NR]
+        g.replay()
+        if gather:
+            keep["g"] = fdist.gather_detections(out["packed"], out["pc"], ids, equal_batch=True)
+
+    ms_graph = ctx.timed(step_graph, steps) if graphs else None
+    best = min(ms, ms_graph) if ms_graph else ms
+    value = ctx.world * B * steps / (best * 1e-3)
+
+    # ---- end to end, strict form: EVERY input of the step from pinned host memory (head outputs, feature map, FC head
+    #      outputs), the packed detections read back on the host, every step, serialised (latency form)
+    pin = {k: ([torch.from_numpy(x).pin_memory() for x in v] if isinstance(v, list) else torch.from_numpy(v).pin_memory())
+           for k, v in h.items()}
+    dd = dict(feat=torch.empty_like(d["feats"][0]), lg=torch.empty_like(d["lgs"][0]), rg=torch.empty_like(d["rgs"][0]),
+              hcls=torch.empty_like(d["hcls"]), hreg=torch.empty_like(d["hreg"]))
+    nrows = B * (ctx.world if gather else 1)
+    h_det = torch.empty((nrows, 100, 6), dtype=torch.float32).pin_memory()
+    h_cnt = torch.empty((nrows,), dtype=torch.int32).pin_memory()
+    sink = [0]
+
+    def e2e_host(i):
+        r = i % NR
+        dd["feat"].copy_(pin["feats"][r], non_blocking=True)
+        dd["lg"].copy_(pin["lgs"][r], non_blocking=True)
+        dd["rg"].copy_(pin["rgs"][r], non_blocking=True)
+        dd["hcls"].copy_(pin["hcls"], non_blocking=True)
+        dd["hreg"].copy_(pin["hreg"], non_blocking=True)
+        out = _predict_step(ops, fdist, plan, dd["feat"], dd["lg"], dd["rg"], dd["hcls"], dd["hreg"], fhw, B, R, NC, ids, gather)
+        h_det.copy_(out["packed"], non_blocking=True)
+        h_cnt.copy_(out["pc"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        sink[0] += int(h_cnt[0])
+
+    def e2e_resident(i):
+        # the reference keeps backbone + heads on the device (models/model.py:315,352): only the detections cross PCIe
+        if graphs:
+            g, out = graphs[i % NR]
+            g.replay()
+            if gather:
+                p, c, _ = fdist.gather_detections(out["packed"], out["pc"], ids, equal_batch=True)
+            else:
+                p, c = out["packed"], out["pc"]
+        else:
+            step(i)
+            p, c = keep["out"]["packed"], keep["out"]["pc"]
+        h_det.copy_(p, non_blocking=True)
+        h_cnt.copy_(c, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        sink[0] += int(h_cnt[0])
+
+    for i in range(3):
+        e2e_host(i); e2e_resident(i)
+    e_steps = max(5, min(steps, 20))
+    ms_e2e = ctx.median_ms(e2e_host, e_steps, runs=3)
+    ms_e2r = ctx.median_ms(e2e_resident, e_steps, runs=3)
+    h2d = sum(int(np.prod(x.shape)) * 4 for x in (h["feats"][0], h["lgs"][0], h["rgs"][0], h["hcls"], h["hreg"]))
+    d2h = nrows * 100 * 6 * 4 + nrows * 4
+    pooled_bytes = B * 512 * fhw[0] * fhw[1] * 4 + B * R * 512 * 49 * 4
+    ms_pool = ctx.kernel_ms(lambda i, st: ops.roi_pool_forward(d["feats"][i % NR], keep["out"]["rois5"], want_argmax=False), 8)
+    res = {
+        "value": value, "unit": "images/s", "ms_per_step": best / steps, "steps": steps,
+        "latency_us_per_step": 1e3 * best / steps,
+        "config": dict(config_of(W_VOC1 if voc else W_INFER, B), l2=f"inputs rotated over {NR} resident sets"),
+        "launch_mode": "cuda-graph replay of the region path" if (ms_graph and ms_graph <= ms) else "eager ops calls",
+        "ms_per_step_eager": ms / steps, "ms_per_step_graph": (ms_graph / steps) if ms_graph else None,
+        "gpu_launches_per_step": int(launches_per_step), "verified": verified,
+        "verified_how": "last image of the last step: RoIPool max (32 channels) and the per-class NMS detections bit-exact vs the "
+                        "CPU oracle on the GPU's own rois / probabilities / decoded boxes",
+        "e2e": {"value": ctx.world * B * e_steps / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / e_steps,
+                "mode": "every input of the step (RPN head outputs, 512-ch feature map, FC head outputs) from pinned host memory, "
+                        "packed detections read back, serialised, median of 3 runs"},
+        "e2e_resident": {"value": ctx.world * B * e_steps / (ms_e2r * 1e-3), "unit": "images/s", "h2d_bytes_per_step": 0,
+                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2r / e_steps,
+                         "mode": "backbone / head outputs resident on the device as in the reference (models/model.py:315,352), "
+                                 "packed detections [B,100,6] + counts read back on the host every step"},
+        "roofline": _hbm_roofline(ctx, "roi_pool_fwd_flat_kernel", pooled_bytes, ms_pool,
+                                  note="RoIPool forward without argmax: features once + pooled output once"),
+        "detections_last_step": int(keep["out"]["pc"].sum()),
+    }
+    if gather:
+        res["collective"] = {"what": "NCCL all_gather_into_tensor of [B,100,6] fp32 + int32 counts + int64 ids (replaces the "
+                                     "pickled all_gather of util/misc.py:89-129)",
+                             "bytes_per_rank": B * 100 * 6 * 4 + B * 4 + B * 8,
+                             "ms_per_step_with": ms / steps, "ms_per_step_without": ms_nogather / steps,
+                             "exposed_ms_per_step": max(0.0, (ms - ms_nogather) / steps)}
+    return res
+
+
+# ------------------------------------------------------------------------------------------ configs[2]
+def run_train(ctx, args) -> dict:
+    torch = ctx.torch
+    from faster_rcnn_pytorch_b200 import ops, region, synth, targets
+    dev, rank, world = ctx.dev, ctx.rank, ctx.world
+    hw, B, G, per, C = (600, 1000), 16, 8, 128, 512
+    fh, fw = hw[0] // 16, hw[1] // 16
+    n = synth.num_anchors(hw)
+    rs = np.random.RandomState(9000 + rank)
+    NR = 3   # rotated input sets: 3 x (75 MB features + 206 MB grad_out) > L2
+    feats = [torch.from_numpy(rs.standard_normal((B, C, fh, fw)).astype(np.float32)).to(dev) for _ in range(NR)]
+    gouts = [torch.from_numpy(rs.standard_normal((B * per, C, 7, 7)).astype(np.float32)).to(dev) for _ in range(NR)]
+    lg = torch.from_numpy(rs.standard_normal((B, n, 2)).astype(np.float32)).to(dev)
+    rg = torch.from_numpy((rs.standard_normal((B, n, 4)) * 0.2).astype(np.float32)).to(dev)
+    gt_h = np.stack([synth.gt_boxes(3000 + 100 * rank + i, G)[0] for i in range(B)])
+    lab_h = np.stack([synth.gt_boxes(3000 + 100 * rank + i, G)[1] for i in range(B)])
+    gt, lab = torch.from_numpy(gt_h).to(dev), torch.from_numpy(lab_h).to(dev)
+    props, pcnt = region.rpn_proposals(lg, rg, image_hw=hw, mode="train")     # config-2 pipeline proposals
+    torch.manual_seed(3000 + rank)
+    gen = targets.DeviceGenerator(dev) if args.sampling == "device" else None    # torch's mt19937 stream on the device
+    stats = {}
+    steps = max(5, min(args.steps, 30))
+
+    def step(i, gt=gt, lab=lab):
+        # device sampling: 6 kernels, no host synchronisation; host sampling: 4 kernels + ONE D2H of counts
+        t = targets.make_targets(gt, None, lab, props, pcnt, image_hw=hw, generator=gen)
+        ns = t["n_samples"] if isinstance(t["n_samples"], torch.Tensor) else None
+        rois5 = ops.rois5(t["sample_rois"], ns, (fh, fw))
+        out, arg = ops.roi_pool_forward(feats[i % NR], rois5)
+        gin = ops.roi_pool_backward(gouts[i % NR], arg, rois5, feats[0].shape)
+        stats["last"] = (out, gin, rois5, arg, t, i % NR)
+        return gin
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    l0 = ctx._lib.launch_count()
+    step(0)
+    launches_per_step = ctx._lib.launch_count() - l0
+    ms = ctx.timed(step, steps)
+    torch.cuda.synchronize()
+    out, gin, rois5, arg, t, r_last = stats["last"]
+
+    verified = None
+    if rank == 0:   # image 0 of the last step: RoIPool forward (max + argmax) bit-exact, backward within 1e-5 of max|grad|
+        from oracle import region_oracle as orc, _cbridge
+        _cbridge.load(required=True)
+        r5 = rois5[:per].cpu().numpy()
+        live = r5[:, 0] >= 0
+        f = feats[r_last][:1, :16].contiguous().cpu().numpy()
+        wo, wa = orc.roi_pool_forward(f, r5[live])
+        verified = bool(np.array_equal(out[:per][torch.from_numpy(live).to(dev)][:, :16].cpu().numpy(), wo)) and \
+            bool(np.array_equal(arg[:per][torch.from_numpy(live).to(dev)][:, :16].cpu().numpy(), wa))
+        # labels: the reference's invariants (<= 128 positives, 256 sampled in total when enough candidates)
+        lbl = t["rpn_cls"][0].cpu().numpy()
+        verified &= int((lbl == 1).sum()) <= 128 and int((lbl >= 0).sum()) == 256
+
+    obytes = B * per * C * 49 * 4
+    fbytes = B * C * fh * fw * 4
+    ms_f = ctx.kernel_ms(lambda i, st: ops.roi_pool_forward(feats[i % NR], rois5), 12)
+    ms_b = ctx.kernel_ms(lambda i, st: ops.roi_pool_backward(gouts[i % NR], arg, rois5, feats[0].shape), 12)
+    gen2 = targets.DeviceGenerator(dev)
+    ms_td = ctx.timed(lambda i: targets.make_targets(gt, None, lab, props, pcnt, image_hw=hw, generator=gen2), 12) / 12
+    ms_th = ctx.timed(lambda i: targets.make_targets(gt, None, lab, props, pcnt, image_hw=hw), 12) / 12
+
+    # ---- end to end: what crosses PCIe in the reference's training step for this stage is the ground truth (boxes +
+    #      labels, from the data loader, main.py:66-75) going in and nothing coming out (targets feed the loss on the
+    #      device); here the sampled class targets + sample counts are read back every step as the step's result
+    h_gt = torch.from_numpy(gt_h).pin_memory()
+    h_lab = torch.from_numpy(lab_h).pin_memory()
+    d_gt, d_lab = torch.empty_like(gt), torch.empty_like(lab)
+    h_cls = torch.empty((B, per), dtype=torch.int64).pin_memory()
+    sink = [0]
+
+    def e2e(i):
+        d_gt.copy_(h_gt, non_blocking=True)
+        d_lab.copy_(h_lab, non_blocking=True)
+        step(i, d_gt, d_lab)
+        h_cls.copy_(stats["last"][4]["frcnn_cls"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        sink[0] += int(h_cls[0, 0])
+
+    for i in range(3):
+        e2e(i)
+    e_steps = max(5, min(steps, 20))
+    ms_e2e = ctx.median_ms(e2e, e_steps, runs=3)
+    fb = fbytes + 2 * obytes
+    return {
+        "value": world * B * steps / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms / steps, "steps": steps,
+        "config": dict(config_of(W_TRAIN, B), l2=f"features / grad_out rotated over {NR} resident sets (> 126 MB L2)"),
+        "kernels_ms_per_batch": {"roi_pool_fwd": ms_f, "roi_pool_bwd": ms_b,
+                                 "make_targets(device sampling: 6 kernels, no sync)": ms_td,
+                                 "make_targets(host sampling: 4 kernels + D2H + randperm + H2D)": ms_th},
+        "sampling": args.sampling, "gpu_launches_per_step": int(launches_per_step), "verified": verified,
+        "verified_how": "image 0 of the last step: RoIPool max + argmax (16 channels) bit-exact vs the CPU oracle on the GPU's "
+                        "sampled rois; sampling invariants of the RPN labels",
+        "e2e": {"value": world * B * e_steps / (ms_e2e * 1e-3), "unit": "images/s",
+                "h2d_bytes_per_step": int(gt_h.nbytes + lab_h.nbytes), "d2h_bytes_per_step": B * per * 8,
+                "ms_per_step": ms_e2e / e_steps,
+                "mode": "ground-truth boxes + labels from pinned host memory, sampled class targets read back, every step, "
+                        "serialised; features / grad_out resident (backbone and head backward run on the device, "
+                        "models/model.py:315)"},
+        "roofline": _hbm_roofline(ctx, "roi_pool_fwd_flat_kernel", fb, ms_f),
+        "roofline_bwd": _hbm_roofline(ctx, "roi_pool_bwd_fast_kernel", fb, ms_b),
+    }
+
+
+# ------------------------------------------------------------------------------------------ configs[4]
+def run_joint(ctx, args) -> dict:
+    """Approximate joint training step, 4 images/GPU at 600x1000: VGG16 backbone + FC head on torch / cuDNN / cuBLAS under DDP
+    (NCCL all-reduce of the 548 MB of fp32 gradients), region stage = libfrr."""
+    torch = ctx.torch
+    from faster_rcnn_pytorch_b200 import targets
+    sys.path.insert(0, os.path.join(REPO, "tools"))
+    import frcnn_harness as fh_
+    dev, rank, world, local = ctx.dev, ctx.rank, ctx.world, ctx.local
+    hw, B, G = (600, 1000), 4, 8
+    torch.manual_seed(1234)
+    model = fh_.FRCNNTrain(21).to(dev).to(memory_format=torch.channels_last)
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
+    opt = torch.optim.SGD(net.parameters(), lr=1e-3, momentum=0.9)
+    torch.manual_seed(4000 + rank)
+    gen = targets.DeviceGenerator(dev)
+    batches = [fh_.make_batch(B, hw, G, dev, seed=10 * rank + i) for i in range(3)]
+
+    def step(i):
+        x, gt, lab = batches[i % 3]
+        opt.zero_grad(set_to_none=True)
+        loss = net(x, gt, lab, gen)
+        loss[:, 0].mean().backward()
+        opt.step()
+        return loss
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    l0 = ctx._lib.launch_count()
+    ms = ctx.timed(step, args.steps)
+    launches = ctx._lib.launch_count() - l0
+    model.timer.enabled = True
+    for i in range(4):
+        step(i)
+    region_ms = model.timer.total_ms() / 4          # forward-side region calls (their backward runs inside autograd)
+    model.timer.enabled = False
+    last = step(0).detach().cpu().numpy()
+    return {
+        "metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[4]: approximate joint training step (fwd + bwd + SGD), VGG16 Faster R-CNN, 4 images/GPU "
+                               "at 600x1000, G=8; backbone/heads torch+cuDNN under DDP (NCCL), region stage libfrr",
+                   "images_per_gpu_per_step": B, "parallelism": f"dp{world}"},
+        "region_stage_forward_ms_per_step": region_ms, "region_stage_share": region_ms / (ms / args.steps),
+        "loss_last_step": [float(v) for v in last.mean(axis=0)], "gpu_launches": int(launches)}
+
+
+def _as_line(ctx, args, res: dict) -> dict:
+    """A sub-result printed on its own (`--workload voc1|train|infer`) in the line format of the contract."""
+    line = {"metric": METRIC, "n_gpus": ctx.world, "warmup": max(args.warmup, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+    line.update(res)
+    line["gpu_launches"] = int(res.get("gpu_launches_per_step", 0)) * int(res.get("steps", 0))
+    return line
+
+
+def run_ours(args):
+    ctx = Ctx()
+    sampler = ClockSampler(ctx.local) if ctx.rank == 0 else None
+    threads = os.cpu_count() or 1
+    want_cpu = ctx.rank == 0 and ctx.world == 1 and not args.no_cpu
     if args.workload == "joint":
-        # configs[4]: approximate joint training step, 4 images/GPU at 600x1000, VGG16 backbone + FC head on torch /
-        # cuDNN / cuBLAS under DDP (NCCL all-reduce of the 548 MB of fp32 gradients), region stage = libfrr
-        sys.path.insert(0, os.path.join(REPO, "tools"))
-        import frcnn_harness as fh_
-        hw, B, G = (600, 1000), 4, 8
-        torch.manual_seed(1234)
-        model = fh_.FRCNNTrain(21).to(dev).to(memory_format=torch.channels_last)
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
-        opt = torch.optim.SGD(net.parameters(), lr=1e-3, momentum=0.9)
-        torch.manual_seed(4000 + rank)
-        gen = targets.DeviceGenerator(dev)
-        batches = [fh_.make_batch(B, hw, G, dev, seed=10 * rank + i) for i in range(3)]
-
-        def step(i):
-            x, gt, lab = batches[i % 3]
-            opt.zero_grad(set_to_none=True)
-            loss = net(x, gt, lab, gen)
-            loss[:, 0].mean().backward()
-            opt.step()
-            return loss
-
-        for i in range(max(args.warmup, 3)):
-            step(i)
-        l0 = _lib.launch_count()
-        ms = maxms(_events_ms(torch, step, args.steps, sync_all))
-        launches = _lib.launch_count() - l0
-        model.timer.enabled = True
-        for i in range(4):
-            step(i)
-        region_ms = model.timer.total_ms() / 4          # forward-side region calls (their backward runs inside autograd)
-        model.timer.enabled = False
-        last = step(0).detach().cpu().numpy()
-        if rank == 0:
-            print(json.dumps({
-                "metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
-                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "configs[4]: approximate joint training step (fwd + bwd + SGD), VGG16 Faster R-CNN, 4 images/GPU "
-                                       "at 600x1000, G=8; backbone/heads torch+cuDNN under DDP (NCCL), region stage libfrr",
-                           "parallelism": f"dp{world}"},
-                "region_stage_forward_ms_per_step": region_ms, "region_stage_share": region_ms / (ms / args.steps),
-                "loss_last_step": [float(v) for v in last.mean(axis=0)], "gpu_launches": int(launches)}))
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    if args.workload == "train":
-        hw, B, G, per = (600, 1000), 16, 8, 128
-        fh, fw = hw[0] // 16, hw[1] // 16
-        n = synth.num_anchors(hw)
-        NR = 3   # rotated input sets: 3 x (75 MB features + 206 MB grad_out) > L2
-        feats = [torch.from_numpy(rs.standard_normal((B, C, fh, fw)).astype(np.float32)).to(dev) for _ in range(NR)]
-        gouts = [torch.from_numpy(rs.standard_normal((B * per, C, 7, 7)).astype(np.float32)).to(dev) for _ in range(NR)]
-        lg = torch.from_numpy(rs.standard_normal((B, n, 2)).astype(np.float32)).to(dev)
-        rg = torch.from_numpy((rs.standard_normal((B, n, 4)) * 0.2).astype(np.float32)).to(dev)
-        gt = torch.from_numpy(np.stack([synth.gt_boxes(3000 + 100 * rank + i, G)[0] for i in range(B)])).to(dev)
-        lab = torch.from_numpy(np.stack([synth.gt_boxes(3000 + 100 * rank + i, G)[1] for i in range(B)])).to(dev)
-        props, pcnt = region.rpn_proposals(lg, rg, image_hw=hw, mode="train")     # config-2 pipeline proposals
-        scale = torch.tensor([fw, fh, fw, fh], dtype=torch.float32, device=dev)
-        bidx = torch.arange(B, device=dev, dtype=torch.float32).repeat_interleave(per)[:, None]
-        stats = {}
-
-        torch.manual_seed(3000 + rank)
-        gen = targets.DeviceGenerator(dev) if args.sampling == "device" else None    # torch's mt19937 stream on the device
-
-        def step(i):
-            # device sampling: 6 kernels, no host synchronisation; host sampling: 4 kernels + ONE D2H of counts
-            t = targets.make_targets(gt, None, lab, props, pcnt, image_hw=hw, generator=gen)
-            rois5 = torch.cat([bidx, (t["sample_rois"] * scale).reshape(-1, 4)], dim=1)
-            out, arg = ops.roi_pool_forward(feats[i % NR], rois5)
-            gin = ops.roi_pool_backward(gouts[i % NR], arg, rois5, feats[0].shape)
-            stats["last"] = (out, gin, rois5, arg)
-            return gin
-
-        for i in range(max(args.warmup, 3)):
-            step(i)
-        sampler = ClockSampler(local) if rank == 0 else None
-        l0 = _lib.launch_count()
-        ms = maxms(_events_ms(torch, step, args.steps, sync_all))
-        launches = _lib.launch_count() - l0
-        out, gin, rois5, arg = stats["last"]
-        obytes = B * per * C * 49 * 4
-        fbytes = B * C * fh * fw * 4
-        ms_f = _events_ms(torch, lambda i: ops.roi_pool_forward(feats[i % NR], rois5), 12, sync_all) / 12
-        ms_b = _events_ms(torch, lambda i: ops.roi_pool_backward(gouts[i % NR], arg, rois5, feats[0].shape), 12, sync_all) / 12
-        ms_t = _events_ms(torch, lambda i: targets.make_targets(gt, None, lab, props, pcnt, image_hw=hw), 12, sync_all) / 12
-        gen2 = targets.DeviceGenerator(dev)
-        ms_td = _events_ms(torch, lambda i: targets.make_targets(gt, None, lab, props, pcnt, image_hw=hw, generator=gen2), 12, sync_all) / 12
-        clocks = sampler.stop() if sampler else None
-        if rank == 0:
-            fb = fbytes + 2 * obytes
-            print(json.dumps({
-                "metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
-                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "configs[2]: training targets (256 anchor / 128 RoI sampling, G=8) + RoIPool 7x7 fwd/bwd on "
-                                       "512-ch stride-16 features (37x62), batch 16 images/GPU, RoIs sampled from the RPN proposals",
-                           "l2": f"features/grad_out rotated over {NR} resident sets (> 126 MB L2)"},
-                "kernels_ms_per_batch": {"roi_pool_fwd": ms_f, "roi_pool_bwd": ms_b, "make_targets(4 kernels + D2H + host randperm + H2D)": ms_t,
-                                         "make_targets(device sampling: 6 kernels, no sync)": ms_td},
-                "sampling": args.sampling,
-                "gpu_launches": int(launches), "clocks": clocks,
-                "roofline": {"kernel": "roi_fwd_fast_kernel", "bound": "hbm", "achieved": fb / (ms_f * 1e-3) / 1e9, "peak": peak,
-                             "unit": "GB/s", "frac": fb / (ms_f * 1e-3) / 1e9 / peak, "traffic": ncu_traffic("roi_pool_fwd_flat_kernel"), "peak_source": how,
-                             "bytes_per_launch": fb},
-                "roofline_bwd": {"kernel": "roi_pool_bwd_fast_kernel", "bound": "hbm", "achieved": fb / (ms_b * 1e-3) / 1e9,
-                                 "peak": peak, "unit": "GB/s", "frac": fb / (ms_b * 1e-3) / 1e9 / peak, "bytes_per_launch": fb},
-            }))
+        line = run_joint(ctx, args)
+    elif args.workload in ("voc1", "infer", "train"):
+        res = run_train(ctx, args) if args.workload == "train" else run_predict(ctx, args, args.workload)
+        line = _as_line(ctx, args, res)
+        if want_cpu:
+            line["cpu_baseline"] = cpu_baseline(args.workload, threads)
     else:
-        hw, B, R, NC = (800, 1333), 8, 300, 81
-        fh, fw = hw[0] // 16, hw[1] // 16
-        n = synth.num_anchors(hw)
-        NR = 4
-        feats = [torch.from_numpy(rs.standard_normal((B, C, fh, fw)).astype(np.float32)).to(dev) for _ in range(NR)]
-        lgs = [torch.from_numpy(rs.standard_normal((B, n, 2)).astype(np.float32)).to(dev) for _ in range(NR)]
-        rgs = [torch.from_numpy((rs.standard_normal((B, n, 4)) * 0.2).astype(np.float32)).to(dev) for _ in range(NR)]
-        hcls = torch.from_numpy(rs.standard_normal((B * R, NC)).astype(np.float32)).to(dev)       # head outputs (FC head is
-        hreg = torch.from_numpy(rs.standard_normal((B * R, 4 * NC)).astype(np.float32)).to(dev)   # cuBLAS, not the product)
-        plan = region.ProposalPlan(B, n, dev, image_hw=hw, mode="test")
-        scale = torch.tensor([fw, fh, fw, fh], dtype=torch.float32, device=dev)
-        bidx = torch.arange(B, device=dev, dtype=torch.float32).repeat_interleave(R)[:, None]
-        ids = torch.arange(rank * B, (rank + 1) * B, dtype=torch.int64, device=dev)
-        keepalive = {}
-
-        def step(i):
-            rois, cnt = plan.run(lgs[i % NR], rgs[i % NR])
-            rois5 = torch.cat([bidx, (rois * scale).reshape(-1, 4)], dim=1)
-            pooled, _ = ops.roi_pool_forward(feats[i % NR], rois5, want_argmax=False)
-            prob, boxes = ops.decode_classwise(hcls, hreg, rois.reshape(-1, 4), NC)
-            db, dl, ds, dc = ops.class_nms(prob.reshape(B, R, NC), boxes.reshape(B, R, 4 * NC), NC, score_thres=0.05,
-                                           roi_count=cnt)
-            packed, pc = fdist.pack_detections(db, dl, ds, dc, 100)
-            keepalive["d"] = fdist.gather_detections(packed, pc, ids, equal_batch=True)
-            return pooled
-
-        for i in range(max(args.warmup, 3)):
-            step(i)
-        sampler = ClockSampler(local) if rank == 0 else None
-        l0 = _lib.launch_count()
-        ms = maxms(_events_ms(torch, step, args.steps, sync_all))
-        launches = _lib.launch_count() - l0
+        line = run_rpn(ctx, args)
+        if args.workload == "all":
+            sub = {}
+            for name in ("voc1", "train", "infer"):
+                sub[name] = run_train(ctx, args) if name == "train" else run_predict(ctx, args, name)
+            line["sub_results"] = sub
         clocks = sampler.stop() if sampler else None
-        if rank == 0:
-            print(json.dumps({
-                "metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
-                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "configs[3]: COCO-shaped 800x1333 inference, 81 classes, 6000 -> 300 proposals, RoIPool of 300 "
-                                       "RoIs x 512 ch, 80-class NMS @0.3 (thres 0.05), 8 images/GPU, detections [8,100,6] all-gathered",
-                           "l2": f"inputs rotated over {NR} resident sets"},
-                "gpu_launches": int(launches), "clocks": clocks, "detections_gathered": int(keepalive["d"][1].sum()),
-            }))
-    if world > 1:
-        dist.destroy_process_group()
+        sampler = None
+        line["clocks"] = clocks
+        if want_cpu:   # bounded samples of the same workloads on the host cores (rank 0, N = 1 only)
+            line["cpu_baseline"] = cpu_baseline("rpn", threads, per_thread=4)
+            for name in line.get("sub_results", {}):
+                line["sub_results"][name]["cpu_baseline"] = cpu_baseline(name, threads)
+        else:
+            line["cpu_baseline"] = None
+    if sampler is not None:
+        line["clocks"] = sampler.stop()
+    if ctx.rank == 0:
+        print(json.dumps(line))
+    ctx.close()
 
 
 def main():
@@ -613,16 +988,15 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--eager", action="store_true", help="time eager C-ABI calls instead of CUDA-graph replays")
     ap.add_argument("--sampling", default="device", choices=["device", "host"],
-                    help="--workload train: where the reference's torch.randperm draws are replayed")
-    ap.add_argument("--workload", default="rpn", choices=["rpn", "train", "infer", "joint"],
-                    help="rpn = BASELINE configs[1] (the driver's line); train = configs[2]; infer = configs[3]; joint = configs[4]")
+                    help="train workload: where the reference's torch.randperm draws are replayed")
+    ap.add_argument("--workload", default="all", choices=["all", "rpn", "voc1", "train", "infer", "joint"],
+                    help="all = configs[1] headline + sub_results for configs[0], [2], [3] (the driver's line); rpn = configs[1] "
+                         "only; voc1 = configs[0]; train = configs[2]; infer = configs[3]; joint = configs[4]")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "rpn":
-        run_ours(args)
     else:
-        run_extra(args)
+        run_ours(args)
 
 
 if __name__ == "__main__":

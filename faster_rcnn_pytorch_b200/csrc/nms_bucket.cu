@@ -37,11 +37,11 @@ namespace frr {
 constexpr int kBkChunk = 2048;     // most candidates per chunk (shared-memory arrays are sized for it)
 constexpr int kBkListCap = 2048;   // kept-list capacity (max_keep <= 2047)
 constexpr int kBkEdgeCap = 8192;   // edges per chunk over the whole cluster (each CTA owns kBkEdgeCap / S)
-constexpr int kBkMaxCls = 6;       // [alo, ahi] spans 2 * log2(1 / thr) * 4 + 1 classes: 5.1 at thr 0.7
-constexpr int kBkUpCls = 3;        // classes above the own one inside [1, ahi]: 2.06 at thr 0.7
+constexpr int kBkBins = 3;         // x bins of a walk whose bounds are prefetched (more: tail loop)
+constexpr int kBkUpBins = 2;       // same for the upward walk (bins above the own one)
 constexpr int kBkHits = 4;         // screen hits a thread parks per walk before it falls back to the slow walk
 
-static std::atomic<int> g_bk_kc0{1024}, g_bk_kcmax{2048};
+static std::atomic<int> g_bk_kc0{1024}, g_bk_kcmax{2048}, g_bk_nsub1{4}, g_bk_nsub2{4};
 
 struct BkSmem {
     unsigned int lhist[kKeyCap];  // kept list: key histogram, then scatter cursors
@@ -52,6 +52,7 @@ struct BkSmem {
     unsigned int edges[kBkEdgeCap];  // (later << 16) | earlier, chunk-local positions; region r belongs to CTA r
     unsigned int ecount[kMaxCluster];
     unsigned int ecursor;
+    unsigned int work[2];  // dynamic dealing of the items of phases D and H
     unsigned int warp_tmp[32];
     float4 cbox[kBkChunk];  // the chunk's candidates, score order
     float csa[kBkChunk];    // c2-scaled screening areas (NaN = always take the exact path)
@@ -100,33 +101,52 @@ __device__ __forceinline__ void bk_scan_keys(unsigned int* hist, unsigned short*
     }
 }
 
+// Bucket key = (x bin, area class), x bin major: for one x bin the admissible area classes of a box are ONE contiguous
+// run of the bucketed array, so a walk is a handful of long ranges (one per admissible x bin) instead of one short range
+// per class.  Boxes without a usable screening area get the extra key kKeys (always tested, last bucket).
+__device__ __forceinline__ int bk_key(const float4& b, float sa) {
+    return (sa != sa) ? kKeys : xbin_of(0.5f * (b.x + b.z)) * kStrips + strip_of_area(box_area(b));
+}
+
+struct BkAdm {
+    int c_lo, c_hi, x_lo, x_hi;
+};
+// Admissible keys of a box: area classes of [alo * A, ahi * A] (IoU <= min / max area) and x bins of cx -+ fx * w.
+__device__ __forceinline__ BkAdm bk_admissible(const float4& cbx, const NmsThr& thr) {
+    BkAdm r;
+    const float a = box_area(cbx);
+    r.c_lo = strip_of_area(a * thr.alo);
+    r.c_hi = strip_of_area(a * thr.ahi);
+    const float cx = 0.5f * (cbx.x + cbx.z);
+    const float rx = thr.fx * (cbx.z - cbx.x) * 1.0001f + 2.0e-6f;
+    r.x_lo = xbin_of(cx - rx);
+    r.x_hi = xbin_of(cx + rx);
+    return r;
+}
+
 // Calls f(k) for every position k of a bucketed array (start offsets `start`) whose key is admissible for the box
 // (cbx, screening area ca); this thread takes every nsub-th position of each range, starting at sub.
 template <class F>
 __device__ __forceinline__ void bk_walk(const unsigned short* __restrict__ start, const float4& cbx, float ca,
                                         const NmsThr& thr, int sub, int nsub, F&& f) {
     if (ca == ca) {
-        const float a = box_area(cbx);
-        const int c_lo = strip_of_area(a * thr.alo), c_hi = strip_of_area(a * thr.ahi);
-        const float cx = 0.5f * (cbx.x + cbx.z);
-        const float rx = thr.fx * (cbx.z - cbx.x) * 1.0001f + 2.0e-6f;
-        const int x_lo = xbin_of(cx - rx), x_hi = xbin_of(cx + rx);
-        // the bounds of all admissible classes are fetched before the first walk (independent loads)
-        int lo_c[kBkMaxCls], hi_c[kBkMaxCls];
+        const BkAdm ad = bk_admissible(cbx, thr);
+        // the bounds of the first bins are fetched before the first walk (independent loads)
+        int lo_b[kBkBins], hi_b[kBkBins];
 #pragma unroll
-        for (int q = 0; q < kBkMaxCls; ++q) {
-            const int c = min(c_lo + q, kStrips - 1);
-            lo_c[q] = start[c * kXBins + x_lo];
-            hi_c[q] = (c_lo + q <= c_hi) ? (int)start[c * kXBins + x_hi + 1] : 0;
+        for (int q = 0; q < kBkBins; ++q) {
+            const int xb = min(ad.x_lo + q, kXBins - 1);
+            lo_b[q] = start[xb * kStrips + ad.c_lo];
+            hi_b[q] = (ad.x_lo + q <= ad.x_hi) ? (int)start[xb * kStrips + ad.c_hi + 1] : 0;
         }
         const int lo2 = start[kKeys], hi2 = start[kKeys + 1];  // boxes that must always be tested
 #pragma unroll
-        for (int q = 0; q < kBkMaxCls; ++q) {
+        for (int q = 0; q < kBkBins; ++q) {
 #pragma unroll 2
-            for (int k = lo_c[q] + sub; k < hi_c[q]; k += nsub) f(k);
+            for (int k = lo_b[q] + sub; k < hi_b[q]; k += nsub) f(k);
         }
-        for (int c = c_lo + kBkMaxCls; c <= c_hi; ++c) {  // thresholds below 0.6: more classes
-            const int lo = start[c * kXBins + x_lo], hi = start[c * kXBins + x_hi + 1];
+        for (int xb = ad.x_lo + kBkBins; xb <= ad.x_hi; ++xb) {  // wide boxes / low thresholds: more bins
+            const int lo = start[xb * kStrips + ad.c_lo], hi = start[xb * kStrips + ad.c_hi + 1];
             for (int k = lo + sub; k < hi; k += nsub) f(k);
         }
         for (int k = lo2 + sub; k < hi2; k += nsub) f(k);
@@ -143,30 +163,26 @@ __device__ __forceinline__ void bk_walk_up(const unsigned short* __restrict__ st
                                            float ca, const NmsThr& thr, int sub, int nsub, F&& f) {
     const int total = start[kKeys + 1];
     if (ca == ca) {
-        const int c = own_key / kXBins;
-        const float a = box_area(cbx);
-        const int c_hi = strip_of_area(a * thr.ahi);
-        const float cx = 0.5f * (cbx.x + cbx.z);
-        const float rx = thr.fx * (cbx.z - cbx.x) * 1.0001f + 2.0e-6f;
-        const int x_lo = xbin_of(cx - rx), x_hi = xbin_of(cx + rx);
-        const int hi0 = start[c * kXBins + x_hi + 1];  // own class: the rest of the own bucket and the bins up to x_hi
-        int lo_c[kBkUpCls], hi_c[kBkUpCls];
+        const BkAdm ad = bk_admissible(cbx, thr);
+        const int xb0 = own_key / kStrips;
+        const int hi0 = start[xb0 * kStrips + ad.c_hi + 1];  // own bin: the rest of the own bucket and the classes up to c_hi
+        int lo_b[kBkUpBins], hi_b[kBkUpBins];
 #pragma unroll
-        for (int q = 0; q < kBkUpCls; ++q) {
-            const int cc = min(c + 1 + q, kStrips - 1);
-            lo_c[q] = start[cc * kXBins + x_lo];
-            hi_c[q] = (c + 1 + q <= c_hi) ? (int)start[cc * kXBins + x_hi + 1] : 0;
+        for (int q = 0; q < kBkUpBins; ++q) {
+            const int xb = min(xb0 + 1 + q, kXBins - 1);
+            lo_b[q] = start[xb * kStrips + ad.c_lo];
+            hi_b[q] = (xb0 + 1 + q <= ad.x_hi) ? (int)start[xb * kStrips + ad.c_hi + 1] : 0;
         }
         const int lo2 = start[kKeys];
 #pragma unroll 2
         for (int k = p + 1 + sub; k < hi0; k += nsub) f(k);
 #pragma unroll
-        for (int q = 0; q < kBkUpCls; ++q) {
+        for (int q = 0; q < kBkUpBins; ++q) {
 #pragma unroll 2
-            for (int k = lo_c[q] + sub; k < hi_c[q]; k += nsub) f(k);
+            for (int k = lo_b[q] + sub; k < hi_b[q]; k += nsub) f(k);
         }
-        for (int cc = c + 1 + kBkUpCls; cc <= c_hi; ++cc) {
-            const int lo = start[cc * kXBins + x_lo], hi = start[cc * kXBins + x_hi + 1];
+        for (int xb = xb0 + 1 + kBkUpBins; xb <= ad.x_hi; ++xb) {
+            const int lo = start[xb * kStrips + ad.c_lo], hi = start[xb * kStrips + ad.c_hi + 1];
             for (int k = lo + sub; k < hi; k += nsub) f(k);
         }
         for (int k = lo2 + sub; k < total; k += nsub) f(k);
@@ -175,48 +191,39 @@ __device__ __forceinline__ void bk_walk_up(const unsigned short* __restrict__ st
     }
 }
 
-// Same set of positions as bk_walk, one compact copy of the code (rare paths: kept out of the hot loops' footprint).
+// Same positions and the same dealing to the sub-threads as bk_walk, one compact copy of the code (rare paths: kept
+// out of the hot loops' footprint).  f returns true to stop.
 template <class F>
 __device__ __noinline__ void bk_walk_slow(const unsigned short* __restrict__ start, float4 cbx, float ca, NmsThr thr,
                                           int sub, int nsub, F f) {
-    int c_lo = 0, c_hi = -1, x_lo = 0, x_hi = 0, lo2 = 0;
+    int lo2 = 0;
     const int hi2 = start[kKeys + 1];
     if (ca == ca) {
-        const float a = box_area(cbx);
-        c_lo = strip_of_area(a * thr.alo);
-        c_hi = strip_of_area(a * thr.ahi);
-        const float cx = 0.5f * (cbx.x + cbx.z);
-        const float rx = thr.fx * (cbx.z - cbx.x) * 1.0001f + 2.0e-6f;
-        x_lo = xbin_of(cx - rx);
-        x_hi = xbin_of(cx + rx);
+        const BkAdm ad = bk_admissible(cbx, thr);
+        for (int xb = ad.x_lo; xb <= ad.x_hi; ++xb) {
+            const int lo = start[xb * kStrips + ad.c_lo], hi = start[xb * kStrips + ad.c_hi + 1];
+            for (int k = lo + sub; k < hi; k += nsub)
+                if (f(k)) return;
+        }
         lo2 = start[kKeys];
-    }
-    for (int c = c_lo; c <= c_hi; ++c) {
-        const int lo = start[c * kXBins + x_lo], hi = start[c * kXBins + x_hi + 1];
-        for (int k = lo + sub; k < hi; k += nsub)
-            if (f(k)) return;
     }
     for (int k = lo2 + sub; k < hi2; k += nsub)
         if (f(k)) return;
 }
 
-// The positions of bk_walk_up with the same dealing to the sub-threads, one compact copy (a thread whose hit ring
+// bk_walk_up's positions with the same dealing to the sub-threads, one compact copy (a thread whose hit ring
 // overflowed re-walks exactly ITS share).
 template <class F>
 __device__ __noinline__ void bk_walk_up_slow(const unsigned short* __restrict__ start, int p, int own_key, float4 cbx, float ca,
                                              NmsThr thr, int sub, int nsub, F f) {
     const int total = start[kKeys + 1];
     if (ca == ca) {
-        const int c = own_key / kXBins;
-        const float a = box_area(cbx);
-        const int c_hi = strip_of_area(a * thr.ahi);
-        const float cx = 0.5f * (cbx.x + cbx.z);
-        const float rx = thr.fx * (cbx.z - cbx.x) * 1.0001f + 2.0e-6f;
-        const int x_lo = xbin_of(cx - rx), x_hi = xbin_of(cx + rx);
-        const int hi0 = start[c * kXBins + x_hi + 1];
+        const BkAdm ad = bk_admissible(cbx, thr);
+        const int xb0 = own_key / kStrips;
+        const int hi0 = start[xb0 * kStrips + ad.c_hi + 1];
         for (int k = p + 1 + sub; k < hi0; k += nsub) f(k);
-        for (int cc = c + 1; cc <= c_hi; ++cc) {
-            const int lo = start[cc * kXBins + x_lo], hi = start[cc * kXBins + x_hi + 1];
+        for (int xb = xb0 + 1; xb <= ad.x_hi; ++xb) {
+            const int lo = start[xb * kStrips + ad.c_lo], hi = start[xb * kStrips + ad.c_hi + 1];
             for (int k = lo + sub; k < hi; k += nsub) f(k);
         }
         for (int k = start[kKeys] + sub; k < total; k += nsub) f(k);
@@ -226,24 +233,27 @@ __device__ __noinline__ void bk_walk_up_slow(const unsigned short* __restrict__ 
 }
 
 // A confirmed suppression pair of the chunk: the later box (chunk position i) has the earlier one (j) as predecessor.
-// Appended to this CTA's edge region in every CTA of the cluster; if the region is full the later box is flagged
-// everywhere and decides from a walk of its own in the fix-point.
-__device__ __noinline__ void bk_push_edge(BkSmem* sm, int i, int j, int S, int rank, int ecap) {
-    cg::cluster_group cluster = cg::this_cluster();
+// Appended to this CTA's edge region (mirrored into the other CTAs after the phase); if the region is full the later
+// box is flagged and decides from a walk of its own in the fix-point.
+__device__ __forceinline__ void bk_push_edge(BkSmem* sm, int i, int j, int rank, int ecap) {
     const unsigned int e = atomicAdd(&sm->ecursor, 1u);
-    if (e < (unsigned int)ecap) {
-        const unsigned int v = ((unsigned int)i << 16) | (unsigned int)j;
-        for (int d = 0; d < S; ++d) *cluster.map_shared_rank(&sm->edges[rank * ecap + e], d) = v;
-    } else {
-        for (int d = 0; d < S; ++d) *cluster.map_shared_rank(&sm->ovf[i], d) = 1;
-    }
+    if (e < (unsigned int)ecap) sm->edges[rank * ecap + e] = ((unsigned int)i << 16) | (unsigned int)j;
+    else sm->ovf[i] = 1;
+}
+
+// A warp takes the next 32 / nsub items of a phase (dynamic dealing: walks differ in length by more than 10x).
+__device__ __forceinline__ int bk_grab(unsigned int* cursor, int per_warp, int lane) {
+    int q0 = 0;
+    if (lane == 0) q0 = (int)atomicAdd(cursor, (unsigned int)per_warp);
+    return __shfl_sync(0xffffffffu, q0, 0);
 }
 
 template <int kThreads>
 __global__ void __launch_bounds__(kThreads)
     nms_bucket_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ counts, int n, int max_keep, NmsThr thr,
                       int32_t* __restrict__ keep, int32_t* __restrict__ keep_count, float4* __restrict__ out_boxes,
-                      long long* __restrict__ dbg, const int32_t* __restrict__ gather_idx, int src_n, int kc0, int kc_max) {
+                      long long* __restrict__ dbg, const int32_t* __restrict__ gather_idx, int src_n, int kc0, int kc_max, int nsub1,
+                      int nsub2) {
     cg::cluster_group cluster = cg::this_cluster();
     const int S = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
@@ -281,7 +291,11 @@ __global__ void __launch_bounds__(kThreads)
         sm->shist[e] = 0u;
     }
     for (int i = tid; i < kBkChunk; i += kThreads) sm->cstate[0][i] = 0;
-    if (tid == 0) sm->ecursor = 0u;
+    if (tid == 0) {
+        sm->ecursor = 0u;
+        sm->work[0] = 0u;
+        sm->work[1] = 0u;
+    }
     cluster.sync();  // every CTA's shared memory is initialised before a peer writes into it
 
     int nk = 0;   // kept so far (identical in every CTA of the cluster)
@@ -296,7 +310,7 @@ __global__ void __launch_bounds__(kThreads)
         for (int i = tid; i < m; i += kThreads) {
             const float4 b = gi ? ib[gi[base + i]] : ib[base + i];
             const float sa = screen_area(b, thr.c2);
-            const int key = strip_of(b, sa);
+            const int key = bk_key(b, sa);
             sm->cbox[i] = b;
             sm->csa[i] = sa;
             sm->ckey[i] = (unsigned short)key;
@@ -304,7 +318,7 @@ __global__ void __launch_bounds__(kThreads)
             sm->ovf[i] = 0;
             if (i % S == rank) atomicAdd(&sm->chist[key], 1u);
         }
-        for (int k = tid; k < nk; k += kThreads) atomicAdd(&sm->lhist[strip_of(bbox[cur][k], barea[cur][k])], 1u);
+        for (int k = tid; k < nk; k += kThreads) atomicAdd(&sm->lhist[bk_key(bbox[cur][k], barea[cur][k])], 1u);
         __syncthreads();
         BK_TICK(BK_LOAD);
         // ---- B: exclusive scans (warp 0: list, warp 1: own candidates)
@@ -316,7 +330,7 @@ __global__ void __launch_bounds__(kThreads)
         for (int k = tid; k < nk; k += kThreads) {
             const float4 b = bbox[cur][k];
             const float a = barea[cur][k];
-            const unsigned int pos = atomicAdd(&sm->lhist[strip_of(b, a)], 1u);
+            const unsigned int pos = atomicAdd(&sm->lhist[bk_key(b, a)], 1u);
             bbox[cur ^ 1][pos] = b;
             barea[cur ^ 1][pos] = a;
         }
@@ -327,18 +341,20 @@ __global__ void __launch_bounds__(kThreads)
         BK_TICK(BK_SCATTER);
         const float4* lb = bbox[cur];
         const float* la = barea[cur];
-        // ---- D: screen the own candidates against the admissible part of the kept list
+        // ---- D: screen the own candidates against the admissible part of the kept list: nsub1 lanes per candidate,
+        //      a warp takes 32 / nsub1 candidates (adjacent in key order: walks of similar length) at a time
         const int n_own = (m - rank + S - 1) / S;
-        int nsub = 1;
-        while (nsub * 2 * n_own <= kThreads && nsub < 32) nsub *= 2;
         if (nk > 0) {
-            const int sub = tid % nsub;
-            for (int q = tid / nsub; q < n_own; q += kThreads / nsub) {
+            const int per_warp = 32 / nsub1, sub = lane % nsub1;
+            for (;;) {
+                const int q = bk_grab(&sm->work[0], per_warp, lane) + lane / nsub1;
+                if (q - lane / nsub1 >= n_own) break;
+                if (q >= n_own) continue;
                 const int i = sm->cord[q];
                 const float4 cbx = sm->cbox[i];
                 const float ca = sm->csa[i];
                 int pk = -1;
-                bk_walk(sm->lstart, cbx, ca, thr, sub, nsub, [&](int k) {
+                bk_walk(sm->lstart, cbx, ca, thr, sub, nsub1, [&](int k) {
                     if (suppress_screen<true>(lb[k], la[k], cbx, ca)) pk = k;
                 });
                 if (pk >= 0) {
@@ -346,7 +362,7 @@ __global__ void __launch_bounds__(kThreads)
                     if (!r) {  // the screen hit was not confirmed by the exact test (rare): exact walk of the own share
                         const float up = thr.up;
                         bool* rp = &r;
-                        bk_walk_slow(sm->lstart, cbx, ca, thr, sub, nsub, [=](int k) {
+                        bk_walk_slow(sm->lstart, cbx, ca, thr, sub, nsub1, [=](int k) {
                             if (suppress_screen<true>(lb[k], la[k], cbx, ca) && suppress_exact(lb[k], cbx, up)) *rp = true;
                             return *rp;
                         });
@@ -397,14 +413,16 @@ __global__ void __launch_bounds__(kThreads)
         __syncthreads();
         BK_TICK(BK_SURV_SORT);
         if (prof) dbg[BK_SURVIVORS] += ns;
-        // ---- H: suppression pairs among the survivors, every pair from its lower bucketed position
+        // ---- H: suppression pairs among the survivors, every pair from its lower bucketed position (nsub2 lanes per
+        //      survivor, dealt like phase D)
         {
             const int ns_own = (ns - rank + S - 1) / S;
-            int nsub2 = 1;
-            while (nsub2 * 2 * ns_own <= kThreads && nsub2 < 32) nsub2 *= 2;
-            const int sub = tid % nsub2;
+            const int per_warp = 32 / nsub2, sub = lane % nsub2;
             unsigned int* hb = sm->hitbuf + tid * kBkHits;
-            for (int q = tid / nsub2; q < ns_own; q += kThreads / nsub2) {
+            for (;;) {
+                const int q = bk_grab(&sm->work[1], per_warp, lane) + lane / nsub2;
+                if (q - lane / nsub2 >= ns_own) break;
+                if (q >= ns_own) continue;
                 const int p = q * S + rank;
                 const int i = sm->sidx[p];
                 const float4 cbx = sb[p];
@@ -416,14 +434,14 @@ __global__ void __launch_bounds__(kThreads)
                         ++nh;
                     }
                 });
-                if (nh > kBkHits) {  // more screen hits than the ring holds: walk again, confirming as they come
+                if (nh > kBkHits) {  // more screen hits than the ring holds: walk the share again, confirming as they come
                     const float up = thr.up;
                     const unsigned short* sidx = sm->sidx;
                     BkSmem* smp = sm;
                     bk_walk_up_slow(sm->sstart, p, sm->ckey[i], cbx, ca, thr, sub, nsub2, [=](int k) {
                         if (suppress_screen<true>(sb[k], sa_[k], cbx, ca) && suppress_exact(sb[k], cbx, up)) {
                             const int j = sidx[k];
-                            bk_push_edge(smp, max(i, j), min(i, j), S, rank, ecap);
+                            bk_push_edge(smp, max(i, j), min(i, j), rank, ecap);
                         }
                     });
                 } else {
@@ -431,14 +449,28 @@ __global__ void __launch_bounds__(kThreads)
                         const int k = (int)hb[h];
                         if (suppress_exact(sb[k], cbx, thr.up)) {
                             const int j = sm->sidx[k];
-                            bk_push_edge(sm, max(i, j), min(i, j), S, rank, ecap);
+                            bk_push_edge(sm, max(i, j), min(i, j), rank, ecap);
                         }
                     }
                 }
             }
         }
         __syncthreads();
-        if (tid < S) *cluster.map_shared_rank(&sm->ecount[rank], tid) = min(sm->ecursor, (unsigned int)ecap);
+        {   // mirror this CTA's edges (and, if its region overflowed, the flags) into the other CTAs of the cluster
+            const unsigned int raw = sm->ecursor;
+            const int ne = (int)min(raw, (unsigned int)ecap);
+            for (int d = 1; d < S; ++d) {
+                const int dst = (rank + d) % S;
+                unsigned int* re = cluster.map_shared_rank(&sm->edges[rank * ecap], dst);
+                for (int e = tid; e < ne; e += kThreads) re[e] = sm->edges[rank * ecap + e];
+                if (raw > (unsigned int)ecap) {
+                    unsigned char* ro = cluster.map_shared_rank(&sm->ovf[0], dst);
+                    for (int i = tid; i < m; i += kThreads)
+                        if (sm->ovf[i]) ro[i] = 1;
+                }
+            }
+            if (tid < S) *cluster.map_shared_rank(&sm->ecount[rank], tid) = (unsigned int)ne;
+        }
         BK_TICK(BK_PRED);
         cluster.sync();
         BK_TICK(BK_SYNC2);
@@ -528,7 +560,11 @@ __global__ void __launch_bounds__(kThreads)
             nk = min(nk + kept_chunk, max_keep);
         }
         for (int e = tid; e < kKeyCap; e += kThreads) sm->shist[e] = 0u;
-        if (tid == 0) sm->ecursor = 0u;
+        if (tid == 0) {
+            sm->ecursor = 0u;
+            sm->work[0] = 0u;
+            sm->work[1] = 0u;
+        }
         base += m;
         // next chunk: enough candidates for the missing keeps at the rate of this chunk, plus half
         {
@@ -564,7 +600,7 @@ int nms_bucket_launch(const float* boxes, const int32_t* counts, int B, int n, c
                       int32_t* keep_count, float* out_boxes, int S, int threads, long long* dbg, frr_stream_t stream,
                       const int32_t* gather_idx, int src_n) {
     using kern_t = void (*)(const float4*, const int32_t*, int, int, NmsThr, int32_t*, int32_t*, float4*, long long*,
-                            const int32_t*, int, int, int);
+                            const int32_t*, int, int, int, int, int);
     kern_t kern = threads <= 256 ? nms_bucket_kernel<256> : threads == 512 ? nms_bucket_kernel<512> : nms_bucket_kernel<1024>;
     if (threads < 256) threads = 256;
     const size_t smem = nms_bucket_smem_bytes();
@@ -593,7 +629,8 @@ int nms_bucket_launch(const float* boxes, const int32_t* counts, int B, int n, c
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     FRR_CUDA(cudaLaunchKernelEx(&cfg, kern, (const float4*)boxes, counts, n, max_keep, thr, keep, keep_count,
-                                (float4*)out_boxes, dbg, gather_idx, src_n, kc0, kc_max));
+                                (float4*)out_boxes, dbg, gather_idx, src_n, kc0, kc_max,
+                                g_bk_nsub1.load(std::memory_order_relaxed), g_bk_nsub2.load(std::memory_order_relaxed)));
     count_launch();
     FRR_CHECK_LAUNCH("nms_bucket_kernel");
     return FRR_OK;
@@ -602,11 +639,17 @@ int nms_bucket_launch(const float* boxes, const int32_t* counts, int B, int n, c
 }  // namespace frr
 
 // Developer knob (profiling tools): sizes of the first chunk and of the largest chunk of the bucketed kernel
-// (multiples of 256, <= 2048).  Process-wide; results never depend on them.
-extern "C" int frr_nms_bucket_tune(int first_chunk, int max_chunk) {
+// (multiples of 256, <= 2048) and the lanes per candidate in the screen / pair phases (1, 2, 4, ... 32; 0 keeps the
+// current value).  Process-wide; results never depend on them.
+extern "C" int frr_nms_bucket_tune(int first_chunk, int max_chunk, int lanes_screen, int lanes_pairs) {
     FRR_CHECK_ARG(first_chunk >= 256 && max_chunk >= 256 && first_chunk <= frr::kBkChunk && max_chunk <= frr::kBkChunk,
                   "frr_nms_bucket_tune: chunk sizes must lie in [256, %d]", frr::kBkChunk);
+    auto pow2 = [](int v) { return v >= 1 && v <= 32 && (v & (v - 1)) == 0; };
+    FRR_CHECK_ARG((lanes_screen == 0 || pow2(lanes_screen)) && (lanes_pairs == 0 || pow2(lanes_pairs)),
+                  "frr_nms_bucket_tune: lanes per candidate must be a power of two <= 32");
     frr::g_bk_kc0.store(first_chunk);
     frr::g_bk_kcmax.store(max_chunk);
+    if (lanes_screen) frr::g_bk_nsub1.store(lanes_screen);
+    if (lanes_pairs) frr::g_bk_nsub2.store(lanes_pairs);
     return FRR_OK;
 }

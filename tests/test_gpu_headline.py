@@ -159,12 +159,12 @@ def test_bucketed_nms_walk_ends_by_count_with_a_partial_last_chunk(oracle):
             assert np.array_equal(got, want), (n, cs)
 
 
-@pytest.mark.parametrize("first,largest", [(256, 256), (256, 2048), (2048, 2048), (512, 1024)])
-def test_bucketed_nms_result_does_not_depend_on_chunk_sizes(oracle, first, largest):
+@pytest.mark.parametrize("first,largest,lanes", [(256, 256, 1), (256, 2048, 32), (2048, 2048, 2), (512, 1024, 8)])
+def test_bucketed_nms_result_does_not_depend_on_chunk_sizes(oracle, first, largest, lanes):
     from faster_rcnn_pytorch_b200 import _lib
     lib = _lib.load()
     try:
-        _lib.check(lib.frr_nms_bucket_tune(first, largest), "frr_nms_bucket_tune")
+        _lib.check(lib.frr_nms_bucket_tune(first, largest, lanes, lanes), "frr_nms_bucket_tune")
         for name in ("rpn_like", "dense_duplicates", "staircase"):
             b = nms_cases.make(name, 5, 7000)
             want = oracle.nms(b, -np.arange(len(b), dtype=np.float32), 0.7)[:2000]
@@ -172,4 +172,4 @@ def test_bucketed_nms_result_does_not_depend_on_chunk_sizes(oracle, first, large
                 got = _run_nms(b, 0.7, 2000, cluster_size=cs, unit_boxes=True)
                 assert np.array_equal(got, want), (name, cs)
     finally:
-        _lib.check(lib.frr_nms_bucket_tune(1024, 2048), "frr_nms_bucket_tune")
+        _lib.check(lib.frr_nms_bucket_tune(1024, 2048, 4, 4), "frr_nms_bucket_tune")

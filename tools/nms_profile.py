@@ -43,11 +43,12 @@ def run(bx, cnt, S, threads, reps=20, dbg=False):
 
 
 one, onec = tb[:1].contiguous(), tc[:1].contiguous()
-for first, largest in ((1024, 2048), (512, 2048), (2048, 2048), (1024, 1024), (512, 1024), (768, 1536)):
-    _lib.check(lib.frr_nms_bucket_tune(first, largest), "tune")
-    print(json.dumps({"first_chunk": first, "largest_chunk": largest}), flush=True)
-    for threads, S in ((1024, 2), (512, 2), (1024, 1), (1024, 4)):
+for first, largest, n1, n2 in ((512, 2048, 4, 4), (512, 2048, 8, 8), (512, 2048, 2, 2), (512, 2048, 1, 1), (512, 2048, 8, 4),
+                               (512, 2048, 16, 8), (1024, 2048, 4, 4), (256, 2048, 4, 4), (512, 1536, 4, 4), (768, 2048, 4, 4)):
+    _lib.check(lib.frr_nms_bucket_tune(first, largest, n1, n2), "tune")
+    print(json.dumps({"first_chunk": first, "largest_chunk": largest, "lanes_screen": n1, "lanes_pairs": n2}), flush=True)
+    for threads, S in ((1024, 2), (1024, 1), (1024, 4)):
         run(tb, tc, S, threads, dbg=True)
-    for threads, S in ((1024, 16), (512, 16), (1024, 8), (512, 8)):
+    for threads, S in ((1024, 16), (512, 16), (1024, 8)):
         run(one, onec, S, threads, reps=50, dbg=True)
-_lib.check(lib.frr_nms_bucket_tune(1024, 2048), "tune")
+_lib.check(lib.frr_nms_bucket_tune(1024, 2048, 4, 4), "tune")
