@@ -611,22 +611,20 @@ def _predict_setup(ctx, hw, B, R, NC, seed, n_sets):
         hreg=rs.standard_normal((B * R, 4 * NC)).astype(np.float32))      # not the product)
     d = {k: ([torch.from_numpy(x).to(dev) for x in v] if isinstance(v, list) else torch.from_numpy(v).to(dev))
          for k, v in h.items()}
-    plan = region.ProposalPlan(B, n, dev, image_hw=hw, mode="test")
+    plan = region.InferPlan(B, hw, NC, dev)
     return h, d, plan, (fh, fw), n
 
 
 def _predict_step(ops, fdist, plan, feat, lg, rg, hcls, hreg, fhw, B, R, NC, ids=None, gather=False):
-    """FRCNN.predict's region path for a batch (models/model.py:346-402): proposals -> rois5 -> RoIPool -> per-class decode
-    -> per-class NMS -> packed detections [B,100,6] (+ NCCL all-gather)."""
-    rois, cnt = plan.run(lg, rg)
-    rois5 = ops.rois5(rois, cnt, fhw)
-    pooled, _ = ops.roi_pool_forward(feat, rois5, want_argmax=False)
-    prob, boxes = ops.decode_classwise(hcls, hreg, rois.reshape(-1, 4), NC)
-    db, dl, ds, dc = ops.class_nms(prob.reshape(B, R, NC), boxes.reshape(B, R, 4 * NC), NC, score_thres=0.05, roi_count=cnt)
-    packed, pc = fdist.pack_detections(db, dl, ds, dc, 100)
+    """FRCNN.predict's region path for a batch (models/model.py:346-402) through region.InferPlan: proposals -> rois5 ->
+    RoIPool | per-class decode -> per-class NMS -> packed detections [B,100,6] (+ NCCL all-gather)."""
+    pooled, rois, cnt = plan.pool(feat, lg, rg)
+    out = plan.detect(hcls, hreg, return_all=True)
+    packed, pc = out["packed"], out["count"]
     if gather:
         packed, pc, _ = fdist.gather_detections(packed, pc, ids, equal_batch=True)
-    return dict(rois=rois, cnt=cnt, rois5=rois5, pooled=pooled, prob=prob, boxes=boxes, det=(db, dl, ds, dc), packed=packed, pc=pc)
+    return dict(rois=rois, cnt=cnt, rois5=plan.rois5, pooled=pooled, prob=out["prob"], boxes=out["boxes"], det=out["det"],
+                packed=packed, pc=pc)
 
 
 def verify_predict(out, feat, image: int, R: int, NC: int, fhw) -> bool:

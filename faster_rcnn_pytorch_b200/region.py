@@ -206,3 +206,97 @@ class HostProposalPipeline:
         s = self.slots[ticket % self.depth]
         s["done"].synchronize()
         return s["h_rois"], s["h_count"]
+
+
+def _capture(fn, device):
+    """Capture fn() into a CUDA graph; tensors fn allocates come from the graph's private pool and are the replay's
+    outputs.  Returns (graph, outputs)."""
+    fn()                                                      # warm-up outside the capture
+    torch.cuda.synchronize(device)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+        out = fn()
+    return graph, out
+
+
+class InferPlan:
+    """FRCNN.predict's region path for a fixed batch shape (models/model.py:346-402), in the two halves the FC head
+    (cuBLAS, not part of this library) sits between:
+
+    ``pool(feat, cls, reg)``      proposal layer in test mode (6000 -> 300) -> feature-map rois with batch index
+                                  (models/model.py:104-110) -> RoIPool 7x7: returns (pooled [B*R,C,7,7], rois [B,R,4], count [B])
+    ``detect(head_cls, head_reg)``  per-class decode (:369-378) -> per-class NMS (:382-402) -> packed detections
+                                  [B,max_det,6] (x1,y1,x2,y2,score,label) + counts, the evaluation hand-off
+
+    Neither half synchronises with the host; ``capture_*`` record them into CUDA graphs (one graph launch per half)."""
+
+    def __init__(self, B: int, image_hw, num_classes: int, device, stride: int = 16, max_det: int = 100,
+                 score_thres: float = 0.05, iou_thr: float = 0.3, mode: str = "test", logits: bool = True):
+        from . import dist as fdist
+        self._fdist = fdist
+        self.B, self.hw, self.NC, self.device = int(B), (int(image_hw[0]), int(image_hw[1])), int(num_classes), torch.device(device)
+        self.fhw = (self.hw[0] // stride, self.hw[1] // stride)
+        self.N = self.fhw[0] * self.fhw[1] * 9
+        self.proposal = ProposalPlan(self.B, self.N, self.device, image_hw=self.hw, mode=mode, stride=stride, logits=logits)
+        self.R = self.proposal.post_k
+        self.max_det, self.score_thres, self.iou_thr = int(max_det), float(score_thres), float(iou_thr)
+        with torch.cuda.device(self.device):
+            self.rois5 = torch.empty((self.B * self.R, 5), dtype=torch.float32, device=self.device)
+
+    def pool(self, feat, cls, reg, want_argmax: bool = False):
+        rois, cnt = self.proposal.run(cls, reg)
+        ops.rois5(rois, cnt, self.fhw, out=self.rois5)
+        pooled, arg = ops.roi_pool_forward(feat, self.rois5, want_argmax=want_argmax)
+        return (pooled, rois, cnt, arg) if want_argmax else (pooled, rois, cnt)
+
+    def detect(self, head_cls, head_reg, return_all: bool = False):
+        B, R, NC = self.B, self.R, self.NC
+        rois, cnt = self.proposal.rois, self.proposal.count
+        prob, boxes = ops.decode_classwise(head_cls, head_reg, rois.reshape(-1, 4), NC)
+        db, dl, ds, dc = ops.class_nms(prob.reshape(B, R, NC), boxes.reshape(B, R, 4 * NC), NC, score_thres=self.score_thres,
+                                       iou_thr=self.iou_thr, roi_count=cnt)
+        packed, pc = self._fdist.pack_detections(db, dl, ds, dc, self.max_det)
+        if return_all:
+            return dict(packed=packed, count=pc, prob=prob, boxes=boxes, det=(db, dl, ds, dc))
+        return packed, pc
+
+    def capture_pool(self, feat, cls, reg):
+        return _capture(lambda: self.pool(feat, cls, reg), self.device)
+
+    def capture_detect(self, head_cls, head_reg):
+        return _capture(lambda: self.detect(head_cls, head_reg), self.device)
+
+
+class TrainPlan:
+    """The training-side region stage for a fixed batch shape (models/model.py:310-335): both target makers with the
+    reference's sampling replayed on the device (no host synchronisation), RoIPool forward of the sampled rois and its
+    backward.  ``targets_and_pool`` / ``pool_backward`` can be recorded into CUDA graphs with ``capture_*``."""
+
+    def __init__(self, B: int, image_hw, device, generator=None, stride: int = 16):
+        from . import targets
+        self._targets = targets
+        self.B, self.hw, self.device = int(B), (int(image_hw[0]), int(image_hw[1])), torch.device(device)
+        self.fhw = (self.hw[0] // stride, self.hw[1] // stride)
+        self.generator = generator if generator is not None else targets.DeviceGenerator(self.device)
+        with torch.cuda.device(self.device):
+            self.rois5 = torch.empty((self.B * targets.FRCNN_BATCH, 5), dtype=torch.float32, device=self.device)
+        self.last = None
+
+    def targets_and_pool(self, feat, gt, gt_label, proposals, proposal_count, gt_count=None):
+        t = self._targets.make_targets(gt, gt_count, gt_label, proposals, proposal_count, image_hw=self.hw,
+                                       generator=self.generator)
+        ops.rois5(t["sample_rois"], t["n_samples"], self.fhw, out=self.rois5)
+        pooled, arg = ops.roi_pool_forward(feat, self.rois5)
+        self.last = dict(targets=t, pooled=pooled, argmax=arg, feat_shape=tuple(feat.shape),
+                         channels_last=(not feat.is_contiguous()))
+        return t, pooled
+
+    def pool_backward(self, grad_out):
+        s = self.last
+        return ops.roi_pool_backward(grad_out, s["argmax"], self.rois5, s["feat_shape"], channels_last=s["channels_last"])
+
+    def capture_targets_and_pool(self, feat, gt, gt_label, proposals, proposal_count):
+        return _capture(lambda: self.targets_and_pool(feat, gt, gt_label, proposals, proposal_count), self.device)
+
+    def capture_pool_backward(self, grad_out):
+        return _capture(lambda: self.pool_backward(grad_out), self.device)
