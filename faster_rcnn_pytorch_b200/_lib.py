@@ -26,6 +26,8 @@ SIGNATURES = {
     "frr_last_error": (C.c_char_p, []),
     "frr_launch_count": (C.c_uint64, []),
     "frr_anchor_base_host": (_i, [_p, _i]),
+    "frr_tv_anchor_base_host": (_i, [_f, _p, _i, _p]),
+    "frr_anchors_pyramid": (_i, [_p, _i, _p, _p, _i, _i, _i, _p]),
     "frr_anchors": (_i, [_p, _i, _i, _i, _p, _i, _p]),
     "frr_rpn_decode": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _i, _i, _p]),
     "frr_topk_desc": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),

@@ -55,6 +55,25 @@ int frr_abi_version(void) { return FRR_ABI_VERSION; }
 const char* frr_last_error(void) { return frr::t_err; }
 uint64_t frr_launch_count(void) { return frr::g_launches.load(); }
 
+// torchvision AnchorGenerator.generate_anchors (TV models/detection/anchor_utils.py; used by models/new_model.py:23-25):
+//   h_ratios = sqrt(ratios); w_ratios = 1 / h_ratios; ws = w_ratios * size; hs = h_ratios * size;
+//   base = round(stack(-ws, -hs, ws, hs) / 2)     -- all in fp32, torch.round = half to even
+int frr_tv_anchor_base_host(float size, const float* aspect_ratios, int n_ratios, float* table_host) {
+    FRR_CHECK_ARG(table_host != nullptr && aspect_ratios != nullptr && n_ratios >= 1 && size > 0.f,
+                  "frr_tv_anchor_base_host: bad arguments");
+    for (int i = 0; i < n_ratios; ++i) {
+        volatile float hr = sqrtf(aspect_ratios[i]);   // volatile: keep every intermediate in fp32
+        volatile float wr = 1.0f / hr;
+        volatile float ws = wr * size, hs = hr * size;
+        float* r = table_host + 4 * i;
+        r[0] = nearbyintf(-ws / 2.0f);
+        r[1] = nearbyintf(-hs / 2.0f);
+        r[2] = nearbyintf(ws / 2.0f);
+        r[3] = nearbyintf(hs / 2.0f);
+    }
+    return FRR_OK;
+}
+
 int frr_anchor_base_host(float* table_host, int base_size) {
     FRR_CHECK_ARG(table_host != nullptr && base_size > 0, "frr_anchor_base_host: bad arguments");
     frr::reference_base_table(table_host, base_size);

@@ -29,6 +29,36 @@ __global__ void __launch_bounds__(256) anchors_kernel(float4* __restrict__ out, 
     out[i] = make_anchor(tab, cell, a, fw, stride, W, H);
 }
 
+// Multi-level anchors of the FPN variant (torchvision AnchorGenerator.grid_anchors as called at models/new_model.py:43-44,
+// then `anchor /= (w, h, w, h)`): level l has fh_l x fw_l cells with strides (img_h // fh_l, img_w // fw_l) and its own
+// A base boxes; anchors are cell-major, anchor-minor inside a level, levels concatenated.
+constexpr int kPyrLevels = 8, kPyrA = 8;
+struct PyramidParams {
+    int L, A;
+    int off[kPyrLevels + 1];  // first anchor of level l
+    int fw[kPyrLevels];
+    float sx[kPyrLevels], sy[kPyrLevels];
+    float tab[kPyrLevels][kPyrA * 4];
+};
+
+__global__ void __launch_bounds__(256) anchors_pyramid_kernel(float4* __restrict__ out, PyramidParams p, int n, float W, float H) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int l = 0;
+#pragma unroll
+    for (int q = 1; q < kPyrLevels; ++q) l += (q < p.L && i >= p.off[q]) ? 1 : 0;
+    const int j = i - p.off[l];
+    const int cell = j / p.A, a = j - cell * p.A;
+    const int y = cell / p.fw[l], x = cell - y * p.fw[l];
+    const float shx = (float)x * p.sx[l], shy = (float)y * p.sy[l];  // exact: small integers
+    float4 r;
+    r.x = __fdiv_rn(__fadd_rn(p.tab[l][4 * a + 0], shx), W);
+    r.y = __fdiv_rn(__fadd_rn(p.tab[l][4 * a + 1], shy), H);
+    r.z = __fdiv_rn(__fadd_rn(p.tab[l][4 * a + 2], shx), W);
+    r.w = __fdiv_rn(__fadd_rn(p.tab[l][4 * a + 3], shy), H);
+    out[i] = r;
+}
+
 // One thread per anchor and kImgs images (grid.y = image group): the anchor (4 IEEE divisions) and its
 // centre form are built once and reused for every image of the group; the 2*kImgs loads of a thread are
 // issued back to back (memory-level parallelism) before any arithmetic.
@@ -115,6 +145,39 @@ int frr_anchors(float* anchors, int img_h, int img_w, int stride, const float* b
                                                                        (float)img_w, (float)img_h);
     count_launch();
     FRR_CHECK_LAUNCH("anchors_kernel");
+    return FRR_OK;
+}
+
+int frr_anchors_pyramid(float* anchors, int L, const int32_t* level_hw_host, const float* base_tables_host, int A, int img_h,
+                        int img_w, frr_stream_t stream) {
+    using namespace frr;
+    FRR_CHECK_ARG(anchors && level_hw_host && base_tables_host, "frr_anchors_pyramid: null pointer");
+    FRR_CHECK_ARG(L >= 1 && L <= kPyrLevels && A >= 1 && A <= kPyrA && img_h > 0 && img_w > 0,
+                  "frr_anchors_pyramid: L must be in [1,%d], A in [1,%d]", kPyrLevels, kPyrA);
+    FRR_CHECK_ARG(aligned16(anchors), "frr_anchors_pyramid: output must be 16-byte aligned");
+    PyramidParams p;
+    p.L = L;
+    p.A = A;
+    long long n = 0;
+    for (int l = 0; l < kPyrLevels; ++l) {
+        p.off[l] = (int)n;
+        p.fw[l] = 1; p.sx[l] = 0.f; p.sy[l] = 0.f;
+        if (l < L) {
+            const int fh = level_hw_host[2 * l], fw = level_hw_host[2 * l + 1];
+            FRR_CHECK_ARG(fh > 0 && fw > 0, "frr_anchors_pyramid: level %d has an empty grid", l);
+            p.fw[l] = fw;
+            p.sy[l] = (float)(img_h / fh);  // integer strides, like torchvision (image_size // grid_size)
+            p.sx[l] = (float)(img_w / fw);
+            for (int q = 0; q < 4 * A; ++q) p.tab[l][q] = base_tables_host[(size_t)l * A * 4 + q];
+            n += (long long)fh * fw * A;
+        }
+    }
+    p.off[kPyrLevels] = (int)n;
+    FRR_CHECK_ARG(n > 0 && n < (1ll << 30), "frr_anchors_pyramid: bad total size");
+    anchors_pyramid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((float4*)anchors, p, (int)n, (float)img_w,
+                                                                                         (float)img_h);
+    count_launch();
+    FRR_CHECK_LAUNCH("anchors_pyramid_kernel");
     return FRR_OK;
 }
 

@@ -36,9 +36,13 @@ def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float) -> torc
     n = boxes.shape[0]
     if n == 0:
         return torch.empty((0,), dtype=torch.int64, device=boxes.device)
-    if n > 16384:
-        raise ValueError("nms: more than 16384 boxes per call is not on the reference path (<= 12000)")
     b = boxes.detach().to(torch.float32).contiguous()
+    if n > 16384:
+        # beyond the in-shared-memory sort of frr_topk_desc (the reference never passes more than 12000 boxes,
+        # models/model.py:24-28): the ordering falls to torch's stable device sort, the NMS itself stays frr_nms_sorted
+        order = torch.argsort(scores.detach().to(torch.float32), descending=True, stable=True)
+        keep, cnt, _ = ops.nms_sorted(b.index_select(0, order).reshape(1, n, 4), float(iou_threshold), gather=False)
+        return order.index_select(0, keep[0, :int(cnt[0])].to(torch.int64))
     top = ops.topk_desc(scores.detach().to(torch.float32).reshape(1, n), n, boxes=b.reshape(1, n, 4))
     keep, cnt, _ = ops.nms_sorted(top["boxes"], float(iou_threshold), gather=False)
     k = int(cnt[0])
@@ -138,12 +142,40 @@ class fpn:
     PROPOSAL_MODES = {"train": (4000, 1000), "test": (2000, 1000)}   # models/new_model.py:52-56
     MIN_SIZE = float(np.float32(10 / 1000))                          # models/new_model.py:21,66 (fp32 compare)
 
+    class AnchorGenerator:
+        """Drop-in for the two anchor lines of ``RegionProposalNetwork.forward`` (models/new_model.py:43-44):
+        ``torchvision...AnchorGenerator(sizes, aspect_ratios)(ImageList(x, ...), features)[0] / (w, h, w, h)``, generated
+        by one kernel on the device and cached per (image size, pyramid shape, device)."""
+
+        def __init__(self, sizes=((32,), (64,), (128,), (256,), (512,)), aspect_ratios=((0.5, 1.0, 2.0),) * 5):
+            if any(len(s) != 1 for s in sizes) or any(tuple(a) != tuple(aspect_ratios[0]) for a in aspect_ratios):
+                raise ValueError("AnchorGenerator: one size per level and the same aspect ratios on every level "
+                                 "(the configuration of models/new_model.py:23-25)")
+            self.sizes = tuple(float(s[0]) for s in sizes)
+            self.aspect_ratios = tuple(float(a) for a in aspect_ratios[0])
+            self._cache = {}
+
+        def __call__(self, image_hw, feature_hws, device):
+            key = (tuple(image_hw), tuple(tuple(x) for x in feature_hws), str(device))
+            if key not in self._cache:
+                self._cache[key] = ops.anchors_pyramid(feature_hws, image_hw, device, self.sizes, self.aspect_ratios)
+            return self._cache[key]
+
+    _default_anchors = None
+
     @staticmethod
-    def region_proposal(cls, reg, anchor, mode):
+    def region_proposal(cls, reg, anchor=None, mode="train", image_hw=None, feature_hws=None):
         """Proposal part of ``RegionProposalNetwork.forward`` (models/new_model.py:46-83): cls [N,2] logits and reg [N,4]
-        of all pyramid levels concatenated, anchor [N,4] normalised (torchvision AnchorGenerator / (w,h,w,h)) ->
-        rois [<=1000, 4].  Same kernels as the VGG variant with min_size 10/1000 and 4000|2000 -> 1000."""
+        of all pyramid levels concatenated -> rois [<=1000, 4].  ``anchor`` [N,4] normalised, or None: the reference's
+        5-level torchvision anchors are generated on the device from ``image_hw`` and the pyramid's ``feature_hws``.
+        Same kernels as the VGG variant with min_size 10/1000 and 4000|2000 -> 1000."""
         pre_k, post_k = fpn.PROPOSAL_MODES["test" if mode == "test" else "train"]
+        if anchor is None:
+            if image_hw is None or feature_hws is None:
+                raise ValueError("region_proposal: give the anchors, or image_hw and feature_hws to generate them")
+            if fpn._default_anchors is None:
+                fpn._default_anchors = fpn.AnchorGenerator()
+            anchor = fpn._default_anchors(image_hw, feature_hws, reg.device)
         anchor = _as_anchor_tensor(anchor, reg.device)
         rois, count = region.rpn_proposals(cls.detach().unsqueeze(0).to(torch.float32),
                                            reg.detach().unsqueeze(0).to(torch.float32), anchors=anchor, mode="train",

@@ -59,6 +59,34 @@ def anchors(image_hw, device, stride: int = 16, table=None) -> torch.Tensor:
     return out
 
 
+def tv_anchor_base(size: float, aspect_ratios=(0.5, 1.0, 2.0)) -> np.ndarray:
+    """torchvision AnchorGenerator.generate_anchors for one level (host, [n_ratios,4] fp32, rounded)."""
+    r = np.ascontiguousarray(aspect_ratios, dtype=np.float32)
+    out = np.empty((r.shape[0], 4), dtype=np.float32)
+    _lib.check(_lib.load().frr_tv_anchor_base_host(float(size), r.ctypes.data, int(r.shape[0]), out.ctypes.data),
+               "frr_tv_anchor_base_host")
+    return out
+
+
+def anchors_pyramid(feature_hws, image_hw, device, sizes=(32, 64, 128, 256, 512), aspect_ratios=(0.5, 1.0, 2.0)) -> torch.Tensor:
+    """models/new_model.py:43-44 on the device: torchvision's multi-level AnchorGenerator + the division by (w,h,w,h).
+    ``feature_hws``: (fh, fw) of every pyramid level; one size per level, the same aspect ratios on every level.
+    Returns [sum_l fh_l*fw_l*A, 4] fp32 normalised anchors, levels concatenated."""
+    lib = _lib.load()
+    L = len(feature_hws)
+    if len(sizes) != L:
+        raise ValueError("anchors_pyramid: one size per pyramid level")
+    tabs = np.stack([tv_anchor_base(float(sz), aspect_ratios) for sz in sizes]).astype(np.float32)      # [L,A,4]
+    A = tabs.shape[1]
+    hw = np.ascontiguousarray([[int(h), int(w)] for h, w in feature_hws], dtype=np.int32)
+    n = int((hw[:, 0] * hw[:, 1]).sum()) * A
+    with torch.cuda.device(device):
+        out = torch.empty((n, 4), dtype=torch.float32, device=device)
+        _lib.check(lib.frr_anchors_pyramid(out.data_ptr(), L, hw.ctypes.data, tabs.ctypes.data, A, int(image_hw[0]),
+                                           int(image_hw[1]), _stream()), "frr_anchors_pyramid")
+    return out
+
+
 def rpn_decode(reg, cls, image_hw=None, anchors=None, stride: int = 16, table=None, min_size: float = _MIN_SIZE):
     """Fused A2+P1+P2+P3.  reg [B,N,4]; cls [B,N,2] logits or [B,N] scores.
     Returns boxes [B,N,4], scores [B,N], valid uint8 [B,N]."""

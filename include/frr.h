@@ -56,6 +56,18 @@ int frr_anchors(float* anchors /* [fh*fw*A,4] */, int img_h, int img_w, int stri
                 const float* base_table_host, int A, frr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * A2 (FPN variant)  torchvision.models.detection.rpn.AnchorGenerator(sizes=((32,),(64,),(128,),(256,),(512,)),
+ *     aspect_ratios=((0.5,1.0,2.0),)*5) as built at models/new_model.py:23-25 and called at :43-44, followed by
+ *     `anchor /= (w, h, w, h)`.  frr_tv_anchor_base_host = generate_anchors of one level (fp32 math, round half to
+ *     even) -> [n_ratios,4] on the host; frr_anchors_pyramid = grid_anchors over L <= 8 levels (level_hw_host
+ *     [L,2] = (fh, fw) per level, strides img // grid like torchvision, base_tables_host [L,A,4], A <= 8) written
+ *     normalised to anchors [sum_l fh_l fw_l A, 4] on the device, levels concatenated, cell-major / anchor-minor.
+ * ------------------------------------------------------------------------------------- */
+int frr_tv_anchor_base_host(float size, const float* aspect_ratios, int n_ratios, float* table_host);
+int frr_anchors_pyramid(float* anchors, int L, const int32_t* level_hw_host, const float* base_tables_host, int A,
+                        int img_h, int img_w, frr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * P1-P3  fused RPN decode -- models/model.py:20 (softmax fg), :31-34 (decode, clamp),
  *        :37-41 (min-size filter); utils/util.py:15-26,46-50.  Anchors are generated in
  *        registers (A2) unless `anchors` is given.

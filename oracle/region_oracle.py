@@ -120,6 +120,35 @@ def enumerate_anchors(image_hw, base_size=16, table: np.ndarray | None = None) -
     return out.reshape(fh * fw * A, 4)
 
 
+def tv_anchor_base(size: float, aspect_ratios=(0.5, 1.0, 2.0)) -> np.ndarray:
+    """TV models/detection/anchor_utils.py ``AnchorGenerator.generate_anchors`` for one size (the configuration of
+    models/new_model.py:23-25): all fp32, ``torch.round`` = half to even."""
+    r = np.asarray(aspect_ratios, dtype=f32)
+    hr = np.sqrt(r).astype(f32)
+    wr = (f32(1) / hr).astype(f32)
+    ws = (wr * f32(size)).astype(f32)
+    hs = (hr * f32(size)).astype(f32)
+    return np.rint((np.stack([-ws, -hs, ws, hs], axis=1) / f32(2)).astype(f32)).astype(f32)
+
+
+def tv_anchors_pyramid(feature_hws, image_hw, sizes=(32, 64, 128, 256, 512), aspect_ratios=(0.5, 1.0, 2.0)) -> np.ndarray:
+    """models/new_model.py:43-44: ``AnchorGenerator(...)(ImageList(x, [(w, h)]), features)[0] / (w, h, w, h)``:
+    per level strides = image // grid (integer), shifts (x, y, x, y) row-major over the grid, anchors = shift + base
+    (cell-major, anchor-minor), levels concatenated, fp32 division by the image size."""
+    H, W = int(image_hw[0]), int(image_hw[1])
+    out = []
+    for (fh, fw), sz in zip(feature_hws, sizes):
+        base = tv_anchor_base(sz, aspect_ratios)
+        sy, sx = H // int(fh), W // int(fw)
+        xs = (np.arange(fw, dtype=np.int32) * sx).astype(f32)
+        ys = (np.arange(fh, dtype=np.int32) * sy).astype(f32)
+        yy, xx = np.meshgrid(ys, xs, indexing="ij")
+        sh = np.stack([xx.ravel(), yy.ravel(), xx.ravel(), yy.ravel()], axis=1).astype(f32)
+        out.append((sh[:, None, :] + base[None, :, :]).astype(f32).reshape(-1, 4))
+    a = np.concatenate(out, axis=0)
+    return (a / np.array([W, H, W, H], dtype=f32)).astype(f32)
+
+
 # ----------------------------------------------------------------------------------------
 # NMS  (TV: csrc/ops/cpu/nms_kernel.cpp semantics, SURVEY §8a rows N1/N2)
 # ----------------------------------------------------------------------------------------

@@ -46,6 +46,14 @@ def test_nms_drop_in_unsorted_input(oracle, key):
     assert np.array_equal(keep.cpu().numpy(), g[key].astype(np.int64))
 
 
+def test_nms_drop_in_more_boxes_than_the_reference_path(oracle):
+    """torchvision.ops.nms has no size limit: 20 000 boxes (beyond frr_topk_desc's 16 384) still give the CPU kernel's list."""
+    b, s = synth.random_boxes(123, 20000, cluster=False)
+    b = (b * np.float32(0.2) + np.float32(0.4) * np.random.RandomState(3).uniform(size=(20000, 1)).astype(np.float32)).astype(np.float32)
+    keep = modules.nms(dev(b), dev(s), 0.5)
+    assert np.array_equal(keep.cpu().numpy(), oracle.nms(b, s, 0.5))
+
+
 def test_nms_drop_in_edge_cases():
     e = modules.nms(torch.zeros((0, 4), device=DEV), torch.zeros((0,), device=DEV), 0.5)
     assert e.dtype == torch.int64 and e.numel() == 0
@@ -80,11 +88,12 @@ def test_region_proposal_module(oracle, name, hw, seed, mode):
         assert np.array_equal(rois.cpu().numpy(), tb[keep])
     # against the reference's own output: same number of rois and the same boxes up to exp() ulps, unless a
     # borderline pair flipped (then the count differs and only the stage-wise check above applies)
-    if rois.shape[0] == int(g[f"{name}_nrois"]):
-        head = g[f"{name}_rois_head"]
-        got = rois[:len(head)].cpu().numpy()
-        if np.allclose(got, head, rtol=1e-4, atol=1e-6):
-            np.testing.assert_allclose(got, head, rtol=1e-4, atol=1e-6)
+    # (a flip removes / inserts one roi and shifts the rows after it, so rows are compared as a set, not by position)
+    assert abs(rois.shape[0] - int(g[f"{name}_nrois"])) <= 2
+    head = g[f"{name}_rois_head"]
+    got = rois.cpu().numpy()
+    matched = [bool(np.isclose(got, h[None], rtol=1e-4, atol=1e-6).all(axis=1).any()) for h in head]
+    assert np.mean(matched) >= 0.98, f"only {np.mean(matched):.3f} of the reference's first rois are among the GPU rois"
 
 
 def test_target_maker_modules_like_the_reference_forward(oracle):

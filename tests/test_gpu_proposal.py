@@ -364,6 +364,36 @@ def test_fpn_variant_proposals_reference_goldens(oracle, name, mode):
     assert out.shape[1] == 4 and 0 < out.shape[0] <= post_k
 
 
+@pytest.mark.parametrize("key", ["128x192", "160x160", "800x1344", "800x1333", "600x1000", "97x131"])
+def test_fpn_variant_anchors_generated_on_the_device(oracle, key):
+    """models/new_model.py:43-44: torchvision's 5-level AnchorGenerator + the division by (w,h,w,h) as one kernel -- bit
+    exact vs the reference's own arrays (sha256 goldens; non-divisible sizes give per-axis integer strides)."""
+    from faster_rcnn_pytorch_b200 import modules
+    g = golden("anchors_fpn")
+    h, w = map(int, key.split("x"))
+    hws = [(-(-h // s), -(-w // s)) for s in (4, 8, 16, 32, 64)]
+    a = ops.anchors_pyramid(hws, (h, w), DEV).cpu().numpy()
+    assert a.shape[0] == int(g[f"n_{key}"])
+    assert np.array_equal(sha(a), g[f"sha_{key}"])
+    assert np.array_equal(a, oracle.tv_anchors_pyramid(hws, (h, w)))
+    gen = modules.fpn.AnchorGenerator()
+    t1 = gen((h, w), hws, DEV)
+    assert t1 is gen((h, w), hws, DEV) and np.array_equal(t1.cpu().numpy(), a)          # cached per shape
+
+
+def test_fpn_variant_region_proposal_generates_its_anchors(oracle):
+    """fpn.region_proposal without an anchor argument == with the reference's anchor tensor."""
+    from faster_rcnn_pytorch_b200 import modules
+    g = golden("proposal_fpn")
+    hw = (128, 192)
+    hws = [(-(-hw[0] // s), -(-hw[1] // s)) for s in (4, 8, 16, 32, 64)]
+    a = modules.fpn.region_proposal(dev(g["train_cls"]), dev(g["train_reg"]), dev(g["train_anchor"]), "train")
+    b = modules.fpn.region_proposal(dev(g["train_cls"]), dev(g["train_reg"]), None, "train", image_hw=hw, feature_hws=hws)
+    assert torch.equal(a, b) and a.shape[0] > 0
+    with pytest.raises(ValueError):
+        modules.fpn.region_proposal(dev(g["train_cls"]), dev(g["train_reg"]), None, "train")
+
+
 def test_topk_more_than_65536_anchors_takes_the_general_kernel(oracle):
     """A full-size FPN pyramid (800x1333: 267 069 anchors) is beyond the u16-index fast path."""
     rs = np.random.RandomState(12)

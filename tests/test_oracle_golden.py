@@ -297,3 +297,37 @@ def test_region_loss_vs_reference(oracle, name, kw):
     got = oracle.region_loss(x["rpn_cls"], x["rpn_reg"], x["rpn_tcls"], x["rpn_treg"], x["frc_cls"], x["frc_reg"],
                              x["frc_tcls"], x["frc_treg"])
     np.testing.assert_allclose(got, g[f"{name}_loss"], rtol=2e-6)
+
+
+# ------------------------------------------------------------------------------------ FPN-variant anchors
+FPN_ANCHOR_SIZES = ["128x192", "160x160", "800x1344", "800x1333", "600x1000", "97x131"]
+
+
+def _pyr_hws(h, w):
+    return [(-(-h // s), -(-w // s)) for s in (4, 8, 16, 32, 64)]
+
+
+def oracle_mod():
+    from oracle import region_oracle
+    return region_oracle
+
+
+def test_tv_anchor_base_oracle_and_abi_host_function():
+    """torchvision AnchorGenerator.generate_anchors (models/new_model.py:23-25): the oracle restatement and the host-side
+    C-ABI function both reproduce torchvision's five base tables bit for bit."""
+    from faster_rcnn_pytorch_b200 import ops
+    g = golden("anchors_fpn")
+    for lvl, size in enumerate((32, 64, 128, 256, 512)):
+        assert np.array_equal(oracle_mod().tv_anchor_base(size), g["base"][lvl])
+        assert np.array_equal(ops.tv_anchor_base(size), g["base"][lvl])
+
+
+@pytest.mark.parametrize("key", FPN_ANCHOR_SIZES)
+def test_tv_anchors_pyramid_oracle_matches_reference(key):
+    """models/new_model.py:43-44 (AnchorGenerator on an ImageList, / (w,h,w,h)): sha256 of the reference's own array."""
+    g = golden("anchors_fpn")
+    h, w = map(int, key.split("x"))
+    a = oracle_mod().tv_anchors_pyramid(_pyr_hws(h, w), (h, w))
+    assert a.shape[0] == int(g[f"n_{key}"])
+    assert np.array_equal(sha(a), g[f"sha_{key}"])
+    assert np.array_equal(a[:6], g[f"head_{key}"]) and np.array_equal(a[-6:], g[f"tail_{key}"])
