@@ -272,6 +272,9 @@ class Ctx:
             raise SystemExit("bench.py: no CUDA device (the region stage has no CPU path; use --impl reference)")
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
+        # pinned staging buffers are allocated (first touch) by this thread: keep it on the GPU's NUMA node
+        from faster_rcnn_pytorch_b200 import hostpin
+        self.numa = hostpin.bind_host_thread_to_gpu_node(self.local) if self.world > 1 else {"bound": False}
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
         from faster_rcnn_pytorch_b200 import _lib
@@ -585,7 +588,8 @@ def run_rpn(ctx, args) -> dict:
                 "mode": "double-buffered host pipeline (H2D of step i+1 overlaps kernels of step i), median of 5 runs",
                 "serialized_value": world * B * e2e_steps / (ms_e2e_serial * 1e-3),
                 "host_copy_ceiling": copy_value, "frac_of_host_copy_ceiling": e2e_value / copy_value,
-                "host_copy_ceiling_how": "the same pinned H2D (33 MB) + D2H (2 MB) per step on a copy stream, no kernels"},
+                "host_copy_ceiling_how": "the same pinned H2D (33 MB) + D2H (2 MB) per step on a copy stream, no kernels",
+                "host_thread_numa_binding": ctx.numa},
         "gpu_launches": int(launches),
         "roofline": roof[dominant],
         "roofline_other": {k: v for k, v in roof.items() if k != dominant},

@@ -2,7 +2,7 @@
 launch-list summary, key ncu metrics per kernel, and profiles/traffic.json (DRAM bytes per launch, read by bench.py)."""
 import csv, json, os, shutil, subprocess, sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-R = sys.argv[1] if len(sys.argv) > 1 else "r1"
+R = sys.argv[1] if len(sys.argv) > 1 else "r2"
 G, P = os.path.join(REPO, "gpurun_out"), os.path.join(REPO, "profiles")
 
 
@@ -17,7 +17,7 @@ for name in (f"{R}_bench_launches.csv", f"{R}_stage_profile.log", f"{R}_nms_phas
 open(os.path.join(P, f"{R}_bench_launches_summary.txt"), "w").write(
     run(sys.executable, os.path.join(REPO, "tools", "launch_summary.py"), os.path.join(G, f"{R}_bench_launches.csv")))
 lines = []
-for w in ("rpn", "train", "infer", "joint", "rpn_n2", "rpn_n8"):   # the multi-GPU lines come from separate gpurun --gpus N calls
+for w in ("all", "reference", "rpn", "train", "infer", "joint", "all_n2", "all_n8"):   # the multi-GPU lines come from separate gpurun --gpus N calls
     f = os.path.join(G, f"{R}_bench_{w}.json")
     if os.path.exists(f):
         lines.append(open(f).read().strip())
@@ -39,6 +39,7 @@ for tag in ("proposal", "roi"):
                                "dram_bytes_write": float(r[wr].replace(",", "")) * scale[units[wr]],
                                "us_under_ncu": float(r[hdr.index("gpu__time_duration.sum")].replace(",", "")) *
                                {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(units[hdr.index("gpu__time_duration.sum")], 1.0),
+                               "inst_executed": float(r[hdr.index("smsp__inst_executed.sum")].replace(",", "")),
                                "source": f"profiles/{R}_{tag}_kernels_ncu.txt (ncu --set full, one launch, cold L2 state of the bench)"})
 json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
 print(json.dumps(traffic, indent=1))
