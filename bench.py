@@ -164,13 +164,42 @@ CPU_ARMS = {
 }
 
 
+def torchvision_cpu_nms_ms(n: int = 12000, post: int = 2000):
+    """the reference's own NMS call (torchvision.ops.nms on CPU tensors, models/model.py:53) on
+    one image's score-sorted RPN boxes, beside the oracle port's C kernel on the same boxes.  (ms, ms) or None."""
+    try:
+        import torch
+        import torchvision
+        from oracle import region_oracle as orc, _cbridge
+        _cbridge.load(required=True)
+        from faster_rcnn_pytorch_b200 import synth
+        _, reg, scores = synth.rpn_head_outputs(2000, HW)
+        boxes = orc.decode_clip(reg, orc.enumerate_anchors(HW))
+        valid = orc.min_size_mask(boxes)
+        order = orc.sort_desc(scores[valid])[:n]
+        tb = np.ascontiguousarray(boxes[valid][order])
+        sc = np.arange(len(tb), 0, -1).astype(np.float32)
+        tt, ts = torch.from_numpy(tb), torch.from_numpy(sc)
+        torchvision.ops.nms(tt, ts, 0.7)
+        t0 = time.perf_counter(); k_tv = torchvision.ops.nms(tt, ts, 0.7)[:post]; t_tv = time.perf_counter() - t0
+        t0 = time.perf_counter(); k_or = orc.nms(tb, sc, 0.7)[:post]; t_or = time.perf_counter() - t0
+        same = bool(np.array_equal(k_tv.numpy(), k_or))
+        return {"torchvision_cpu_nms_ms": 1e3 * t_tv, "oracle_c_nms_ms": 1e3 * t_or, "keep_lists_equal": same,
+                "what": f"one image, {len(tb)} score-sorted RPN boxes -> first {post} keeps @0.7, single call"}
+    except Exception as e:  # torchvision missing on the box: the port alone stands
+        return {"unavailable": str(e)[:120]}
+
+
 def cpu_baseline(name: str, threads: int, per_thread: int = 2) -> dict:
     fn, _, _, how = CPU_ARMS[name]
     sample = max(threads, 8) * per_thread
     v, dt = fn(sample, threads)
-    return {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
-            "sample": f"{sample} images of the same workload, oracle port ({how}), one image per thread on {threads} "
-                      f"threads, {dt:.1f} s wall"}
+    out = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
+           "sample": f"{sample} images of the same workload, oracle port ({how}), one image per thread on {threads} "
+                     f"threads, {dt:.1f} s wall"}
+    if name == "rpn":
+        out["nms_kernel_check"] = torchvision_cpu_nms_ms()
+    return out
 
 
 def run_reference(args):
