@@ -14,6 +14,9 @@
 //
 // Numerics: RoIPool max/argmax bit-exact (first strict maximum in h-then-w order, -FLT_MAX start,
 // empty bin -> 0/-1); RoIAlign sums w1*v1+w2*v2+w3*v3+w4*v4 left to right without FMA contraction.
+#include <stdlib.h>
+#include <string.h>
+
 #include "roi_common.cuh"
 
 namespace frr {
@@ -267,6 +270,23 @@ int roi_pool_bwd_fast(const float* grad_out, const int32_t* argmax, const float*
                       int PH, int PW, int nhwc, float* grad_in, frr_stream_t stream);
 int roi_align_bwd_fast(const float* grad_out, const float* rois, int K, int B, int C, int H, int W, int PH, int PW,
                        float scale, int sampling, int aligned, int nhwc, float* grad_in, frr_stream_t stream);
+// colour-class RoIPool backward (roi_pool_bwd.cu): 0 = launched, 1 = outside that path, < 0 = error
+int roi_pool_bwd_color(const float* grad_out, const int32_t* argmax, const float* rois, int K, int B, int C, int H, int W,
+                       int PH, int PW, float scale, int nhwc, float* grad_in, int force_cb, frr_stream_t stream);
+
+// developer knob (A/B measurements only): FRR_ROI_POOL_BWD = old | cb4 | cb8 | cb16
+static int pool_bwd_variant() {
+    static const int v = [] {
+        const char* e = getenv("FRR_ROI_POOL_BWD");
+        if (!e) return 0;
+        if (!strcmp(e, "old")) return -1;
+        if (!strcmp(e, "cb4")) return 4;
+        if (!strcmp(e, "cb8")) return 8;
+        if (!strcmp(e, "cb16")) return 16;
+        return 0;
+    }();
+    return v;
+}
 
 static size_t roi_smem_bytes(int CB, int HW) {
     return ((sizeof(RoiSmemHdr) + 127) & ~(size_t)127) + (size_t)CB * HW * sizeof(float);
@@ -326,8 +346,15 @@ static int roi_backward(const float* grad_out, const int32_t* argmax, const floa
     FRR_CHECK_ARG(K >= 0 && B > 0 && C > 0 && H > 0 && W > 0 && PH > 0 && PW > 0 && B <= 65535, "roi backward: bad sizes");
     bool direct = false;
     if (K > 0) {
-        const int rc = kAlign ? roi_align_bwd_fast(grad_out, rois, K, B, C, H, W, PH, PW, scale, sampling, aligned, nhwc, grad_in, stream)
-                              : roi_pool_bwd_fast(grad_out, argmax, rois, K, B, C, H, W, PH, PW, nhwc, grad_in, stream);
+        int rc = 1;
+        if (kAlign) {
+            rc = roi_align_bwd_fast(grad_out, rois, K, B, C, H, W, PH, PW, scale, sampling, aligned, nhwc, grad_in, stream);
+        } else {
+            const int variant = pool_bwd_variant();
+            if (variant >= 0)
+                rc = roi_pool_bwd_color(grad_out, argmax, rois, K, B, C, H, W, PH, PW, scale, nhwc, grad_in, variant, stream);
+            if (rc == 1) rc = roi_pool_bwd_fast(grad_out, argmax, rois, K, B, C, H, W, PH, PW, nhwc, grad_in, stream);
+        }
         if (rc <= 0) return rc;
         direct = rc == 2;  // the fast path asks for the global-atomic kernel
     }

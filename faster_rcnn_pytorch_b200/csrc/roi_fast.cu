@@ -828,10 +828,19 @@ int roi_align_bwd_fast(const float* grad_out, const float* rois, int K, int B, i
 // Developer hook: copies the 16 phase counters (cycles of CTA (0,0): forward 0 plane load, 1 roi scan, 2 geometry +
 // buffer wait, 3 compute, 4 store issue, 5 drain; backward 8 zero, 9 roi scan, 10 accumulate, 11 tile syncs,
 // 12 plane store) to the host and clears them.  Synchronises the device.
+namespace frr { void pool_bwd_debug_fetch(long long* host_out8); }
 extern "C" int frr_roi_debug_cycles(int64_t* host_out16) {
     FRR_CHECK_ARG(host_out16 != nullptr, "frr_roi_debug_cycles: null pointer");
     long long z[16] = {0};
     FRR_CUDA(cudaMemcpyFromSymbol(host_out16, frr::g_roi_dbg, sizeof(z)));
     FRR_CUDA(cudaMemcpyToSymbol(frr::g_roi_dbg, z, sizeof(z)));
+    // slots 8-15 when the colour-class RoIPool backward ran (roi_pool_bwd.cu): 8 wait full, 9 ring loads + adds, 10 release,
+    // 11 producer wait empty, 12 producer issue, 13 roi scan, 14 zero, 15 store
+    long long pb[8];
+    frr::pool_bwd_debug_fetch(pb);
+    bool any = false;
+    for (int i = 0; i < 8; ++i) any = any || pb[i] != 0;
+    if (any)
+        for (int i = 0; i < 8; ++i) host_out16[8 + i] = pb[i];
     return FRR_OK;
 }

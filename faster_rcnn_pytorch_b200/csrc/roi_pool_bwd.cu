@@ -1,0 +1,460 @@
+// R3: RoIPool 7x7 backward, conflict-free by construction (autograd of models/model.py:113 <- train.py:36;
+// torchvision::_roi_pool_backward: grad_in[b, c, argmax[k, c, bin]] += grad_out[k, c, bin] for argmax != -1).
+//
+// torchvision scatters one global atomic per output element (K*C*49 RED.ADD.F32, at the L2 atomic floor); shared-memory
+// float atomics are a CAS loop on sm_100.  This kernel needs neither:
+//
+//   * a CTA keeps CB channel planes of one image in shared memory (zeroed once, written once with a TMA bulk store);
+//     a WARP owns two planes exclusively (lanes = 2 planes x 16 bins), so no two warps ever touch the same word and
+//     the warps never synchronise with each other while they accumulate;
+//   * the bins of a roi are processed in four COLOUR classes (ph mod 2, pw mod 2).  For a roi of at least 6 feature
+//     pixels per side the pooling windows of two bins that are two apart in a dimension are disjoint
+//         floor((p + 2) * b) >= ceil((p + 1) * b)      (checked per roi with the forward's own fp32 arithmetic),
+//     clipping to the map only shrinks windows, and an argmax lies inside its bin's window -- so within one colour
+//     class all <= 16 argmax pixels of the plane are distinct and the adds are plain LDS / FADD / STS in a fixed
+//     order (deterministic, unlike atomics);
+//   * smaller rois (bin size < 1, windows two apart may coincide) use the smallest stride s per dimension for which
+//     windows s apart are disjoint and walk s_h x s_w colour classes; when that takes more than 12 steps (a side of 1-2
+//     pixels) the roi has few distinct pixels and a general path is cheaper: 32 bins per step, lanes with the same
+//     argmax found with MATCH.ANY (2 cycles per distinct value on sm_100, measured), summed in lane order by the
+//     group's first lane;
+//   * every warp streams the grad_out / argmax rows of its two planes (2 x 98 contiguous words per roi) into its own
+//     shared-memory ring with cp.async, kPbDepth rois ahead of the adds, each word to a class-major position so that
+//     an adding lane fetches its four class values with one 16-byte read: HBM latency is covered without registers,
+//     without a producer warp and without barriers.
+//
+// HBM traffic = the algorithmic bytes: grad_out + argmax read once, grad_in written once (no memset pass).
+// The contract on argmax is torchvision's: it comes from the forward call on the same rois and map shape (an index
+// outside [0, H*W) is ignored instead of written out of bounds).
+#include <stddef.h>
+#include <stdlib.h>
+
+#include "roi_common.cuh"
+
+namespace frr {
+
+constexpr int kPbDepth = 8;     // rois in flight per warp (ring slots)
+constexpr int kPbSlotBytes = 1024;  // ring slot: [32 lanes][4 classes] argmax words, then the same for grad_out
+constexpr int kPbIdCap = 1024;  // input rois scanned per round
+
+constexpr int kPbCombos = 7;  // (stride h, stride w) pairs with at most 12 classes besides (2, 2)
+struct PoolBwdHdr {
+    int cnt[32];
+    int id[kPbIdCap];  // roi index (24 bits) | class stride in h << 24 | class stride in w << 27
+    // per (combo, slot i < 16): the ring word positions (plane half 0) of the slot's bin in each of the <= 12 classes
+    // (0xff = none), byte 12 = number of classes
+    unsigned char steps[kPbCombos][16][16];
+};
+// combo index of a (stride h, stride w) pair, -1 = not tabulated ((2, 2) has its own path, the rest take MATCH.ANY)
+__host__ __device__ constexpr int pb_combo(int sh, int sw) {
+    return sh == 2 && sw == 3 ? 0 : sh == 3 && sw == 2 ? 1 : sh == 3 && sw == 3 ? 2 : sh == 2 && sw == 4 ? 3
+         : sh == 4 && sw == 2 ? 4 : sh == 3 && sw == 4 ? 5 : sh == 4 && sw == 3 ? 6 : -1;
+}
+constexpr int kPbHdrBytes = (sizeof(PoolBwdHdr) + 127) & ~127;
+constexpr int kPbIdMask = (1 << 24) - 1;
+
+// Word position of (plane half, bin) inside the argmax block of a ring slot: the four colour-class values of RMW lane
+// (half, i) are adjacent (one 16-byte read), i = index of the bin inside its class (rows of 4 for even pw, of 3 for odd)
+__host__ __device__ constexpr int ring_pos(int half, int bin) {
+    const int ph = bin / 7, pw = bin - ph * 7;
+    const int q = (ph & 1) * 2 + (pw & 1);
+    const int i = (ph >> 1) * ((pw & 1) ? 3 : 4) + (pw >> 1);
+    return (half * 16 + i) * 4 + q;
+}
+
+// Step table of the strided colour classes, built at compile time: per (combo, slot i < 16) the ring word positions
+// (plane half 0) of the slot's bin in each of the <= 12 classes (0xff = none), byte 12 = number of classes.
+struct PbStepTable {
+    unsigned char v[kPbCombos * 16 * 16];
+    constexpr PbStepTable() : v() {
+        for (int e = 0; e < kPbCombos * 16 * 16; ++e) {
+            const int combo = e >> 8, i = (e >> 4) & 15, t = e & 15;
+            const int sh = combo == 0 || combo == 3 ? 2 : combo == 4 || combo == 6 ? 4 : 3;
+            const int sw = combo == 1 || combo == 4 ? 2 : combo == 3 || combo == 5 ? 4 : 3;
+            const int nw = 6 / sw + 1, nh = 6 / sh + 1;
+            const int ih = i / nw, iw = i - ih * nw;
+            int x = 0xff;
+            if (t < sh * sw) {
+                const int ph = t / sw + sh * ih, pw = t % sw + sw * iw;
+                if (ih < nh && ph < 7 && pw < 7) x = ring_pos(0, ph * 7 + pw);
+            } else if (t == 12) {
+                x = sh * sw;
+            }
+            v[e] = (unsigned char)x;
+        }
+    }
+};
+__device__ const PbStepTable g_pb_steps = PbStepTable();
+
+// developer instrumentation: clock64() cycles of CTA (0,0) warp 0, accumulated over launches (0 accumulate loop, 5 roi
+// scan, 6 zero, 7 store); read through frr_roi_debug_cycles (slots 8-15)
+__device__ long long g_pb_dbg[8];
+#define PB_TICK(slot)                           \
+    if (prof) {                                 \
+        const long long t1_ = clock64();        \
+        acc_[slot] += t1_ - t0_;                \
+        t0_ = t1_;                              \
+    }
+
+// shared memory through 32-bit shared-window addresses (no generic -> shared conversion inside the loops); volatile +
+// "memory": the read-modify-write steps of a warp stay in program order
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t a) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Smallest s in 2..7 such that the (unclipped) windows of bins p and p + s never overlap: floor((p+s)*b) >= ceil((p+1)*b)
+// for all p, evaluated with the forward's own fp32 arithmetic.  r >= 6 gives 2; 7 puts every bin of the dimension into
+// its own class.
+__device__ __forceinline__ int class_stride(int r) {
+    if (r >= 7) return 2;
+    const float bsz = __fdiv_rn((float)r, 7.0f);
+    int lo[8], hi[7];
+#pragma unroll
+    for (int p = 0; p < 7; ++p) {
+        lo[p] = (int)floorf(__fmul_rn((float)p, bsz));
+        hi[p] = (int)ceilf(__fmul_rn((float)(p + 1), bsz));
+    }
+    int s = 2;
+#pragma unroll
+    for (int t = 2; t <= 6; ++t) {
+        bool ok = true;
+#pragma unroll
+        for (int p = 0; p + t < 7; ++p) ok = ok && (lo[p + t] >= hi[p]);
+        if (s == t && !ok) s = t + 1;
+    }
+    return s;
+}
+
+// One round of the roi scan: the rois of image b among rois[k0, k0 + kPbIdCap) are appended to hd->id in ascending order
+// (every thread takes a contiguous run, one block-wide prefix sum).  Returns the list length.  Called by all threads.
+__device__ __forceinline__ int collect_rois(const float* __restrict__ rois, int K, int k0, int b, float scale, PoolBwdHdr* hd) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nt = blockDim.x, nwarps = nt >> 5;
+    const int span = min(kPbIdCap, K - k0);
+    const int per = (span + nt - 1) / nt;  // <= 16 for >= 64 threads
+    const int lo = k0 + tid * per, hi = min(lo + per, k0 + span);
+    unsigned int mine = 0;  // bit j: roi lo + j belongs to image b
+    for (int j = 0; j < per; ++j)
+        if (lo + j < hi && (int)__ldg(rois + 5 * (size_t)(lo + j)) == b) mine |= 1u << j;
+    const int cnt = __popc(mine);
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) hd->cnt[warp] = inc;
+    __syncthreads();
+    int pre = 0, tot = 0;
+    for (int w = 0; w < nwarps; ++w) {
+        const int c = hd->cnt[w];
+        if (w < warp) pre += c;
+        tot += c;
+    }
+    int pos = pre + inc - cnt;
+    while (mine) {
+        const int j = __ffs(mine) - 1;
+        mine &= mine - 1u;
+        const int k = lo + j;
+        const PoolGeom gm = pool_geom(rois + 5 * (size_t)k, scale);
+        hd->id[pos++] = k | (class_stride(gm.rh) << 24) | (class_stride(gm.rw) << 27);
+    }
+    __syncthreads();
+    return tot;
+}
+
+// One accumulate step of the colour path, split in two so that independent work can be placed between the load and the
+// add (the warp stalls only at the first use of `t`): both halves are predicated on a valid pixel index, no branches.
+__device__ __forceinline__ void rmw_load(float& t, int a, uint32_t hw, uint32_t addr) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p ld.shared.f32 %0, [%3];\n\t}" : "+f"(t) : "r"(a), "r"(hw), "r"(addr) : "memory");
+}
+__device__ __forceinline__ void rmw_store(float v, int a, uint32_t hw, uint32_t addr) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p st.shared.f32 [%3], %0;\n\t}" ::"f"(v), "r"(a), "r"(hw), "r"(addr) : "memory");
+}
+__device__ __forceinline__ void cp_async4_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+struct PbVals {  // the four colour-class values of one lane for one roi
+    int a0, a1, a2, a3;
+    float g0, g1, g2, g3;
+    int entry;
+};
+
+template <int CB>
+__global__ void __launch_bounds__(CB * 16)
+    roi_pool_bwd_color_kernel(const float* __restrict__ grad_out, const int32_t* __restrict__ argmax,
+                              const float* __restrict__ rois, int K, int C, int H, int W, float scale, int nhwc,
+                              float* __restrict__ grad_in) {
+    constexpr int kWarps = CB / 2;  // a warp owns two planes
+    constexpr int D = kPbDepth;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    PoolBwdHdr* hd = reinterpret_cast<PoolBwdHdr*>(smem_raw);
+    int* ring = reinterpret_cast<int*>(smem_raw + kPbHdrBytes);  // [kWarps][D][256 words]
+    float* planes = reinterpret_cast<float*>(smem_raw + kPbHdrBytes + kWarps * D * kPbSlotBytes);  // [CB][HW]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y, c0 = blockIdx.x * CB;
+    const int HW = H * W;
+    const int cb = min(CB, C - c0);
+
+    const bool prof = blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
+    long long t0_ = clock64();
+    long long acc_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    {
+        float4* p4 = reinterpret_cast<float4*>(planes);
+        const int n4 = CB * HW / 4;
+        for (int i = tid; i < n4; i += blockDim.x) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = n4 * 4 + tid; i < CB * HW; i += blockDim.x) planes[i] = 0.f;
+        // argmax positions of bins that do not exist (classes with fewer than 16 bins) stay -1 for good
+        for (int i = tid; i < kWarps * D * (kPbSlotBytes / 4); i += blockDim.x) ring[i] = -1;
+        for (int e = tid; e < kPbCombos * 16 * 4; e += blockDim.x)
+            reinterpret_cast<uint32_t*>(&hd->steps[0][0][0])[e] = reinterpret_cast<const uint32_t*>(g_pb_steps.v)[e];
+    }
+    PB_TICK(6);
+
+    // the shared-window base, converted once inside a volatile asm (the compiler would otherwise rematerialise the
+    // conversion -- an S2R -- inside the loop)
+    uint32_t sbase;
+    {
+        uint64_t t;
+        asm volatile("cvta.to.shared.u64 %0, %1;" : "=l"(t) : "l"(smem_raw));
+        sbase = (uint32_t)t;
+    }
+    const uint32_t id0 = sbase + (uint32_t)offsetof(PoolBwdHdr, id);
+    const uint32_t steps0 = sbase + (uint32_t)offsetof(PoolBwdHdr, steps) + 16u * (uint32_t)(lane & 15);
+    const uint32_t ring0 = sbase + kPbHdrBytes + (uint32_t)warp * (D * kPbSlotBytes);
+    const uint32_t planes0 = sbase + kPbHdrBytes + kWarps * D * kPbSlotBytes;
+    const int half = lane >> 4;
+    const int my_pl = 2 * warp + half;
+    const bool pl_ok = my_pl < cb;
+    const uint32_t pl0 = planes0 + (uint32_t)(pl_ok ? my_pl : 0) * (uint32_t)HW * 4u;
+    const uint32_t pair0 = planes0 + (uint32_t)(2 * warp) * (uint32_t)HW * 4u;
+    const int npl = min(2, cb - 2 * warp);  // planes of this warp that exist (<= 0: idle warp)
+    // copy roles: lane l moves words l, l + 32, l + 64, l + 96 of the 49 * npl contiguous words of a roi's row pair to
+    // their class-major positions
+    uint32_t dpos[4];
+    bool cpy[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int w = lane + 32 * j;
+        cpy[j] = w < 49 * npl;
+        dpos[j] = ring0 + (cpy[j] ? 4u * (uint32_t)ring_pos(w / 49, w % 49) : 0u);
+    }
+    const int32_t* src_a = argmax + (size_t)(c0 + 2 * warp) * 49 + lane;
+    const float* src_g = grad_out + (size_t)(c0 + 2 * warp) * 49 + lane;
+    const uint32_t row_pitch = (uint32_t)C * 49u;  // words between consecutive rois
+    const uint32_t myq = ring0 + 16u * (uint32_t)lane;  // this lane's 4 class values inside slot 0
+    const uint32_t uHW = (uint32_t)HW;
+
+    for (int k0 = 0; k0 < K; k0 += kPbIdCap) {
+        const int n = collect_rois(rois, K, k0, b, scale, hd);  // (its barriers also order the initialisation above)
+        PB_TICK(5);
+        if (npl > 0 && n > 0) {
+            // copies of roi r into the ring slot at byte offset `so` (always commits a group; past the end of the list
+            // nothing is read)
+            auto issue = [&](int r, uint32_t so) {
+                const uint32_t live = r < n ? 4u : 0u;
+                const int idn = lds_s32(id0 + 4u * (uint32_t)min(r, n - 1)) & kPbIdMask;
+                const size_t off = (size_t)(uint32_t)idn * row_pitch;
+                const int32_t* sa = src_a + off;
+                const float* sg = src_g + off;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (cpy[j]) {
+                        cp_async4_zfill(dpos[j] + so, sa + 32 * j, live);
+                        cp_async4_zfill(dpos[j] + so + 512u, sg + 32 * j, live);
+                    }
+                }
+                cp_async_commit();
+            };
+            // this lane's class values of the roi in slot `so`; rois that take another path (or a missing plane) get -1
+            auto fetch = [&](int r, uint32_t so, PbVals& v) {
+                v.entry = lds_s32(id0 + 4u * (uint32_t)min(r, n - 1));
+                asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.a0), "=r"(v.a1), "=r"(v.a2), "=r"(v.a3) : "r"(myq + so) : "memory");
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.g0), "=f"(v.g1), "=f"(v.g2), "=f"(v.g3) : "r"(myq + so + 512u) : "memory");
+            };
+            auto mask = [&](PbVals& v) {
+                if (!pl_ok || ((v.entry >> 24) & 63) != (2 | (2 << 3))) v.a0 = v.a1 = v.a2 = v.a3 = -1;
+            };
+            // rois whose windows need more than the four (mod 2, mod 2) classes: straight from the ring slot
+            auto slow = [&](int entry, uint32_t so) {
+                const int sh = (entry >> 24) & 7, sw = (entry >> 27) & 7;
+                const uint32_t sa = ring0 + so;
+                const int combo = pb_combo(sh, sw);
+                if (combo >= 0) {
+                    // classes (ph mod sh, pw mod sw): <= 4 x 4 bins each, windows pairwise disjoint; the slot's bin per
+                    // class comes from the table (one 16-byte read), every step is branch-free
+                    uint32_t w0, w1, w2, w3;
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                                 : "r"(steps0 + (uint32_t)combo * 256u) : "memory");
+                    const int nst = (int)(w3 & 0xffu);
+                    const uint32_t hoff = sa + (uint32_t)half * 256u;
+#define FRR_STEP(word, sh8, t)                                                                           \
+    if (t < nst) {                                                                                       \
+        const uint32_t pb_ = ((word) >> (sh8)) & 0xffu;                                                  \
+        const uint32_t o_ = hoff + 4u * pb_;                                                             \
+        int av_ = -1;                                                                                    \
+        float gv_ = 0.f, t_ = 0.f;                                                                       \
+        if (pl_ok && pb_ != 0xffu) {                                                                     \
+            av_ = lds_s32(o_);                                                                           \
+            gv_ = lds_f32(o_ + 512u);                                                                    \
+        }                                                                                                \
+        const uint32_t pa_ = pl0 + 4u * (uint32_t)av_;                                                   \
+        rmw_load(t_, av_, uHW, pa_);                                                                     \
+        rmw_store(__fadd_rn(t_, gv_), av_, uHW, pa_);                                                    \
+        __syncwarp();                                                                                    \
+    }
+                    FRR_STEP(w0, 0, 0) FRR_STEP(w0, 8, 1) FRR_STEP(w0, 16, 2) FRR_STEP(w0, 24, 3)
+                    FRR_STEP(w1, 0, 4) FRR_STEP(w1, 8, 5) FRR_STEP(w1, 16, 6) FRR_STEP(w1, 24, 7)
+                    FRR_STEP(w2, 0, 8) FRR_STEP(w2, 8, 9) FRR_STEP(w2, 16, 10) FRR_STEP(w2, 24, 11)
+#undef FRR_STEP
+                } else {
+                    // few distinct pixels: 32 bins of one plane per step, equal argmax merged with MATCH.ANY
+#pragma unroll 1
+                    for (int p = 0; p < npl; ++p) {
+                        const uint32_t pp = pair0 + (uint32_t)p * uHW * 4u;
+#pragma unroll 1
+                        for (int ch = 0; ch < 2; ++ch) {
+                            const int bin = ch * 32 + lane;
+                            int av = -1;
+                            float gv = 0.f;
+                            if (bin < 49) {
+                                const uint32_t o = sa + 4u * (uint32_t)ring_pos(p, bin);
+                                av = lds_s32(o);
+                                gv = lds_f32(o + 512u);
+                            }
+                            const bool valid = (uint32_t)av < uHW;
+                            const unsigned int m = __match_any_sync(0xffffffffu, valid ? av : -1 - lane);
+                            const bool leader = (m & (0u - m)) == (1u << lane);
+                            unsigned int rest = (leader && valid) ? (m & (m - 1u)) : 0u;
+                            float sum = gv;
+                            while (__any_sync(0xffffffffu, rest != 0u)) {
+                                const int src = rest ? __ffs(rest) - 1 : lane;
+                                const float v = __shfl_sync(0xffffffffu, gv, src);
+                                if (rest) sum = __fadd_rn(sum, v);
+                                rest &= rest - 1u;
+                            }
+                            if (leader && valid) {
+                                const uint32_t pa = pp + 4u * (uint32_t)av;
+                                sts_f32(pa, __fadd_rn(lds_f32(pa), sum));
+                            }
+                            __syncwarp();
+                        }
+                    }
+                }
+            };
+            // One roi: `cur` (already in registers) is accumulated while its ring slot is refilled with roi r + D and the
+            // values of roi r + 1 are fetched into `nxt` -- three independent instruction streams, interleaved in source
+            // order so that each one's shared-memory latency is covered by the other two.
+            auto body = [&](int r, uint32_t so, uint32_t so_next, PbVals& cur, PbVals& nxt) {
+                if (((cur.entry >> 24) & 63) != (2 | (2 << 3))) slow(cur.entry, so);  // warp-uniform, rare
+                __syncwarp();  // every lane is done with slot `so`
+                float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+                const uint32_t p0 = pl0 + 4u * (uint32_t)cur.a0, p1 = pl0 + 4u * (uint32_t)cur.a1;
+                const uint32_t p2 = pl0 + 4u * (uint32_t)cur.a2, p3 = pl0 + 4u * (uint32_t)cur.a3;
+                rmw_load(t0, cur.a0, uHW, p0);
+                issue(r + D, so);
+                rmw_store(__fadd_rn(t0, cur.g0), cur.a0, uHW, p0);
+                rmw_load(t1, cur.a1, uHW, p1);
+                cp_async_wait<D - 1>();  // this lane's copies of roi r + 1 have landed ...
+                __syncwarp();            // ... and so have the other lanes'
+                fetch(r + 1, so_next, nxt);
+                rmw_store(__fadd_rn(t1, cur.g1), cur.a1, uHW, p1);
+                rmw_load(t2, cur.a2, uHW, p2);
+                mask(nxt);
+                rmw_store(__fadd_rn(t2, cur.g2), cur.a2, uHW, p2);
+                rmw_load(t3, cur.a3, uHW, p3);
+                rmw_store(__fadd_rn(t3, cur.g3), cur.a3, uHW, p3);
+            };
+            for (int r = 0; r < D; ++r) issue(r, (uint32_t)r * kPbSlotBytes);
+            cp_async_wait<D - 1>();
+            __syncwarp();
+            PbVals va, vb;
+            fetch(0, 0u, va);
+            mask(va);
+            uint32_t so = 0;
+#pragma unroll 1
+            for (int r = 0; r < n; r += 2) {
+                const uint32_t so1 = so + kPbSlotBytes == D * kPbSlotBytes ? 0u : so + kPbSlotBytes;
+                body(r, so, so1, va, vb);
+                if (r + 1 >= n) break;
+                const uint32_t so2 = so1 + kPbSlotBytes == D * kPbSlotBytes ? 0u : so1 + kPbSlotBytes;
+                body(r + 1, so1, so2, vb, va);
+                so = so2;
+            }
+            cp_async_wait<0>();
+        }
+        PB_TICK(0);
+        __syncthreads();  // the id list is rewritten by the next round
+    }
+    store_planes(planes, grad_in, b, c0, cb, C, HW, nhwc != 0);
+    PB_TICK(7);
+    if (prof) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (acc_[i]) atomicAdd(reinterpret_cast<unsigned long long*>(&g_pb_dbg[i]), (unsigned long long)acc_[i]);
+    }
+}
+
+void pool_bwd_debug_fetch(long long* host_out8) {
+    long long z[8] = {0};
+    cudaMemcpyFromSymbol(host_out8, g_pb_dbg, sizeof(z));
+    cudaMemcpyToSymbol(g_pb_dbg, z, sizeof(z));
+}
+
+static const size_t kPbSmemLimit = 227 * 1024;
+static size_t pool_bwd_color_smem(int CB, int HW) {
+    return kPbHdrBytes + (size_t)(CB / 2) * kPbDepth * kPbSlotBytes + (size_t)CB * HW * 4;
+}
+
+template <int CB>
+static int launch_pool_bwd_color(const float* go, const int32_t* argmax, const float* rois, int K, int B, int C, int H, int W,
+                                 float scale, int nhwc, float* gin, cudaStream_t st) {
+    auto kern = roi_pool_bwd_color_kernel<CB>;
+    FRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPbSmemLimit));
+    kern<<<dim3((C + CB - 1) / CB, B), CB * 16, pool_bwd_color_smem(CB, H * W), st>>>(go, argmax, rois, K, C, H, W, scale, nhwc,
+                                                                                        gin);
+    return FRR_OK;
+}
+
+// 0 = launched, 1 = outside this path (caller falls back), < 0 = error
+int roi_pool_bwd_color(const float* grad_out, const int32_t* argmax, const float* rois, int K, int B, int C, int H, int W,
+                       int PH, int PW, float scale, int nhwc, float* grad_in, int force_cb, frr_stream_t stream) {
+    if (PH != 7 || PW != 7 || K > kPbIdMask) return 1;
+    if ((reinterpret_cast<uintptr_t>(grad_out) & 3u) || (reinterpret_cast<uintptr_t>(argmax) & 3u)) return 1;
+    const int HW = H * W;
+    // two co-resident CTAs (one zeroes / scans / stores while the other accumulates) when they fit, else one
+    int cbk = 0;
+    if (2 * (pool_bwd_color_smem(8, HW) + 1024) <= kPbSmemLimit) cbk = 8;
+    else if (2 * (pool_bwd_color_smem(4, HW) + 1024) <= kPbSmemLimit) cbk = 4;
+    else if (pool_bwd_color_smem(16, HW) <= kPbSmemLimit) cbk = 16;
+    else if (pool_bwd_color_smem(8, HW) <= kPbSmemLimit) cbk = 8;
+    else if (pool_bwd_color_smem(4, HW) <= kPbSmemLimit) cbk = 4;
+    if (force_cb == 4 || force_cb == 8 || force_cb == 16) cbk = pool_bwd_color_smem(force_cb, HW) <= kPbSmemLimit ? force_cb : 0;
+    if (cbk == 0) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rc = cbk == 16 ? launch_pool_bwd_color<16>(grad_out, argmax, rois, K, B, C, H, W, scale, nhwc, grad_in, st)
+                 : cbk == 8  ? launch_pool_bwd_color<8>(grad_out, argmax, rois, K, B, C, H, W, scale, nhwc, grad_in, st)
+                             : launch_pool_bwd_color<4>(grad_out, argmax, rois, K, B, C, H, W, scale, nhwc, grad_in, st);
+    if (rc) return rc;
+    count_launch();
+    FRR_CHECK_LAUNCH("roi_pool_bwd_color_kernel");
+    return FRR_OK;
+}
+
+}  // namespace frr

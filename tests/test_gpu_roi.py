@@ -98,6 +98,53 @@ def test_roi_align_full_size_vs_oracle(oracle, B, C, fh, fw, K, scale, sr, align
     close_accum(gin.cpu().numpy(), oracle.roi_align_backward(go, rois5, feat.shape, spatial_scale=scale, sampling_ratio=sr, aligned=aligned))
 
 
+def _mixed_rois(seed, K, fh, fw, B, small_frac=0.4):
+    """random rois, a share of them thinner than 7 feature pixels (bin size < 1: coinciding windows), interleaved images,
+    a few masked (-1) rows"""
+    rs = np.random.RandomState(seed)
+    rois5 = synth.random_rois(seed, K, fh, fw, B)
+    small = rs.rand(K) < small_frac
+    for k in np.nonzero(small)[0]:
+        x1, y1 = rs.uniform(0, fw - 1), rs.uniform(0, fh - 1)
+        w = rs.uniform(0.2, 6.0) if rs.rand() < 0.7 else rs.uniform(6.0, fw / 2)
+        h = rs.uniform(0.2, 6.0) if rs.rand() < 0.7 else rs.uniform(6.0, fh / 2)
+        rois5[k, 1:] = [x1, y1, min(x1 + w, fw - 0.01), min(y1 + h, fh - 0.01)]
+    rois5[:, 0] = rs.randint(0, B, size=K)
+    rois5[rs.rand(K) < 0.03, 0] = -1
+    return rois5.astype(np.float32)
+
+
+@pytest.mark.parametrize("B,C,fh,fw,K,relu,channels_last", [
+    (2, 32, 37, 62, 300, False, False),     # 8 planes per CTA, two CTAs per SM
+    (2, 20, 37, 62, 200, True, False),      # partial last channel group (20 = 8 + 8 + 4), post-ReLU ties at 0
+    (1, 16, 50, 83, 1300, True, False),     # 800x1333 map; > 512 rois of one image: several list rounds
+    (3, 16, 37, 62, 400, True, True),       # channels_last gradient
+    (1, 8, 110, 110, 150, False, False),    # 48 KB planes: 4 planes per CTA
+    (2, 6, 20, 20, 100, True, False),       # partial single channel group
+])
+def test_roi_pool_backward_colour_kernel(oracle, B, C, fh, fw, K, relu, channels_last):
+    """roi_pool_bwd_color_kernel (colour classes for rois >= 7x7 pixels, MATCH.ANY merge for smaller ones) against the
+    CPU loop, on the forward's own argmax."""
+    feat = synth.features(740, B, C, fh, fw)
+    if relu:
+        feat = np.maximum(feat, 0.0)  # VGG features are post-ReLU: whole windows of zeros, argmax ties
+    rois5 = _mixed_rois(741, K, fh, fw, B)
+    go = np.random.RandomState(742).standard_normal((K, C, 7, 7)).astype(np.float32)
+    f = dev(feat)
+    if channels_last:
+        f = f.contiguous(memory_format=torch.channels_last)
+    out, arg = ops.roi_pool_forward(f, dev(rois5))
+    live = rois5[:, 0] >= 0
+    wo, wa = oracle.roi_pool_forward(feat, rois5[live])
+    assert np.array_equal(out.cpu().numpy()[live], wo) and np.array_equal(arg.cpu().numpy()[live], wa)
+    gin = ops.roi_pool_backward(dev(go), arg, dev(rois5), feat.shape, channels_last=channels_last)
+    want = oracle.roi_pool_backward(go[live], wa, rois5[live], feat.shape)
+    close_accum(gin.cpu().numpy(), want)
+    # deterministic: fixed summation order, no atomics
+    gin2 = ops.roi_pool_backward(dev(go), arg, dev(rois5), feat.shape, channels_last=channels_last)
+    assert torch.equal(gin, gin2)
+
+
 def test_large_planes_take_the_direct_kernels(oracle):
     """FPN level-0 sized map (200x336 = 262 KB per plane) does not fit shared memory."""
     B, C, fh, fw, K = 1, 4, 200, 336, 60
