@@ -266,24 +266,17 @@ __global__ void __launch_bounds__(256)
 // 7x7 fast paths (roi_fast.cu): 0 = launched, 1 = shape outside the fast path, 2 = use the direct atomic kernel, < 0 = error
 int roi_fwd_fast(bool align, const float* feat, const float* rois, int K, int B, int C, int H, int W, int PH, int PW,
                  float scale, int sampling, int aligned, int nhwc, float* out, int32_t* argmax, frr_stream_t stream);
-int roi_pool_bwd_fast(const float* grad_out, const int32_t* argmax, const float* rois, int K, int B, int C, int H, int W,
-                      int PH, int PW, int nhwc, float* grad_in, frr_stream_t stream);
 int roi_align_bwd_fast(const float* grad_out, const float* rois, int K, int B, int C, int H, int W, int PH, int PW,
                        float scale, int sampling, int aligned, int nhwc, float* grad_in, frr_stream_t stream);
 // colour-class RoIPool backward (roi_pool_bwd.cu): 0 = launched, 1 = outside that path, < 0 = error
 int roi_pool_bwd_color(const float* grad_out, const int32_t* argmax, const float* rois, int K, int B, int C, int H, int W,
-                       int PH, int PW, float scale, int nhwc, float* grad_in, int force_cb, frr_stream_t stream);
+                       int PH, int PW, float scale, int nhwc, float* grad_in, int force_tail, frr_stream_t stream);
 
-// developer knob (A/B measurements only): FRR_ROI_POOL_BWD = old | cb4 | cb8 | cb16
-static int pool_bwd_variant() {
+// developer knob (A/B measurements only): FRR_ROI_POOL_BWD=tail sends every roi through the streaming atomic kernel
+static int pool_bwd_force_tail() {
     static const int v = [] {
         const char* e = getenv("FRR_ROI_POOL_BWD");
-        if (!e) return 0;
-        if (!strcmp(e, "old")) return -1;
-        if (!strcmp(e, "cb4")) return 4;
-        if (!strcmp(e, "cb8")) return 8;
-        if (!strcmp(e, "cb16")) return 16;
-        return 0;
+        return (e && !strcmp(e, "tail")) ? 1 : 0;
     }();
     return v;
 }
@@ -350,10 +343,7 @@ static int roi_backward(const float* grad_out, const int32_t* argmax, const floa
         if (kAlign) {
             rc = roi_align_bwd_fast(grad_out, rois, K, B, C, H, W, PH, PW, scale, sampling, aligned, nhwc, grad_in, stream);
         } else {
-            const int variant = pool_bwd_variant();
-            if (variant >= 0)
-                rc = roi_pool_bwd_color(grad_out, argmax, rois, K, B, C, H, W, PH, PW, scale, nhwc, grad_in, variant, stream);
-            if (rc == 1) rc = roi_pool_bwd_fast(grad_out, argmax, rois, K, B, C, H, W, PH, PW, nhwc, grad_in, stream);
+            rc = roi_pool_bwd_color(grad_out, argmax, rois, K, B, C, H, W, PH, PW, scale, nhwc, grad_in, pool_bwd_force_tail(), stream);
         }
         if (rc <= 0) return rc;
         direct = rc == 2;  // the fast path asks for the global-atomic kernel

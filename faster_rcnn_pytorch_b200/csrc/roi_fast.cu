@@ -15,15 +15,7 @@
 //   consecutive addresses): no per-pass barriers, no staging tile, every lane busy.
 //   RoIAlign (roi_align_fwd_fast_kernel): 9 rois x 49 bins per pass, results staged in a [roi][channel][49] tile (= the
 //   output layout) and written with coalesced 16-byte streaming stores.
-// Backward (RoIPool, CB = 16 or 8): shared-memory float atomics are a CAS loop on sm_100 (LDS / FADD /
-//   ATOMS.CAST.SPIN) and global RED.ADD.F32 costs ~1.3 cycles per lane, so neither is used.  A WARP owns a plane
-//   exclusively (no inter-warp conflicts) and adds with plain LDS / FADD / STS.  Its lanes are 4 rois x 8
-//   bin-slices (lane j of a roi takes bins q = j (mod 8), in a per-lane rotated order so that the lanes of one roi
-//   work on far-apart bins); grad_out / argmax are read straight into registers (8 consecutive floats per roi and
-//   load -> full sectors), software-pipelined one roi-group ahead.  The only possible collisions -- two lanes
-//   hitting the same pixel in the same step -- are resolved by a one-byte ticket per pixel.  (Putting all 224
-//   items of a group into one ticket round was measured 1.6x slower: neighbouring bins then compete.)  Every
-//   plane is written once (TMA store): no memset pass, no global atomics.
+// Backward: RoIPool in roi_pool_bwd.cu (colour classes, no atomics on the plane path); RoIAlign below (separable).
 //
 // Numerics: RoIPool max/argmax bit-exact vs torchvision CPU (same scan order, strict >); RoIAlign keeps
 // torchvision's operation order (w1*v1+w2*v2+w3*v3+w4*v4, samples iy-major, / count), no FMA contraction.
@@ -434,101 +426,6 @@ __global__ void __launch_bounds__(kFlatThreads, (CB <= 8) ? 2 : 1)
 }
 
 // ---------------------------------------------------------------------------------------------
-// RoIPool backward
-// ---------------------------------------------------------------------------------------------
-template <int CB>
-__global__ void __launch_bounds__(CB * 32, 1)
-    roi_pool_bwd_fast_kernel(const float* __restrict__ grad_out, const int32_t* __restrict__ argmax,
-                             const float* __restrict__ rois, int K, int C, int H, int W, int nhwc,
-                             float* __restrict__ grad_in) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    FastHdr* hd = reinterpret_cast<FastHdr*>(smem_raw);
-    float* planes = reinterpret_cast<float*>(smem_raw + kHdrBytes);
-    const int HW = H * W;
-    const int HWp = (HW + 15) & ~15;
-    unsigned char* tags = reinterpret_cast<unsigned char*>(planes + (size_t)CB * HW);  // [CB][HWp]
-    float* itm_g = reinterpret_cast<float*>(tags + (size_t)CB * HWp);                   // [CB][7][32]
-    int* itm_a = reinterpret_cast<int*>(itm_g + CB * 7 * 32);                           // [CB][7][32]
-
-    const int tid = threadIdx.x, lane = tid & 31, c = tid >> 5;  // warp c owns plane c
-    const int b = blockIdx.y, c0 = blockIdx.x * CB;
-    const int cb = min(CB, C - c0);
-    const bool prof = (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0);
-    long long t0_ = clock64();
-    for (int i = tid; i < CB * HW; i += CB * 32) planes[i] = 0.f;
-    float* pl = planes + (size_t)c * HW;
-    unsigned char* tg = tags + (size_t)c * HWp;
-    float* ig = itm_g + c * 7 * 32 + lane;
-    int* ia = itm_a + c * 7 * 32 + lane;
-    __syncthreads();
-    ROI_TICK(8);
-
-    const int rl = lane >> 3, j = lane & 7;  // lane = (roi of the group, bin slice): bins q = j + 8k, k rotated per lane
-    const int rot = (j == 7) ? 1 : (3 * j) % 7;
-    const size_t chan = (size_t)(c0 + c) * 49;
-    for (int tile = 0; tile < K; tile += CB * 32) {
-        const int ns = stage_ids(rois, K, tile, b, hd);
-        ROI_TICK(9);
-        if (c < cb) {
-            float g[7], gn[7];
-            int a[7], an[7];
-            auto fetch = [&](int r0, float* gg, int* aa) {
-                const int r = r0 + rl;
-                const bool have = r < ns;
-                const size_t base = have ? (size_t)hd->id[r] * C * 49 + chan : 0;
-#pragma unroll
-                for (int k = 0; k < 7; ++k) {
-                    const int q = j + 8 * k;
-                    gg[k] = 0.f;
-                    aa[k] = -1;
-                    if (have && q < 49) {
-                        gg[k] = __ldg(grad_out + base + q);
-                        aa[k] = __ldg(argmax + base + q);
-                    }
-                }
-            };
-            fetch(0, g, a);
-            for (int r0 = 0; r0 < ns; r0 += 4) {
-                fetch(r0 + 4, gn, an);  // next group in flight while this one is accumulated
-                // the lane's 7 items go through shared memory ([k][lane], conflict free) so that the rotated order
-                // below is a dynamic address, not a 7-way select chain
-#pragma unroll
-                for (int k = 0; k < 7; ++k) { ig[k * 32] = g[k]; ia[k * 32] = a[k]; }
-                int kk = rot;
-#pragma unroll 1
-                for (int st = 0; st < 7; ++st) {
-                    // rotated order: at step st lane j works on k = (st + rot_j) % 7, rot = {0,3,6,2,5,1,4,1}: the lanes
-                    // of one roi are then >= 2 bins apart in both directions
-                    const int av = ia[kk * 32];
-                    const float gv = ig[kk * 32];
-                    kk = (kk == 6) ? 0 : kk + 1;
-                    bool act = av >= 0;
-                    unsigned int pending = __ballot_sync(0xffffffffu, act);
-                    while (pending) {  // one trip unless two lanes hit the same pixel in this step
-                        if (act) tg[av] = (unsigned char)lane;
-                        __syncwarp();
-                        const bool won = act && tg[av] == (unsigned char)lane;
-                        __syncwarp();
-                        if (won) {
-                            pl[av] = __fadd_rn(pl[av], gv);
-                            act = false;
-                        }
-                        pending = __ballot_sync(0xffffffffu, act);
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 7; ++k) { g[k] = gn[k]; a[k] = an[k]; }
-            }
-        }
-        ROI_TICK(10);
-        __syncthreads();  // ids are rewritten by the next tile
-    }
-    ROI_TICK(11);
-    store_planes(planes, grad_in, b, c0, cb, C, HW, nhwc != 0);
-    ROI_TICK(12);
-}
-
-// ---------------------------------------------------------------------------------------------
 // RoIAlign backward (sampling_ratio = 2)
 // ---------------------------------------------------------------------------------------------
 // The bilinear weights are separable and channel independent.  Per roi the CTA builds, once, the 14 y-sample records
@@ -684,9 +581,6 @@ static size_t align_fwd_smem(int CB, int HW, int rp) {
 }
 // CB <= 8 kernels are built for two CTAs per SM (28 warps hide the shared-memory latency of the window loops)
 static size_t fwd_budget(int CB) { return CB <= 8 ? (kSmemLimit - 2048) / 2 : kSmemLimit; }
-static size_t bwd_fast_smem(int CB, int HW) {
-    return kHdrBytes + (size_t)CB * HW * 4 + (size_t)CB * ((HW + 15) & ~15) + (size_t)CB * 7 * 32 * 8;
-}
 
 template <int CB>
 static int launch_align_fwd(const float* feat, const float* rois, int K, int B, int C, int H, int W, float scale, int aligned,
@@ -750,41 +644,6 @@ int roi_fwd_fast(bool align, const float* feat, const float* rois, int K, int B,
     if (rc) return rc;
     count_launch();
     FRR_CHECK_LAUNCH("roi_align_fwd_fast_kernel");
-    return FRR_OK;
-}
-
-template <int CB>
-static int launch_pool_bwd(const float* go, const int32_t* argmax, const float* rois, int K, int B, int C, int H, int W,
-                           int nhwc, float* gin, cudaStream_t st) {
-    auto kern = roi_pool_bwd_fast_kernel<CB>;
-    const size_t smem = bwd_fast_smem(CB, H * W);
-    FRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-    kern<<<dim3((C + CB - 1) / CB, B), CB * 32, smem, st>>>(go, argmax, rois, K, C, H, W, nhwc, gin);
-    return FRR_OK;
-}
-
-int roi_pool_bwd_fast(const float* grad_out, const int32_t* argmax, const float* rois, int K, int B, int C, int H, int W,
-                      int PH, int PW, int nhwc, float* grad_in, frr_stream_t stream) {
-    if (PH != 7 || PW != 7) return 1;
-    const int HW = H * W;
-    int cbk = 0;
-    for (int t = 16; t >= 4; t >>= 1) {
-        if (bwd_fast_smem(t, HW) > kSmemLimit) continue;
-        cbk = t;
-        if ((long)B * ((C + t - 1) / t) >= (long)num_sms()) break;
-    }
-    if (cbk == 0) return 1;
-    // When 16 planes do not fit shared memory (maps above ~3400 pixels: the 50x83 map of an 800x1333 image) the
-    // warp-owned plane kernel is left with 8 or 4 warps per SM and is latency bound (measured 520 us against 320 us for
-    // global RED.ADD on the config-4 shape): the caller takes the direct atomic kernel then.
-    if (bwd_fast_smem(16, HW) > kSmemLimit) return 2;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int rc = cbk == 16 ? launch_pool_bwd<16>(grad_out, argmax, rois, K, B, C, H, W, nhwc, grad_in, st)
-                 : cbk == 8  ? launch_pool_bwd<8>(grad_out, argmax, rois, K, B, C, H, W, nhwc, grad_in, st)
-                             : launch_pool_bwd<4>(grad_out, argmax, rois, K, B, C, H, W, nhwc, grad_in, st);
-    if (rc) return rc;
-    count_launch();
-    FRR_CHECK_LAUNCH("roi_pool_bwd_fast_kernel");
     return FRR_OK;
 }
 

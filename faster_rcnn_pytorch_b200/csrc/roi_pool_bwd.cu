@@ -13,11 +13,12 @@
 //     clipping to the map only shrinks windows, and an argmax lies inside its bin's window -- so within one colour
 //     class all <= 16 argmax pixels of the plane are distinct and the adds are plain LDS / FADD / STS in a fixed
 //     order (deterministic, unlike atomics);
-//   * smaller rois (bin size < 1, windows two apart may coincide) use the smallest stride s per dimension for which
-//     windows s apart are disjoint and walk s_h x s_w colour classes; when that takes more than 12 steps (a side of 1-2
-//     pixels) the roi has few distinct pixels and a general path is cheaper: 32 bins per step, lanes with the same
-//     argmax found with MATCH.ANY (2 cycles per distinct value on sm_100, measured), summed in lane order by the
-//     group's first lane;
+//   * smaller rois (a side under 6 pixels: bin size < 1, windows two apart may coincide) would need s_h x s_w > 4 classes
+//     (s = smallest stride with disjoint windows) -- more shared-memory steps than one global atomic per element costs.
+//     The plane kernel leaves them out and roi_pool_bwd_tail_kernel adds them afterwards: one CTA per roi streams the
+//     roi's C * 49 contiguous values and issues RED.ADD.F32 onto the stored planes (faster than torchvision's kernel of
+//     the same atomics: perfectly coalesced reads, no per-element index arithmetic).  The strided-class / MATCH.ANY
+//     code stays as the in-kernel path for any roi the list builder does not classify as small;
 //   * every warp streams the grad_out / argmax rows of its two planes (2 x 98 contiguous words per roi) into its own
 //     shared-memory ring with cp.async, kPbDepth rois ahead of the adds, each word to a class-major position so that
 //     an adding lane fetches its four class values with one 16-byte read: HBM latency is covered without registers,
@@ -35,7 +36,7 @@ namespace frr {
 
 constexpr int kPbDepth = 8;     // rois in flight per warp (ring slots)
 constexpr int kPbSlotBytes = 1024;  // ring slot: [32 lanes][4 classes] argmax words, then the same for grad_out
-constexpr int kPbIdCap = 1024;  // input rois scanned per round
+constexpr int kPbIdCap = 512;    // input rois scanned per round
 
 constexpr int kPbCombos = 7;  // (stride h, stride w) pairs with at most 12 classes besides (2, 2)
 struct PoolBwdHdr {
@@ -139,42 +140,84 @@ __device__ __forceinline__ int class_stride(int r) {
     return s;
 }
 
-// One round of the roi scan: the rois of image b among rois[k0, k0 + kPbIdCap) are appended to hd->id in ascending order
-// (every thread takes a contiguous run, one block-wide prefix sum).  Returns the list length.  Called by all threads.
-__device__ __forceinline__ int collect_rois(const float* __restrict__ rois, int K, int k0, int b, float scale, PoolBwdHdr* hd) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nt = blockDim.x, nwarps = nt >> 5;
-    const int span = min(kPbIdCap, K - k0);
-    const int per = (span + nt - 1) / nt;  // <= 16 for >= 64 threads
-    const int lo = k0 + tid * per, hi = min(lo + per, k0 + span);
-    unsigned int mine = 0;  // bit j: roi lo + j belongs to image b
-    for (int j = 0; j < per; ++j)
-        if (lo + j < hi && (int)__ldg(rois + 5 * (size_t)(lo + j)) == b) mine |= 1u << j;
-    const int cnt = __popc(mine);
-    int inc = cnt;
+// rois of a side below ~3-6 pixels: their strided classes need more than 6 steps per roi, more than a global atomic
+// per element costs -> roi_pool_bwd_tail_kernel
+__device__ __forceinline__ bool pb_small(int sh, int sw) { return sh * sw > 4; }
+
+// block-wide exclusive prefix sum of one int per thread (blockDim a multiple of 32, <= 1024); *total = block sum
+__device__ __forceinline__ int pb_block_scan(int v, int* warp_cnt, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    int inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += t;
     }
-    if (lane == 31) hd->cnt[warp] = inc;
+    __syncthreads();  // warp_cnt reuse
+    if (lane == 31) warp_cnt[warp] = inc;
     __syncthreads();
     int pre = 0, tot = 0;
     for (int w = 0; w < nwarps; ++w) {
-        const int c = hd->cnt[w];
+        const int c = warp_cnt[w];
         if (w < warp) pre += c;
         tot += c;
     }
-    int pos = pre + inc - cnt;
+    *total = tot;
+    return pre + inc - v;
+}
+
+// One round of the roi scan over rois[k0, k0 + kPbIdCap): the rois of image b that take the shared-memory paths go to
+// hd->id with their class strides (rois whose strided classes need more than 6 steps are left to
+// roi_pool_bwd_tail_kernel).  The order of the list is a fixed function of the input (determinism of the sums).
+// PER = kPbIdCap / blockDim.  Returns the length of hd->id.  Called by all threads.
+template <int PER>
+__device__ __forceinline__ int collect_rois(const float* __restrict__ rois, int K, int k0, int b, float scale, PoolBwdHdr* hd) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    // pass 1: batch indices of a contiguous run per thread (all loads in flight), compaction of the matching rois
+    const int lo = k0 + tid * PER;
+    float bi[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) bi[j] = __ldg(rois + 5 * (size_t)min(lo + j, K - 1));
+    unsigned int mine = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j)
+        if (lo + j < K && (int)bi[j] == b) mine |= 1u << j;
+    int n = 0;
+    int pos = pb_block_scan(__popc(mine), hd->cnt, &n);
     while (mine) {
         const int j = __ffs(mine) - 1;
         mine &= mine - 1u;
-        const int k = lo + j;
-        const PoolGeom gm = pool_geom(rois + 5 * (size_t)k, scale);
-        hd->id[pos++] = k | (class_stride(gm.rh) << 24) | (class_stride(gm.rw) << 27);
+        hd->id[pos++] = lo + j;
     }
     __syncthreads();
-    return tot;
+    if (n == 0) return 0;  // block-uniform
+    // pass 2: geometry of list entries tid, tid + blockDim, ... (balanced over the threads), split into the two lists
+    int ent[PER];
+    int nb = 0, ns = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        const int e = tid + j * nt;
+        ent[j] = -1;
+        if (e < n) {
+            const int k = hd->id[e];
+            const PoolGeom gm = pool_geom(rois + 5 * (size_t)k, scale);
+            const int sh = class_stride(gm.rh), sw = class_stride(gm.rw);
+            const bool small = pb_small(sh, sw);
+            ent[j] = k | (sh << 24) | (sw << 27) | (small ? (1 << 30) : 0);
+            nb += small ? 0 : 1;
+            ns += small ? 1 : 0;
+        }
+    }
+    int tot = 0;
+    const int packed = pb_block_scan(nb | (ns << 16), hd->cnt, &tot);  // (its barriers: every entry of id has been read)
+    int pb = packed & 0xffff;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        if (ent[j] < 0) continue;
+        if (!(ent[j] & (1 << 30))) hd->id[pb++] = ent[j];
+    }
+    __syncthreads();
+    return tot & 0xffff;
 }
 
 // One accumulate step of the colour path, split in two so that independent work can be placed between the load and the
@@ -262,7 +305,8 @@ __global__ void __launch_bounds__(CB * 16)
     const uint32_t uHW = (uint32_t)HW;
 
     for (int k0 = 0; k0 < K; k0 += kPbIdCap) {
-        const int n = collect_rois(rois, K, k0, b, scale, hd);  // (its barriers also order the initialisation above)
+        // (the barriers of the scan also order the initialisation above)
+        const int n = collect_rois<kPbIdCap / (CB * 16)>(rois, K, k0, b, scale, hd);
         PB_TICK(5);
         if (npl > 0 && n > 0) {
             // copies of roi r into the ring slot at byte offset `so` (always commits a group; past the end of the list
@@ -411,6 +455,49 @@ __global__ void __launch_bounds__(CB * 16)
     }
 }
 
+// The rois the plane kernel skipped (pb_small): one CTA per roi, which leaves at once unless the roi is small; a small
+// roi streams its C * 49 contiguous grad_out / argmax values (8 independent elements per thread in flight) and adds
+// them with RED.ADD.F32 onto the planes the first kernel has already written (stream order).
+__global__ void __launch_bounds__(256)
+    roi_pool_bwd_tail_kernel(const float* __restrict__ grad_out, const int32_t* __restrict__ argmax,
+                             const float* __restrict__ rois, int B, int C, int H, int W, float scale, int nhwc, int all,
+                             float* __restrict__ grad_in) {
+    const int k = blockIdx.x;
+    const float* r = rois + 5 * (size_t)k;
+    const int b = (int)__ldg(r);
+    if (b < 0 || b >= B) return;
+    if (!all) {
+        const PoolGeom gm = pool_geom(r, scale);
+        if (!pb_small(class_stride(gm.rh), class_stride(gm.rw))) return;
+    }
+    const int HW = H * W;
+    const uint32_t uHW = (uint32_t)HW;
+    const int total = C * 49;
+    const size_t src0 = (size_t)k * total, img = (size_t)b * C * HW;
+    constexpr int U = 8;
+    for (int e0 = threadIdx.x; e0 < total; e0 += U * 256) {
+        int av[U];
+        float gv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * 256;
+            av[u] = -1;
+            if (e < total) {
+                av[u] = __ldg(argmax + src0 + e);
+                gv[u] = __ldg(grad_out + src0 + e);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if ((uint32_t)av[u] < uHW) {
+                const int c = (e0 + u * 256) / 49;
+                const size_t o = nhwc ? img + (size_t)av[u] * C + c : img + (size_t)c * HW + av[u];
+                atomicAdd(grad_in + o, gv[u]);
+            }
+        }
+    }
+}
+
 void pool_bwd_debug_fetch(long long* host_out8) {
     long long z[8] = {0};
     cudaMemcpyFromSymbol(host_out8, g_pb_dbg, sizeof(z));
@@ -434,26 +521,30 @@ static int launch_pool_bwd_color(const float* go, const int32_t* argmax, const f
 
 // 0 = launched, 1 = outside this path (caller falls back), < 0 = error
 int roi_pool_bwd_color(const float* grad_out, const int32_t* argmax, const float* rois, int K, int B, int C, int H, int W,
-                       int PH, int PW, float scale, int nhwc, float* grad_in, int force_cb, frr_stream_t stream) {
+                       int PH, int PW, float scale, int nhwc, float* grad_in, int force_tail, frr_stream_t stream) {
     if (PH != 7 || PW != 7 || K > kPbIdMask) return 1;
     if ((reinterpret_cast<uintptr_t>(grad_out) & 3u) || (reinterpret_cast<uintptr_t>(argmax) & 3u)) return 1;
     const int HW = H * W;
-    // two co-resident CTAs (one zeroes / scans / stores while the other accumulates) when they fit, else one
-    int cbk = 0;
-    if (2 * (pool_bwd_color_smem(8, HW) + 1024) <= kPbSmemLimit) cbk = 8;
-    else if (2 * (pool_bwd_color_smem(4, HW) + 1024) <= kPbSmemLimit) cbk = 4;
-    else if (pool_bwd_color_smem(16, HW) <= kPbSmemLimit) cbk = 16;
-    else if (pool_bwd_color_smem(8, HW) <= kPbSmemLimit) cbk = 8;
-    else if (pool_bwd_color_smem(4, HW) <= kPbSmemLimit) cbk = 4;
-    if (force_cb == 4 || force_cb == 8 || force_cb == 16) cbk = pool_bwd_color_smem(force_cb, HW) <= kPbSmemLimit ? force_cb : 0;
-    if (cbk == 0) return 1;
     cudaStream_t st = (cudaStream_t)stream;
-    const int rc = cbk == 16 ? launch_pool_bwd_color<16>(grad_out, argmax, rois, K, B, C, H, W, scale, nhwc, grad_in, st)
-                 : cbk == 8  ? launch_pool_bwd_color<8>(grad_out, argmax, rois, K, B, C, H, W, scale, nhwc, grad_in, st)
-                             : launch_pool_bwd_color<4>(grad_out, argmax, rois, K, B, C, H, W, scale, nhwc, grad_in, st);
+    // Two co-resident CTAs of 8 planes (one zeroes / scans / stores while the other accumulates) when they fit: the
+    // 37 x 62 map of a 600 x 1000 image.  Larger maps (50 x 83 of an 800 x 1333 image: 4 accumulating warps per SM)
+    // are faster with every roi through the streaming atomic kernel (measured 216-300 us against 287-330 us, torchvision
+    // 320-341 us).
+    int cbk = 2 * (pool_bwd_color_smem(8, HW) + 1024) <= kPbSmemLimit ? 8 : 0;
+    if (cbk == 0 || force_tail) {
+        FRR_CUDA(cudaMemsetAsync(grad_in, 0, (size_t)B * C * HW * sizeof(float), st));
+        roi_pool_bwd_tail_kernel<<<K, 256, 0, st>>>(grad_out, argmax, rois, B, C, H, W, scale, nhwc, 1, grad_in);
+        count_launch();
+        FRR_CHECK_LAUNCH("roi_pool_bwd_tail_kernel");
+        return FRR_OK;
+    }
+    const int rc = launch_pool_bwd_color<8>(grad_out, argmax, rois, K, B, C, H, W, scale, nhwc, grad_in, st);
     if (rc) return rc;
     count_launch();
     FRR_CHECK_LAUNCH("roi_pool_bwd_color_kernel");
+    roi_pool_bwd_tail_kernel<<<K, 256, 0, st>>>(grad_out, argmax, rois, B, C, H, W, scale, nhwc, 0, grad_in);
+    count_launch();
+    FRR_CHECK_LAUNCH("roi_pool_bwd_tail_kernel");
     return FRR_OK;
 }
 

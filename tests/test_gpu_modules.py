@@ -212,7 +212,9 @@ def test_torch_library_ops_match_the_module_path_and_pass_opcheck():
     assert torch.equal(out, want) and torch.equal(arg, warg)
     go = torch.randn_like(out)
     out.backward(go)
-    assert torch.equal(feat.grad, ops.roi_pool_backward(go, warg, rois5, feat.shape))
+    # (rois thinner than 6 pixels are added with global atomics: same sums, fp32 order not fixed)
+    ref = ops.roi_pool_backward(go, warg, rois5, feat.shape)
+    assert float((feat.grad - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
     f2 = feat.detach().clone().requires_grad_(True)
     oa = torch.ops.frr.roi_align(f2, rois5, 0.5, 7, 7, 2, False)
     assert torch.equal(oa, ops.roi_align_forward(f2.detach(), rois5, spatial_scale=0.5, sampling_ratio=2))

@@ -31,7 +31,7 @@ for _ in range(reps):
 e1.record()
 torch.cuda.synchronize()
 lib.frr_roi_debug_cycles(buf)
-names = ["", "", "", "", "", "", "", "", "wait_full", "adds", "release", "prod_wait_empty", "prod_issue", "roi_scan", "zero", "store"]
+names = ["", "", "", "", "", "", "", "", "accumulate_loop", "atomic_tail", "-", "-", "-", "roi_scan", "init", "store"]
 print(f"variant {os.environ.get('FRR_ROI_POOL_BWD', 'default')} roi side {lo}-{hi} shape {(B, C, fh, fw, per)}: "
       f"{e0.elapsed_time(e1) / reps * 1e3:.1f} us per launch; cycles of CTA (0,0) per launch:",
       {names[i]: buf[i] // reps for i in range(8, 16)})
