@@ -606,6 +606,10 @@ __global__ void __launch_bounds__(kRsThreads, 1)
         //         per pair: ~2.6 pairs per bucket, so the loops are a few iterations long and every lane is busy (a
         //         thread sorting whole buckets left the warp waiting for its largest bucket: 19 k of 59 k cycles).
         const int stored = (int)hd->stored;
+        // the scatter cursors are dead: their 32 KB stage the output row (u16 anchor index per rank), so that the global
+        // writes of the index row are coalesced instead of one sector per pair (12 000 scattered 4-byte stores)
+        unsigned short* orow = reinterpret_cast<unsigned short*>(hist);
+        const bool stage_row = (size_t)keff * 2 <= 4 * (size_t)kBuckets;
         for (int p2 = tid; p2 < stored; p2 += kRsThreads) {
             const unsigned int ku = keyA[p2];
             const unsigned int ki = idxA[p2];
@@ -619,11 +623,17 @@ __global__ void __launch_bounds__(kRsThreads, 1)
             if (rank < keff) {
                 const size_t oo = (size_t)b * k + rank;
                 const int i = (int)ki;
-                out_idx[oo] = i;
+                if (stage_row) orow[rank] = (unsigned short)ki;
+                else out_idx[oo] = i;
                 if (out_scores) out_scores[oo] = ordered_to_float(ku);
                 if (out_cidx) out_cidx[oo] = (int)(vpre[i >> 5] + __popc(vbits[i >> 5] & ((1u << (i & 31)) - 1u)));
                 if (out_boxes) out_boxes[oo] = boxes[(size_t)b * N + i];
             }
+        }
+        if (stage_row) {
+            __syncthreads();
+            int32_t* orow_g = out_idx + (size_t)b * k;
+            for (int j2 = tid; j2 < keff; j2 += kRsThreads) orow_g[j2] = (int32_t)orow[j2];
         }
     }
     // ---- 5. padding past the count ----------------------------------------------------------------------

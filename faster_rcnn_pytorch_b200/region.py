@@ -142,6 +142,62 @@ class ProposalPlan:
         return graph
 
 
+class ProposalPipeline:
+    """Throughput mode for DEVICE-resident head outputs: ``depth`` independent plans, each on its own stream, so
+    that consecutive batches overlap on the GPU (the top-k kernel runs one CTA per image and the NMS kernel one cluster
+    per image: at 64 images they leave 84 and 20 of the 148 SMs idle, which the neighbouring batch's kernels fill).
+
+    ``submit(cls, reg)`` orders the plan's stream after the caller's current stream (the producer of cls / reg),
+    issues one ``frr_rpn_proposals`` call (or replays the graph captured for these tensors) and returns a ticket;
+    ``result(ticket)`` orders the caller's current stream after that step and returns the plan's ``(rois, count)``
+    (overwritten ``depth`` submits later).  No host synchronisation anywhere."""
+
+    def __init__(self, B: int, N: int, device, depth: int = 2, **plan_kwargs):
+        self.depth = int(depth)
+        self.device = torch.device(device)
+        self.plans = [ProposalPlan(B, N, device, **plan_kwargs) for _ in range(self.depth)]
+        with torch.cuda.device(self.device):
+            self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.depth)]
+        self._done = [torch.cuda.Event() for _ in range(self.depth)]
+        self._graphs = {}
+        self._n = 0
+
+    def capture(self, cls, reg):
+        """Capture the call for these input tensors once per plan; ``submit`` on the same tensors then replays."""
+        for j, plan in enumerate(self.plans):
+            with torch.cuda.stream(self.streams[j]):
+                self._graphs[(j, cls.data_ptr(), reg.data_ptr())] = plan.capture(cls, reg)
+        torch.cuda.synchronize(self.device)
+
+    def submit(self, cls, reg) -> int:
+        t = self._n
+        j = t % self.depth
+        s = self.streams[j]
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            g = self._graphs.get((j, cls.data_ptr(), reg.data_ptr()))
+            if g is not None:
+                g.replay()
+            else:
+                self.plans[j].run(cls, reg)
+            self._done[j].record(s)
+        self._n += 1
+        return t
+
+    def result(self, ticket: int):
+        if ticket < self._n - self.depth or ticket >= self._n:
+            raise ValueError("ProposalPipeline.result: the step's buffers have been reused (or it was never submitted)")
+        j = ticket % self.depth
+        torch.cuda.current_stream(self.device).wait_event(self._done[j])
+        return self.plans[j].rois, self.plans[j].count
+
+    def drain(self):
+        """Order the caller's current stream after every submitted step."""
+        cur = torch.cuda.current_stream(self.device)
+        for e in self._done[:min(self._n, self.depth)]:
+            cur.wait_event(e)
+
+
 class HostProposalPipeline:
     """Proposal layer for HOST inputs (numpy / CPU tensors), double buffered.
 

@@ -16,13 +16,13 @@ N = scores.shape[1]
 names = ["r_load", "r_select", "r_compact", "r_sort", "r_write", "-", "-", "-", "load", "hist", "scan", "scatter", "sort", "write"]
 for k in (12000, 6000):
     oi = torch.empty((B, k), dtype=torch.int32, device=dev)
-    ob = torch.empty((B, k, 4), dtype=torch.float32, device=dev)
+    ob = None if os.environ.get("TOPK_NOBOX") else torch.empty((B, k, 4), dtype=torch.float32, device=dev)  # fused path: indices only
     oc = torch.empty((B,), dtype=torch.int32, device=dev)
     d = torch.zeros(16, dtype=torch.int64, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     def run(dbg):
         _lib.check(lib.frr_topk_desc_profile(scores.data_ptr(), valid.data_ptr(), boxes.data_ptr(), B, N, k, None, oi.data_ptr(),
-                                             None, ob.data_ptr(), oc.data_ptr(), dbg, st), "topk")
+                                             None, ob.data_ptr() if ob is not None else None, oc.data_ptr(), dbg, st), "topk")
     for _ in range(3):
         run(d.data_ptr())
     d.zero_()
