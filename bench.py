@@ -479,12 +479,12 @@ def run_rpn(ctx, args) -> dict:
         run_step(i)
     ms_one = ctx.timed(run_step, args.steps)
     ms_eager = ctx.timed(step, args.steps) if graphs else ms_one
-    # throughput mode (the headline): two batches in flight on two streams (region.ProposalPipeline) -- the top-k kernel
-    # (one CTA per image) and the NMS kernel (one 2-CTA cluster per image) leave 84 / 20 of the 148 SMs idle at 64 images,
-    # which the neighbouring batch's kernels fill.  Every step is still one complete frr_rpn_proposals call on its batch.
+    # throughput mode (the headline): several batches in flight on their own streams (region.ProposalPipeline), NMS with
+    # one CTA per image (least SM time) -- the top-k and NMS kernels leave 84 of the 148 SMs idle at 64 images, which the
+    # neighbouring batches' kernels fill.  Every step is still one complete frr_rpn_proposals call on its batch.
     pipe2 = None
     if graphs and not args.single_stream:
-        pipe2 = region.ProposalPipeline(B, n, dev, depth=2, image_hw=HW, mode="train", logits=True)
+        pipe2 = region.ProposalPipeline(B, n, dev, depth=args.pipe_depth, image_hw=HW, mode="train", logits=True)
         for lg, rg in sets:
             pipe2.capture(lg, rg)
 
@@ -506,12 +506,11 @@ def run_rpn(ctx, args) -> dict:
     torch.cuda.synchronize()
     verified = verify_proposals(plan, plan.rois, plan.count, (0, B - 1)) if rank == 0 else None
     if pipe2 is not None and rank == 0:   # ... and of both plans of the two-stream pipeline, on two consecutive batches
-        for t in range(2):
+        for t in range(pipe2.depth):
             pipe2.submit(*sets[(3 + t) % N_ROTATE])
         pipe2.drain()
         torch.cuda.synchronize()
-        for j, r in enumerate((3 % N_ROTATE, 4 % N_ROTATE)):
-            pj = pipe2.plans[(pipe2._n - 2 + j) % 2]
+        for pj in pipe2.plans:
             verified = verified and verify_proposals(pj, pj.rois, pj.count, (1, B - 2))
     variant = ops.nms_variant(B, PRE_K, THR, POST_K, unit_boxes=True, device=dev)
 
@@ -629,14 +628,14 @@ def run_rpn(ctx, args) -> dict:
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": dict(config_of(WORKLOAD, B), anchors_per_image=n,
                        l2=f"inputs rotated over {N_ROTATE} resident batches ({N_ROTATE * B * n * 24 / 1e6:.0f} MB > 126 MB L2)"),
-        "launch_mode": ("cuda-graph replay of one frr_rpn_proposals call per step, two steps in flight on two streams "
-                        "(region.ProposalPipeline)") if pipe2 is not None else
+        "launch_mode": (f"cuda-graph replay of one frr_rpn_proposals call per step, {args.pipe_depth} steps in flight on "
+                        f"{args.pipe_depth} streams, NMS one CTA per image (region.ProposalPipeline)") if pipe2 is not None else
                        ("cuda-graph replay of one frr_rpn_proposals call per step" if graphs else "eager C-ABI call per step"),
         "value_single_stream": world * B * args.steps / (ms_one * 1e-3),
         "value_eager": world * B * args.steps / (ms_eager * 1e-3),
         "verified": verified,
-        "verified_how": "images 0 and 63 of a timed batch (single-stream plan) and images 1 and 62 of two consecutive batches of "
-                        "the two-stream pipeline (one per plan): valid mask, top-k order, NMS keep list, count and rois bit-exact "
+        "verified_how": "images 0 and 63 of a timed batch (single-stream plan) and images 1 and 62 of one batch per plan of "
+                        "the multi-stream pipeline: valid mask, top-k order, NMS keep list, count and rois bit-exact "
                         "vs the CPU oracle fed the GPU's decoded boxes (outside the timed region)",
         "nms_variant": variant,
         "nms_us_per_image": 1e3 * ms_nms / B,
@@ -1050,6 +1049,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--eager", action="store_true", help="time eager C-ABI calls instead of CUDA-graph replays")
     ap.add_argument("--single-stream", action="store_true", help="rpn workload: one step at a time on one stream")
+    ap.add_argument("--pipe-depth", type=int, default=4, help="rpn workload: batches in flight (region.ProposalPipeline)")
     ap.add_argument("--sampling", default="device", choices=["device", "host"],
                     help="train workload: where the reference's torch.randperm draws are replayed")
     ap.add_argument("--workload", default="all", choices=["all", "rpn", "voc1", "train", "infer", "joint"],

@@ -35,6 +35,7 @@ SIGNATURES = {
     "frr_nms_sorted": (_i, [_p, _p, _i, _i, _d, _i, _p, _p, _p, _i, _p]),
     "frr_rpn_proposals_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i]),
     "frr_rpn_proposals": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _i, _f, _i, _i, _i, _i, _d, _p, _p, _p, C.c_size_t, _p]),
+    "frr_rpn_proposals_opt": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _i, _f, _i, _i, _i, _i, _d, _p, _p, _p, C.c_size_t, _i, _p]),
     "frr_nms_bucket_tune": (_i, [_i, _i, _i, _i]),
     "frr_nms_variant": (_i, [_i, _i, _d, _i, _i, _i, _i, _p]),
     "frr_rpn_proposals_workspace_layout": (_i, [_i, _i, _i, _i, _p]),

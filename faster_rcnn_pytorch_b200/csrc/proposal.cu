@@ -57,7 +57,18 @@ int frr_rpn_proposals(const float* reg, const float* cls, int cls_is_logits, con
                       const float* base_table_host, int A, int img_h, int img_w, int stride, float min_size, int B, int N,
                       int pre_nms_top_k, int post_nms_top_k, double iou_thr, float* rois, int32_t* roi_count,
                       void* workspace, size_t workspace_bytes, frr_stream_t stream) {
+    return frr_rpn_proposals_opt(reg, cls, cls_is_logits, anchors, base_table_host, A, img_h, img_w, stride, min_size, B, N,
+                                 pre_nms_top_k, post_nms_top_k, iou_thr, rois, roi_count, workspace, workspace_bytes, 0, stream);
+}
+
+int frr_rpn_proposals_opt(const float* reg, const float* cls, int cls_is_logits, const float* anchors,
+                          const float* base_table_host, int A, int img_h, int img_w, int stride, float min_size, int B,
+                          int N, int pre_nms_top_k, int post_nms_top_k, double iou_thr, float* rois, int32_t* roi_count,
+                          void* workspace, size_t workspace_bytes, int nms_cluster_size, frr_stream_t stream) {
     using namespace frr;
+    FRR_CHECK_ARG(nms_cluster_size == 0 || nms_cluster_size == 1 || nms_cluster_size == 2 || nms_cluster_size == 4 ||
+                      nms_cluster_size == 8 || nms_cluster_size == 16,
+                  "frr_rpn_proposals_opt: nms_cluster_size must be 0 (automatic), 1, 2, 4, 8 or 16");
     FRR_CHECK_ARG(B >= 0 && N >= 0 && pre_nms_top_k >= 1 && post_nms_top_k >= 1, "frr_rpn_proposals: bad sizes");
     FRR_CHECK_ARG(rois && roi_count && aligned16(rois), "frr_rpn_proposals: rois must be non-null and 16-byte aligned");
     if (B == 0) return FRR_OK;
@@ -88,8 +99,8 @@ int frr_rpn_proposals(const float* reg, const float* cls, int cls_is_logits, con
     rc = frr_topk_desc(scores, valid, nullptr, B, N, k, nullptr, top_idx, nullptr, nullptr, top_count, stream);
     if (rc) return rc;
     // the decoded boxes are clamped to [0,1] (models/model.py:34): unit-range screening
-    return nms_launch(boxes, top_count, B, k, iou_thr, post_nms_top_k, keep, roi_count, rois, 0, 0, nullptr, 1, stream,
-                      top_idx, N);
+    return nms_launch(boxes, top_count, B, k, iou_thr, post_nms_top_k, keep, roi_count, rois, nms_cluster_size, 0, nullptr, 1,
+                      stream, top_idx, N);
 }
 
 }  // extern "C"

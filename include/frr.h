@@ -154,6 +154,15 @@ int frr_rpn_proposals(const float* reg /* [B,N,4] */, const float* cls /* [B,N,2
                       int img_h, int img_w, int stride, float min_size, int B, int N, int pre_nms_top_k,
                       int post_nms_top_k, double iou_thr, float* rois, int32_t* roi_count, void* workspace,
                       size_t workspace_bytes, frr_stream_t stream);
+/* The same call with the NMS launch geometry chosen by the caller: nms_cluster_size = CTAs per image (1, 2, 4, 8, 16;
+ * 0 = automatic, the lowest latency of ONE call: 2 at 64 images, 8-16 for a single image).  1 spends the least SM time
+ * per image (9.8 k vs 15.7 k SM-microseconds per 64 images): the setting for several batches in flight on different
+ * streams (region.ProposalPipeline), where the other batches' kernels fill the SMs a single CTA per image leaves idle.
+ * Results are identical for every setting.                                                                        */
+int frr_rpn_proposals_opt(const float* reg, const float* cls, int cls_is_logits, const float* anchors,
+                          const float* base_table_host, int A, int img_h, int img_w, int stride, float min_size, int B,
+                          int N, int pre_nms_top_k, int post_nms_top_k, double iou_thr, float* rois, int32_t* roi_count,
+                          void* workspace, size_t workspace_bytes, int nms_cluster_size, frr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * R1-R3  RoIPool -- torchvision.ops.RoIPool((7,7), 1.0) at models/model.py:97,113 and its autograd

@@ -68,6 +68,41 @@ def test_headline_config1_every_image_eager_and_graph(oracle):
     _check_plan_outputs(oracle, plan, plan.rois.clone(), plan.count.clone(), sc2, 12000, 2000)
 
 
+def test_proposal_pipeline_batches_in_flight(oracle):
+    """region.ProposalPipeline (the bench's throughput mode): four batches in flight on four streams, NMS with one CTA per
+    image (frr_rpn_proposals_opt, nms_cluster_size = 1), graph replays.  Every image of every batch against the oracle,
+    and bit-equal to the single-plan / automatic-cluster result."""
+    B, n = 64, synth.num_anchors(HW)
+    v = ops.nms_variant(B, 12000, 0.7, 2000, cluster_size=1, unit_boxes=True)
+    assert v["variant"] == "bucketed" and v["cluster_size"] == 1, v
+    pipe = region.ProposalPipeline(B, n, DEV, depth=4, image_hw=HW, mode="train", logits=False)
+    plan = region.ProposalPlan(B, n, DEV, image_hw=HW, mode="train", logits=False)
+    batches = []
+    for t in range(4):
+        _, rg, sc = _inputs(B, 2000 + 100 * t)
+        batches.append((sc, dev(sc), dev(rg)))
+    for _, d_sc, d_rg in batches[:2]:
+        pipe.capture(d_sc, d_rg)                          # two of the batches replay graphs, two run eagerly
+    tickets = [pipe.submit(d_sc, d_rg) for _, d_sc, d_rg in batches]
+    with pytest.raises(ValueError):
+        pipe.result(tickets[-1] + 1)
+    outs = []
+    for t in tickets:
+        rois, count = pipe.result(t)
+        outs.append((rois.clone(), count.clone()))
+    torch.cuda.synchronize()
+    for t, (sc, d_sc, d_rg) in enumerate(batches):
+        _check_plan_outputs(oracle, pipe.plans[t % 4], outs[t][0], outs[t][1], sc, 12000, 2000)
+        r1, c1 = plan.run(d_sc, d_rg)
+        assert torch.equal(r1, outs[t][0]) and torch.equal(c1, outs[t][1])
+    # the buffers of a step are reused `depth` submits later
+    pipe.submit(batches[0][1], batches[0][2])
+    with pytest.raises(ValueError):
+        pipe.result(tickets[0])
+    pipe.drain()
+    torch.cuda.synchronize()
+
+
 def test_headline_logits_path_matches_scores_path_ordering(oracle):
     """Same call with [B,N,2] logits (what bench.py feeds): index-valued outputs checked on the GPU's own scores."""
     B, n = 64, synth.num_anchors(HW)
