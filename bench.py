@@ -310,6 +310,7 @@ class Ctx:
         self._lib = _lib
         self.lib = _lib.load()
         self.peak, self.peak_how, self.sm_mhz = peaks()
+        self.num_sms = int(torch.cuda.get_device_properties(self.dev).multi_processor_count)
 
     def sync_all(self):
         self.torch.cuda.synchronize()
@@ -392,17 +393,18 @@ class Ctx:
             self.dist.destroy_process_group()
 
 
-def _issue_roofline(ctx, kernel: str, ms: float) -> dict:
+def _issue_roofline(ctx, kernel: str, ms: float, sms: int = 148) -> dict:
     """Instruction-issue roofline of a latency / ALU-bound kernel: executed warp instructions per launch (ncu
-    smsp__inst_executed.sum of the committed capture: same kernel, same inputs, deterministic) / live duration, against
-    148 SMs x 4 schedulers x SM clock."""
+    smsp__inst_executed.sum of the committed capture: same kernel, same launch geometry, same inputs, deterministic) /
+    live duration, against the issue rate of the SMs the launch occupies (`sms` x 4 schedulers x SM clock: with several
+    batches in flight the other SMs run the neighbouring batches' kernels)."""
     c = profile_counters(kernel)
     inst = c.get("inst_executed")
-    peak = 148 * 4 * ctx.sm_mhz * 1e6 / 1e9      # G warp-instructions / s
+    peak = sms * 4 * ctx.sm_mhz * 1e6 / 1e9      # G warp-instructions / s
     ach = inst / (ms * 1e-3) / 1e9 if inst else None
     return {"kernel": kernel, "bound": "issue", "achieved": ach, "peak": peak, "unit": "Gwarp-inst/s",
             "frac": (ach / peak) if ach else None, "traffic": ncu_traffic(kernel),
-            "inst_executed_per_launch": inst, "peak_source": f"148 SM x 4 schedulers x {ctx.sm_mhz:.0f} MHz",
+            "inst_executed_per_launch": inst, "peak_source": f"{sms} SMs occupied x 4 schedulers x {ctx.sm_mhz:.0f} MHz",
             "note": "neither HBM- nor tensor-bound: ~0.2 MB of boxes per image; see DESIGN.md 4.3"}
 
 
@@ -451,7 +453,7 @@ def run_rpn(ctx, args) -> dict:
     for r in range(N_ROTATE):
         lg, rg = make_inputs(2000 + 1000 * rank + r, B)
         sets.append((torch.from_numpy(lg).to(dev), torch.from_numpy(rg).to(dev)))
-    plan = region.ProposalPlan(B, n, dev, image_hw=HW, mode="train", logits=True)
+    plan = region.ProposalPlan(B, n, dev, image_hw=HW, mode="train", logits=True, nms_cluster_size=args.nms_cluster)
 
     def step(i):
         lg, rg = sets[i % N_ROTATE]
@@ -512,7 +514,8 @@ def run_rpn(ctx, args) -> dict:
         torch.cuda.synchronize()
         for pj in pipe2.plans:
             verified = verified and verify_proposals(pj, pj.rois, pj.count, (1, B - 2))
-    variant = ops.nms_variant(B, PRE_K, THR, POST_K, unit_boxes=True, device=dev)
+    variant = ops.nms_variant(B, PRE_K, THR, POST_K, cluster_size=1 if pipe2 is not None else args.nms_cluster, unit_boxes=True,
+                              device=dev)
 
     # ---- end to end through the public host-buffer API: pinned host inputs -> H2D -> proposal layer -> D2H of
     #      rois + counts, EVERY step; double buffered (copies of step i+1 overlap the kernels of step i) and,
@@ -588,16 +591,20 @@ def run_rpn(ctx, args) -> dict:
                                      None, t_idx[r].data_ptr(), None, None, t_cnt[r].data_ptr(), st),
                    "frr_topk_desc")
 
-    def k_nms(i, st):
+    nms_cs = 1 if pipe2 is not None else args.nms_cluster     # the launch geometry of the timed path
+
+    def k_nms(i, st, cs=None):
         r = i % N_ROTATE
         _lib.check(lib.frr_nms_sorted_indirect(d_boxes[r].data_ptr(), n, t_idx[r].data_ptr(), t_cnt[r].data_ptr(), B, PRE_K,
-                                               THR, POST_K, keep.data_ptr(), kcnt.data_ptr(), rois.data_ptr(), 0, 1, st),
+                                               THR, POST_K, keep.data_ptr(), kcnt.data_ptr(), rois.data_ptr(),
+                                               nms_cs if cs is None else cs, 1, st),
                    "frr_nms_sorted_indirect")
 
     reps = max(16, min(args.steps, 64))
     ms_dec = ctx.kernel_ms(k_decode, reps)
     ms_topk = ctx.kernel_ms(k_topk, reps)
     ms_nms = ctx.kernel_ms(k_nms, reps)
+    ms_nms_auto = ctx.kernel_ms(lambda i, st: k_nms(i, st, 0), reps)   # automatic geometry: lowest latency of one call
     # single-image NMS latency (whole GPU available to one image: clusters of 8 / 16 CTAs)
     one_src = d_boxes[0][:1].contiguous()
     one_idx = t_idx[0][:1].contiguous()
@@ -613,13 +620,18 @@ def run_rpn(ctx, args) -> dict:
     dec_bytes = B * n * 44.0                      # reg 16 + logits 8 + box 16 + score 4 per anchor
     topk_bytes = B * (n * 5.0 + PRE_K * 4.0)      # scores 4 + valid 1 per anchor; sorted index 4 per pick (NMS gathers)
     kern = {"rpn_decode_kernel": ms_dec, "topk_bucket_kernel": ms_topk, "nms_bucket_kernel": ms_nms}
-    dominant = max(kern, key=kern.get)
+    # SMs a launch occupies (grid / CTAs per SM, capped by the machine): with several batches in flight the step time is
+    # the sum of SM time over the kernels / 148, not the sum of the kernel durations
+    nsm = ctx.num_sms
+    ctas = {"rpn_decode_kernel": nsm, "topk_bucket_kernel": min(B, nsm), "nms_bucket_kernel": min(B * variant["cluster_size"], nsm)}
+    sm_ms = {k: kern[k] * ctas[k] for k in kern}
+    dominant = max(sm_ms, key=sm_ms.get)
     roof = {
         "rpn_decode_kernel": _hbm_roofline(ctx, "rpn_decode_kernel", dec_bytes, ms_dec,
                                            traffic_note="ncu dram read+write of one launch; below the algorithmic bytes because "
                                                         "the 28 MB of outputs stay in the 126 MB L2 for the top-k / NMS kernels"),
         "topk_bucket_kernel": _hbm_roofline(ctx, "topk_bucket_kernel", topk_bytes, ms_topk),
-        "nms_bucket_kernel": _issue_roofline(ctx, "nms_bucket_kernel", ms_nms),
+        "nms_bucket_kernel": _issue_roofline(ctx, "nms_bucket_kernel", ms_nms, sms=ctas["nms_bucket_kernel"]),
     }
     step_ms = ms / args.steps
     line = {
@@ -638,10 +650,13 @@ def run_rpn(ctx, args) -> dict:
                         "the multi-stream pipeline: valid mask, top-k order, NMS keep list, count and rois bit-exact "
                         "vs the CPU oracle fed the GPU's decoded boxes (outside the timed region)",
         "nms_variant": variant,
-        "nms_us_per_image": 1e3 * ms_nms / B,
+        "nms_us_per_image": 1e3 * ms_nms_auto / B,
+        "nms_ms_per_batch_auto_geometry": ms_nms_auto,
         "nms_single_image_latency_us": {f"cluster{cs}": 1e3 * v for cs, v in ms_nms1.items()},
         "kernels_ms_per_batch": kern,
-        "kernels_share_of_step": {k: v / step_ms for k, v in kern.items()},
+        "kernels_sms_occupied": ctas,
+        "kernels_share_of_sm_time": {k: v / sum(sm_ms.values()) for k, v in sm_ms.items()},
+        "step_ms_if_sm_time_packed_perfectly": sum(sm_ms.values()) / nsm,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": pipe.h2d_bytes,
                 "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": ms_e2e / e2e_steps,
                 "mode": "double-buffered host pipeline (H2D of step i+1 overlaps kernels of step i), median of 5 runs",
@@ -652,9 +667,35 @@ def run_rpn(ctx, args) -> dict:
         "gpu_launches": int(launches),
         "roofline": roof[dominant],
         "roofline_other": {k: v for k, v in roof.items() if k != dominant},
-        "dominant_kernel": {"kernel": dominant, "share_of_step": kern[dominant] / step_ms},
+        "dominant_kernel": {"kernel": dominant, "share_of_sm_time": sm_ms[dominant] / sum(sm_ms.values())},
     }
     return line
+
+
+class InFlight:
+    """`depth` side streams for throughput timing: step i runs on stream i % depth (steps on one stream stay ordered, steps
+    on different streams overlap on the GPU); `begin` orders every side stream after the caller's stream (the timing
+    event), `drain` orders the caller's stream after all of them."""
+
+    def __init__(self, torch, dev, depth: int):
+        self.torch, self.dev, self.depth = torch, dev, depth
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+
+    def begin(self):
+        cur = self.torch.cuda.current_stream(self.dev)
+        for st in self.streams:
+            st.wait_stream(cur)
+
+    def run(self, i, fn):
+        if i == 0:
+            self.begin()
+        with self.torch.cuda.stream(self.streams[i % self.depth]):
+            return fn()
+
+    def drain(self):
+        cur = self.torch.cuda.current_stream(self.dev)
+        for st in self.streams:
+            cur.wait_stream(st)
 
 
 # ------------------------------------------------------------------------------------------ configs[0] / configs[3]
@@ -761,6 +802,53 @@ def run_predict(ctx, args, which: str) -> dict:
     best = min(ms, ms_graph) if ms_graph else ms
     value = ctx.world * B * steps / (best * 1e-3)
 
+    # throughput form (configs[3] only; configs[0] is a latency number): `depth` batches in flight, each on its own stream
+    # with its own plan and graphs -- 8 images leave most of the 148 SMs idle in every kernel but RoIPool.  The NCCL gather
+    # of a step is issued on the caller's stream once that step's graph has finished (no host synchronisation).
+    ms_multi, depth = None, args.pipe_depth
+    if graphs and not voc and not args.single_stream:
+        from faster_rcnn_pytorch_b200 import region
+        fl = InFlight(torch, ctx.dev, depth)
+        mg, ok = [], True
+        plans = [region.InferPlan(B, hw, NC, ctx.dev) for _ in range(depth)]   # (kept alive: the graphs hold their buffers)
+        keep["plans"] = plans
+        for j in range(depth):
+            pj = plans[j]
+            row = []
+            with torch.cuda.stream(fl.streams[j]):
+                for r in range(NR):
+                    g, out = ctx.graph_of(lambda r=r, pj=pj: _predict_step(ops, fdist, pj, d["feats"][r], d["lgs"][r], d["rgs"][r],
+                                                                           d["hcls"], d["hreg"], fhw, B, R, NC))
+                    ok &= g is not None
+                    row.append((g, out))
+            mg.append(row)
+        torch.cuda.synchronize()
+        if ok:
+            done = [torch.cuda.Event() for _ in range(depth)]
+
+            def step_multi(i):
+                j = i % depth
+                g, out = mg[j][i % NR]
+
+                def go():
+                    g.replay()
+                    done[j].record()
+                fl.run(i, go)
+                if gather:
+                    torch.cuda.current_stream().wait_event(done[j])
+                    keep["g"] = fdist.gather_detections(out["packed"], out["pc"], ids, equal_batch=True)
+
+            for i in range(max(args.warmup, 3)):
+                step_multi(i)
+            fl.drain()
+            ms_multi = ctx.timed(step_multi, steps, tail=fl.drain)
+            torch.cuda.synchronize()
+            if ctx.rank == 0:   # the last batch every plan produced, against the oracle
+                for j in range(min(depth, steps)):
+                    i_last = ((steps - 1 - j) // depth) * depth + j
+                    verified = bool(verified) and verify_predict(mg[j][i_last % NR][1], d["feats"][i_last % NR], B - 1, R, NC, fhw)
+            value = ctx.world * B * steps / (ms_multi * 1e-3)
+
     # ---- end to end, strict form: EVERY input of the step from pinned host memory (head outputs, feature map, FC head
     #      outputs), the packed detections read back on the host, every step, serialised (latency form)
     pin = {k: ([torch.from_numpy(x).pin_memory() for x in v] if isinstance(v, list) else torch.from_numpy(v).pin_memory())
@@ -812,11 +900,14 @@ def run_predict(ctx, args, which: str) -> dict:
     pooled_bytes = B * 512 * fhw[0] * fhw[1] * 4 + B * R * 512 * 49 * 4
     ms_pool = ctx.kernel_ms(lambda i, st: ops.roi_pool_forward(d["feats"][i % NR], keep["out"]["rois5"], want_argmax=False), 8)
     res = {
-        "value": value, "unit": "images/s", "ms_per_step": best / steps, "steps": steps,
+        "value": value, "unit": "images/s", "ms_per_step": (ms_multi or best) / steps, "steps": steps,
         "latency_us_per_step": 1e3 * best / steps,
         "config": dict(config_of(W_VOC1 if voc else W_INFER, B), l2=f"inputs rotated over {NR} resident sets"),
-        "launch_mode": "cuda-graph replay of the region path" if (ms_graph and ms_graph <= ms) else "eager ops calls",
+        "launch_mode": (f"cuda-graph replay of the region path, {depth} batches in flight on {depth} streams" if ms_multi else
+                        "cuda-graph replay of the region path" if (ms_graph and ms_graph <= ms) else "eager ops calls"),
         "ms_per_step_eager": ms / steps, "ms_per_step_graph": (ms_graph / steps) if ms_graph else None,
+        "ms_per_step_in_flight": (ms_multi / steps) if ms_multi else None,
+        "value_single_stream": ctx.world * B * steps / (best * 1e-3),
         "gpu_launches_per_step": int(launches_per_step), "verified": verified,
         "verified_how": "last image of the last step: RoIPool max (32 channels) and the per-class NMS detections bit-exact vs the "
                         "CPU oracle on the GPU's own rois / probabilities / decoded boxes",
@@ -879,8 +970,49 @@ def run_train(ctx, args) -> dict:
     l0 = ctx._lib.launch_count()
     step(0)
     launches_per_step = ctx._lib.launch_count() - l0
-    ms = ctx.timed(step, steps)
+    ms_one = ctx.timed(step, steps)
     torch.cuda.synchronize()
+    gen2 = targets.DeviceGenerator(dev)
+    ms_td = ctx.timed(lambda i: targets.make_targets(gt, None, lab, props, pcnt, image_hw=hw, generator=gen2), 12) / 12
+    ms_th = ctx.timed(lambda i: targets.make_targets(gt, None, lab, props, pcnt, image_hw=hw), 12) / 12
+
+    # throughput form: `depth` batches in flight on their own streams (each with its own device generator: the sampling
+    # stream of a batch is serial, 75 us on one CTA, and the target makers run small grids -- the RoIPool kernels of the
+    # neighbouring batch fill the machine meanwhile)
+    ms, depth = ms_one, args.pipe_depth
+    if not args.single_stream and args.sampling == "device":
+        fl = InFlight(torch, dev, depth)
+        tplans, tg = [], []
+        for j in range(depth):
+            with torch.cuda.stream(fl.streams[j]):
+                pj = region.TrainPlan(B, hw, dev, generator=targets.DeviceGenerator(dev))
+                row = []
+                for r in range(NR):
+                    # the two halves of the step as CUDA graphs (the head's forward / backward sits between them in a real
+                    # step): targets + rois5 + RoIPool forward, then RoIPool backward on that forward's argmax
+                    g1, o1 = pj.capture_targets_and_pool(feats[r], gt, lab, props, pcnt)
+                    last = dict(pj.last)
+                    g2, o2 = pj.capture_pool_backward(gouts[r])
+                    row.append((g1, g2, o1, o2, last))
+            tplans.append(pj)
+            tg.append(row)
+        torch.cuda.synchronize()
+
+        def step_multi(i):
+            j, r = i % depth, i % NR
+
+            def go():
+                g1, g2, o1, o2, last = tg[j][r]
+                g1.replay()
+                g2.replay()
+                stats["last"] = (o1[1], o2, tplans[j].rois5, last["argmax"], o1[0], r)
+            fl.run(i, go)
+
+        for i in range(max(args.warmup, 3)):
+            step_multi(i)
+        fl.drain()
+        ms = ctx.timed(step_multi, steps, tail=fl.drain)
+        torch.cuda.synchronize()
     out, gin, rois5, arg, t, r_last = stats["last"]
 
     verified = None
@@ -901,10 +1033,6 @@ def run_train(ctx, args) -> dict:
     fbytes = B * C * fh * fw * 4
     ms_f = ctx.kernel_ms(lambda i, st: ops.roi_pool_forward(feats[i % NR], rois5), 12)
     ms_b = ctx.kernel_ms(lambda i, st: ops.roi_pool_backward(gouts[i % NR], arg, rois5, feats[0].shape), 12)
-    gen2 = targets.DeviceGenerator(dev)
-    ms_td = ctx.timed(lambda i: targets.make_targets(gt, None, lab, props, pcnt, image_hw=hw, generator=gen2), 12) / 12
-    ms_th = ctx.timed(lambda i: targets.make_targets(gt, None, lab, props, pcnt, image_hw=hw), 12) / 12
-
     # ---- end to end: what crosses PCIe in the reference's training step for this stage is the ground truth (boxes +
     #      labels, from the data loader, main.py:66-75) going in and nothing coming out (targets feed the loss on the
     #      device); here the sampled class targets + sample counts are read back every step as the step's result
@@ -929,6 +1057,9 @@ def run_train(ctx, args) -> dict:
     fb = fbytes + 2 * obytes
     return {
         "value": world * B * steps / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms / steps, "steps": steps,
+        "value_single_stream": world * B * steps / (ms_one * 1e-3), "ms_per_step_single_stream": ms_one / steps,
+        "launch_mode": (f"cuda-graph replays (targets + RoIPool forward | RoIPool backward), {depth} batches in flight on "
+                        f"{depth} streams" if ms is not ms_one else "eager ops calls, one batch at a time"),
         "config": dict(config_of(W_TRAIN, B), l2=f"features / grad_out rotated over {NR} resident sets (> 126 MB L2)"),
         "kernels_ms_per_batch": {"roi_pool_fwd": ms_f, "roi_pool_bwd": ms_b,
                                  "make_targets(device sampling: 6 kernels, no sync)": ms_td,
@@ -1049,6 +1180,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--eager", action="store_true", help="time eager C-ABI calls instead of CUDA-graph replays")
     ap.add_argument("--single-stream", action="store_true", help="rpn workload: one step at a time on one stream")
+    ap.add_argument("--nms-cluster", type=int, default=0, help="rpn workload, single-stream plan: NMS CTAs per image (0 = auto)")
     ap.add_argument("--pipe-depth", type=int, default=4, help="rpn workload: batches in flight (region.ProposalPipeline)")
     ap.add_argument("--sampling", default="device", choices=["device", "host"],
                     help="train workload: where the reference's torch.randperm draws are replayed")
