@@ -40,7 +40,7 @@ def phases(tag, fn, names):
     lib.frr_roi_debug_cycles(buf)
     print(tag, {n: int(buf[i]) for i, n in names.items()})
 F = {0: "load", 1: "roiscan", 2: "geom+bufwait", 3: "compute", 4: "store_issue", 5: "drain"}
-Bk = {8: "zero", 9: "roiscan", 10: "accum", 11: "tilesync", 12: "planestore"}
+Bk = {8: "accumulate_loop", 13: "roiscan", 14: "init", 15: "planestore"}
 phases("pool_fwd", lambda: ops.roi_pool_forward(feat, rois), F)
 phases("pool_bwd", lambda: ops.roi_pool_backward(go, arg, rois, feat.shape), Bk)
 phases("align_fwd", lambda: ops.roi_align_forward(feat, rois, sampling_ratio=2), F)
