@@ -380,28 +380,40 @@ __global__ void __launch_bounds__(kFlatThreads, (CB <= 8) ? 2 : 1)
                 for (int c = 0; c < CB; ++c) { best[c] = init; bidx[c] = -1; }
 #pragma unroll 1
                 for (int h = hs; h < he; ++h) {
+                    const int end = h * W + we;
+                    // two pixels per trip: four 16-byte reads in flight before the first compare (the loop is bound by the
+                    // latency of its shared-memory reads, not by an execution pipe); an odd tail pixel is fed as -FLT_MAX,
+                    // which never passes the strict compare
 #pragma unroll 1
-                    for (int idx = h * W + ws; idx < h * W + we; ++idx) {
-                        const float4* pp = px + (size_t)idx * NCH;
+                    for (int idx = h * W + ws; idx < end; idx += 2) {
+                        const bool two = idx + 1 < end;
+                        float4 va[NCH], vb[NCH];
 #pragma unroll
                         for (int k = 0; k < NCH; ++k) {
-                            const float4 v = pp[chunk_slot<CB>(idx, k)];
+                            va[k] = px[(size_t)idx * NCH + chunk_slot<CB>(idx, k)];
+                            vb[k] = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+                            if (two) vb[k] = px[(size_t)(idx + 1) * NCH + chunk_slot<CB>(idx + 1, k)];
+                        }
+#pragma unroll
+                        for (int k = 0; k < NCH; ++k) {
                             if (kArg) {
                                 // first strict maximum in scan order (torchvision).  Compare + index select on the ALU
                                 // pipe, the conditional move of the maximum as a predicated FFMA (x * 1 - 0, exact) on
                                 // the FMA pipe
-#define FRR_UPD(val, c)                                                                                                   \
+#define FRR_UPD(val, c, ix)                                                                                               \
     asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %2, %0;\n\t@p fma.rn.f32 %0, %2, 0f3F800000, 0f80000000;\n\tselp.b32 %1, %3, %1, p;\n\t}" \
         : "+f"(best[c]), "+r"(bidx[c])                                                                                     \
-        : "f"(val), "r"(idx))
-                                FRR_UPD(v.x, 4 * k + 0); FRR_UPD(v.y, 4 * k + 1);
-                                FRR_UPD(v.z, 4 * k + 2); FRR_UPD(v.w, 4 * k + 3);
+        : "f"(val), "r"(ix))
+                                FRR_UPD(va[k].x, 4 * k + 0, idx); FRR_UPD(va[k].y, 4 * k + 1, idx);
+                                FRR_UPD(va[k].z, 4 * k + 2, idx); FRR_UPD(va[k].w, 4 * k + 3, idx);
+                                FRR_UPD(vb[k].x, 4 * k + 0, idx + 1); FRR_UPD(vb[k].y, 4 * k + 1, idx + 1);
+                                FRR_UPD(vb[k].z, 4 * k + 2, idx + 1); FRR_UPD(vb[k].w, 4 * k + 3, idx + 1);
 #undef FRR_UPD
                             } else {
-                                best[4 * k + 0] = fmaxf(best[4 * k + 0], v.x);
-                                best[4 * k + 1] = fmaxf(best[4 * k + 1], v.y);
-                                best[4 * k + 2] = fmaxf(best[4 * k + 2], v.z);
-                                best[4 * k + 3] = fmaxf(best[4 * k + 3], v.w);
+                                best[4 * k + 0] = fmaxf(best[4 * k + 0], fmaxf(va[k].x, vb[k].x));
+                                best[4 * k + 1] = fmaxf(best[4 * k + 1], fmaxf(va[k].y, vb[k].y));
+                                best[4 * k + 2] = fmaxf(best[4 * k + 2], fmaxf(va[k].z, vb[k].z));
+                                best[4 * k + 3] = fmaxf(best[4 * k + 3], fmaxf(va[k].w, vb[k].w));
                             }
                         }
                     }
