@@ -260,6 +260,93 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// RoIAlign backward for maps on which the separable plane kernel (roi_fast.cu) is left with 8 or fewer planes per SM
+// (50 x 83: latency bound, 2.7 ms): one CTA per roi.  The <= 16 bilinear taps of every bin (2 x 2 samples x 4 taps,
+// channel independent) are built once per roi, weights divided by the sample count and taps on the same pixel merged
+// (neighbouring samples share pixel rows / columns: ~9 distinct pixels per bin instead of 16), then the roi's C * 49
+// contiguous gradients are streamed and scattered with RED.ADD.F32.  A thread keeps ONE bin for every element it visits
+// (490 = 10 x 49 threads, element t + 490 j has bin t % 49), so the bin's taps live in registers for the whole roi and an
+// element costs one load + one multiply and one atomic per tap: 1.10-1.49 ms on that map (torchvision, which recomputes
+// the geometry per element and issues all 16 atomics: 1.82-1.90 ms); 0.84-1.30 ms at 37 x 62 (plane kernel 1.21-1.25 ms).
+struct AlignTapTable {
+    int n[49];
+    int idx[49][16];
+    float w[49][16];
+};
+
+constexpr int kAlignStreamThreads = 490;  // 10 x 49: thread t keeps bin t % 49 for every element t + 490 j it visits
+
+__global__ void __launch_bounds__(kAlignStreamThreads)
+    roi_align_bwd_stream_kernel(const float* __restrict__ grad_out, const float* __restrict__ rois, int B, int C, int H, int W,
+                                float scale, int aligned, int nhwc, float* __restrict__ grad_in /* zeroed */) {
+    __shared__ AlignTapTable tb;
+    const int k = blockIdx.x;
+    const float* r = rois + 5 * (size_t)k;
+    const int b = (int)__ldg(r);
+    if (b < 0 || b >= B) return;
+    if (threadIdx.x < 49) {
+        const int bin = threadIdx.x, ph = bin / 7, pw = bin - ph * 7;
+        const AlignGeom g = align_geom(r, scale, 7, 7, 2, aligned != 0);
+        int n = 0;
+        for (int iy = 0; iy < 2; ++iy) {
+            const float y = sample_y(g, ph, iy);
+            for (int ix = 0; ix < 2; ++ix) {
+                const float x = sample_x(g, pw, ix);
+                Taps t;
+                if (!bilinear_taps(y, x, H, W, t)) continue;
+                const int pi[4] = {t.p1, t.p2, t.p3, t.p4};
+                const float wi[4] = {t.w1, t.w2, t.w3, t.w4};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float wq = __fmul_rn(wi[q], 0.25f);
+                    int j = 0;
+                    while (j < n && tb.idx[bin][j] != pi[q]) ++j;
+                    if (j < n) {
+                        tb.w[bin][j] = __fadd_rn(tb.w[bin][j], wq);
+                    } else {
+                        tb.idx[bin][n] = pi[q];
+                        tb.w[bin][n] = wq;
+                        ++n;
+                    }
+                }
+            }
+        }
+        for (int j = n; j < 16; ++j) { tb.idx[bin][j] = 0; tb.w[bin][j] = 0.f; }
+        tb.n[bin] = n;
+    }
+    __syncthreads();
+    // the taps of this thread's bin, in registers for the whole roi (pixel offsets pre-multiplied by the pixel stride)
+    const int bin = threadIdx.x % 49;
+    const int HW = H * W;
+    const size_t ps = nhwc ? (size_t)C : 1;
+    const int n = tb.n[bin];
+    int ti[16];
+    float tw[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { ti[j] = tb.idx[bin][j] * (int)ps; tw[j] = tb.w[bin][j]; }
+    const int total = C * 49;
+    const size_t src0 = (size_t)k * total, img = (size_t)b * C * HW;
+    const size_t cstep = nhwc ? (size_t)1 : (size_t)HW;  // channel stride
+    constexpr int U = 4;
+    for (int e0 = threadIdx.x; e0 < total; e0 += U * kAlignStreamThreads) {
+        float gv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * kAlignStreamThreads;
+            gv[u] = e < total ? __ldg(grad_out + src0 + e) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * kAlignStreamThreads;
+            if (e >= total) break;
+            float* base = grad_in + img + (size_t)(e / 49) * cstep;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (j < n) atomicAdd(base + ti[j], __fmul_rn(gv[u], tw[j]));
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -350,6 +437,13 @@ static int roi_backward(const float* grad_out, const int32_t* argmax, const floa
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int HW = H * W;
+    if (kAlign && direct) {  // (rc == 2 is only returned for 7x7 bins with sampling_ratio 2)
+        FRR_CUDA(cudaMemsetAsync(grad_in, 0, (size_t)B * C * HW * sizeof(float), st));
+        roi_align_bwd_stream_kernel<<<K, kAlignStreamThreads, 0, st>>>(grad_out, rois, B, C, H, W, scale, aligned, nhwc, grad_in);
+        count_launch();
+        FRR_CHECK_LAUNCH("roi_align_bwd_stream_kernel");
+        return FRR_OK;
+    }
     const int cb = direct ? 0 : pick_cb(B, C, HW);
     if (cb > 0) {
         const size_t smem = roi_smem_bytes(cb, HW);

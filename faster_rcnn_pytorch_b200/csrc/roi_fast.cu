@@ -684,6 +684,9 @@ int roi_align_bwd_fast(const float* grad_out, const float* rois, int K, int B, i
         if ((long)B * ((C + t - 1) / t) >= (long)num_sms()) break;
     }
     if (cbk == 0) return 1;
+    // when 16 planes do not fit (maps above ~3400 pixels: 50 x 83) this kernel is left with 8 warps per SM and is latency
+    // bound (2.7 ms on the config-4 shape): the caller takes the streaming atomic kernel (1.9-2.3 ms)
+    if (align_bwd_smem(16, HW) > kSmemLimit) return 2;
     cudaStream_t st = (cudaStream_t)stream;
     const int rc = cbk == 16 ? launch_align_bwd<16>(grad_out, rois, K, B, C, H, W, scale, aligned, nhwc, grad_in, st)
                  : cbk == 8  ? launch_align_bwd<8>(grad_out, rois, K, B, C, H, W, scale, aligned, nhwc, grad_in, st)
