@@ -181,7 +181,10 @@ int frr_rois5(const float* rois, const int32_t* count, int B, int R, float fw, f
               frr_stream_t stream);
 int frr_roi_pool_fwd(const float* feat, const float* rois, int K, int B, int C, int H, int W, int PH, int PW,
                      float spatial_scale, int channels_last, float* out, int32_t* argmax, frr_stream_t stream);
-/* grad_in [B,C,H,W] (same memory format as feat) is fully written (no pre-zeroing needed). */
+/* grad_in [B,C,H,W] (same memory format as feat) is fully written (no pre-zeroing needed).  Rois of at least 6 feature
+ * pixels per side are accumulated in shared memory in a fixed order (bit-reproducible); smaller rois, and every roi on maps
+ * whose 8 planes do not fit twice per SM, are added with global fp32 atomics (same sums, order not fixed).  argmax must be
+ * the forward's output for the same rois / map shape (torchvision's contract); indices outside [0, H*W) are ignored. */
 int frr_roi_pool_bwd(const float* grad_out, const int32_t* argmax, const float* rois, int K, int B, int C, int H,
                      int W, int PH, int PW, float spatial_scale, int channels_last, float* grad_in,
                      frr_stream_t stream);
