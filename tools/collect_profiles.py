@@ -20,7 +20,9 @@ lines = []
 for w in ("all", "reference", "rpn", "train", "infer", "joint", "all_n2", "all_n8"):   # the multi-GPU lines come from separate gpurun --gpus N calls
     f = os.path.join(G, f"{R}_bench_{w}.json")
     if os.path.exists(f):
-        lines.append(open(f).read().strip())
+        js = [l for l in open(f).read().splitlines() if l.startswith("{")]   # (torchrun prints a banner on stdout)
+        if js:
+            lines.append(js[-1])
 open(os.path.join(P, f"{R}_bench.json"), "w").write("\n".join(lines) + "\n")
 traffic = {}
 for tag in ("proposal", "roi"):
