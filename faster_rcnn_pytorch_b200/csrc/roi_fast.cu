@@ -338,9 +338,21 @@ __global__ void __launch_bounds__(kFlatThreads, (CB <= 8) ? 2 : 1)
     ROI_TICK(0);
 
     for (int tile = 0; tile < K; tile += kFlatThreads) {
-        const int ns = stage_ids(rois, K, tile, b, hd);
+        int ns = stage_ids(rois, K, tile, b, hd);
         if (ns == 0) continue;  // block-uniform
         if (ns > kWarps) order_ids_by_window(rois, scale, ns, hd);
+        if (gridDim.z > 1) {
+            // thin grids (one image): the rois of the image are dealt to gridDim.z CTAs that hold the same planes, every
+            // gridDim.z-th entry of the list ordered by window size each
+            const int nz = gridDim.z, z = blockIdx.z;
+            const int mine = (ns - z + nz - 1) / nz;
+            const int v = (tid < mine) ? hd->id[tid * nz + z] : 0;
+            __syncthreads();
+            if (tid < mine) hd->id[tid] = v;
+            __syncthreads();
+            ns = mine;
+            if (ns <= 0) continue;  // block-uniform
+        }
         ROI_TICK(1);
         for (int g0 = 0; g0 < ns; g0 += kFlatGeoCap) {
             const int ng = min(kFlatGeoCap, ns - g0);
@@ -614,8 +626,11 @@ static int launch_flat(const float* feat, const float* rois, int K, int B, int C
                        float* out, int32_t* argmax, cudaStream_t st) {
     auto kern = roi_pool_fwd_flat_kernel<CB, kArg>;
     FRR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-    kern<<<dim3((C + CB - 1) / CB, B), kFlatThreads, flat_smem(CB, H * W), st>>>(feat, rois, K, C, H, W, scale, nhwc, out,
-                                                                                  argmax);
+    // fewer CTAs than resident slots (two per SM): split the rois of an image over 2 or 4 CTAs with the same planes
+    const long ctas = (long)B * ((C + CB - 1) / CB), slots = 2L * num_sms();
+    const int nz = (CB <= 8 && ctas * 4 <= slots) ? 4 : (CB <= 8 && ctas * 2 <= slots) ? 2 : 1;
+    kern<<<dim3((C + CB - 1) / CB, B, nz), kFlatThreads, flat_smem(CB, H * W), st>>>(feat, rois, K, C, H, W, scale, nhwc, out,
+                                                                                      argmax);
     return FRR_OK;
 }
 
@@ -631,6 +646,9 @@ int roi_fwd_fast(bool align, const float* feat, const float* rois, int K, int B,
         int cbk = 0;
         if (flat_smem(8, HW) <= fwd_budget(8)) cbk = 8;
         else if (flat_smem(4, HW) <= fwd_budget(4)) cbk = 4;
+        // a single image (or a thin batch) with 8 channels per CTA leaves SMs without a CTA (1 x 512 / 8 = 64 CTAs on 148
+        // SMs): 4 channels per CTA then
+        if (cbk == 8 && (long)B * ((C + 7) / 8) < (long)num_sms()) cbk = 4;
         for (int t = 16; t >= 4 && cbk == 0; t >>= 1)
             if (flat_smem(t, HW) <= kSmemLimit) cbk = t;
         if (cbk == 0) return 1;
