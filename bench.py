@@ -813,7 +813,8 @@ def run_predict(ctx, args, which: str) -> dict:
         from faster_rcnn_pytorch_b200 import region
         fl = InFlight(torch, ctx.dev, depth)
         mg, ok = [], True
-        plans = [region.InferPlan(B, hw, NC, ctx.dev) for _ in range(depth)]   # (kept alive: the graphs hold their buffers)
+        # (kept alive: the graphs hold their buffers; one NMS / top-k CTA per image = the least SM time, as in ProposalPipeline)
+        plans = [region.InferPlan(B, hw, NC, ctx.dev, nms_cluster_size=1) for _ in range(depth)]
         keep["plans"] = plans
         for j in range(depth):
             pj = plans[j]

@@ -5,6 +5,9 @@
 
 namespace frr {
 
+int topk_desc_impl(const float* scores, const uint8_t* valid, const float* boxes, int B, int N, int k, float* out_scores,
+                   int32_t* out_idx, int32_t* out_cidx, float* out_boxes, int32_t* out_count, int cluster_hint,
+                   frr_stream_t stream);
 int nms_launch(const float* boxes, const int32_t* counts, int B, int n, double iou_thr, int max_keep, int32_t* keep,
                int32_t* keep_count, float* out_boxes, int cluster_size, int threads, long long* dbg, int unit_boxes,
                frr_stream_t stream, const int32_t* gather_idx = nullptr, int src_n = 0);
@@ -96,7 +99,9 @@ int frr_rpn_proposals_opt(const float* reg, const float* cls, int cls_is_logits,
         return FRR_OK;
     }
     // top-k writes only the sorted indices; NMS gathers the candidates it visits straight from the decoded boxes
-    rc = frr_topk_desc(scores, valid, nullptr, B, N, k, nullptr, top_idx, nullptr, nullptr, top_count, stream);
+    // (nms_cluster_size = 1 is the caller's throughput setting: one CTA per image in the top-k as well)
+    rc = topk_desc_impl(scores, valid, nullptr, B, N, k, nullptr, top_idx, nullptr, nullptr, top_count,
+                        nms_cluster_size == 1 ? 1 : 0, stream);
     if (rc) return rc;
     // the decoded boxes are clamped to [0,1] (models/model.py:34): unit-range screening
     return nms_launch(boxes, top_count, B, k, iou_thr, post_nms_top_k, keep, roi_count, rois, nms_cluster_size, 0, nullptr, 1,

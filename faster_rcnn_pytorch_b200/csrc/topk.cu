@@ -223,7 +223,11 @@ static size_t topk_smem_bytes(int nchunks, int P) {
 
 int topk_radix_launch(const float* scores, const uint8_t* valid, const float* boxes, int B, int N, int k,
                       float* out_scores, int32_t* out_idx, int32_t* out_cidx, float* out_boxes, int32_t* out_count,
-                      long long* dbg, frr_stream_t stream);
+                      long long* dbg, frr_stream_t stream, int cluster_hint);
+
+int topk_desc_impl(const float* scores, const uint8_t* valid, const float* boxes, int B, int N, int k, float* out_scores,
+                   int32_t* out_idx, int32_t* out_cidx, float* out_boxes, int32_t* out_count, int cluster_hint,
+                   frr_stream_t stream);
 
 }  // namespace frr
 
@@ -236,13 +240,20 @@ extern "C" int frr_topk_desc_profile(const float* scores, const uint8_t* valid, 
     using namespace frr;
     FRR_CHECK_ARG(scores && out_idx && out_count && dbg_cycles && B > 0 && N > 0 && k > 0, "frr_topk_desc_profile: bad arguments");
     const int rc = topk_radix_launch(scores, valid, boxes, B, N, k, out_scores, out_idx, out_cidx, out_boxes, out_count,
-                                     (long long*)dbg_cycles, stream);
+                                     (long long*)dbg_cycles, stream, 1);
     return rc == 1 ? FRR_E_UNSUPPORTED : rc;
 }
 
 extern "C" int frr_topk_desc(const float* scores, const uint8_t* valid, const float* boxes, int B, int N, int k,
                              float* out_scores, int32_t* out_idx, int32_t* out_cidx, float* out_boxes,
                              int32_t* out_count, frr_stream_t stream) {
+    return frr::topk_desc_impl(scores, valid, boxes, B, N, k, out_scores, out_idx, out_cidx, out_boxes, out_count, 0, stream);
+}
+
+// cluster_hint: 0 = CTAs per image chosen for the lowest latency of this call, 1 = one CTA per image
+int frr::topk_desc_impl(const float* scores, const uint8_t* valid, const float* boxes, int B, int N, int k, float* out_scores,
+                        int32_t* out_idx, int32_t* out_cidx, float* out_boxes, int32_t* out_count, int cluster_hint,
+                        frr_stream_t stream) {
     using namespace frr;
     FRR_CHECK_ARG(scores && out_idx && out_count, "frr_topk_desc: null pointer");
     FRR_CHECK_ARG(B >= 0 && N >= 0 && k >= 0, "frr_topk_desc: bad sizes B=%d N=%d k=%d", B, N, k);
@@ -252,7 +263,7 @@ extern "C" int frr_topk_desc(const float* scores, const uint8_t* valid, const fl
     FRR_CHECK_ARG(k <= 16384, "frr_topk_desc: k=%d exceeds the in-smem sort capacity 16384", k);
     {   // fast path: shared-memory radix sort (topk_radix.cu); shapes outside it take the bitonic kernel below
         const int rc = topk_radix_launch(scores, valid, boxes, B, N, k, out_scores, out_idx, out_cidx, out_boxes, out_count,
-                                         nullptr, stream);
+                                         nullptr, stream, cluster_hint);
         if (rc <= 0) return rc;
     }
     int P = 32;

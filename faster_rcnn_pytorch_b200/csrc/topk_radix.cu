@@ -14,6 +14,9 @@
 //   4. scores / indices / compacted indices / gathered boxes are written out (padded past count).
 // Compared with the bitonic version (105 compare-exchange stages with a barrier each, contended histogram
 // atomics) this is ~10x fewer shared-memory wavefronts and barriers.  HBM bytes: 5N in, 40k out per image.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "frr_common.cuh"
 
 namespace frr {
@@ -82,7 +85,8 @@ __device__ __forceinline__ void topk_radix_body(unsigned char* smem, const float
                                                 int k, int kcap, int nchunks, const RsLayout& L,
                                                 float* __restrict__ out_scores, int32_t* __restrict__ out_idx,
                                                 int32_t* __restrict__ out_cidx, float4* __restrict__ out_boxes,
-                                                int32_t* __restrict__ out_count, long long* __restrict__ dbg) {
+                                                int32_t* __restrict__ out_count, long long* __restrict__ dbg,
+                                                int img = -1) {
     const bool prof = (dbg != nullptr) && blockIdx.x == 0 && threadIdx.x == 0;
     long long t0 = prof ? clock64() : 0;
 #define RS_TICK(slot)                   \
@@ -105,7 +109,7 @@ __device__ __forceinline__ void topk_radix_body(unsigned char* smem, const float
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int lt = (1u << lane) - 1u;
-    const int b = blockIdx.x;
+    const int b = img >= 0 ? img : (int)blockIdx.x;
     const float* sc = scores + (size_t)b * N;
     const uint8_t* va = valid ? valid + (size_t)b * N : nullptr;
 
@@ -649,6 +653,316 @@ __global__ void __launch_bounds__(kRsThreads, 1)
 #undef BK_TICK
 }
 
+// ------------------------------------------------------------------------------------------------
+// Bucket top-k over a thread-block CLUSTER per image (small batches: one CTA per image leaves most SMs idle -- a single
+// image ran on ONE SM).  CTA r of the S CTAs owns a contiguous range of the 32-anchor chunks: it loads / stages /
+// histograms its own scores; the S histograms are merged through distributed shared memory (every CTA reads the peers'
+// counts and derives the same bucket starts, plus the offset of its own pairs inside every bucket); pairs are scattered
+// straight into the shared memory of the CTA that OWNS their bucket (buckets are dealt to the CTAs by their start
+// position, whole buckets only), which ranks them and writes its contiguous piece of the output row.  Same buckets, same
+// exact total order (key descending, index ascending) as the one-CTA kernel: identical results; inputs that do not bucket
+// are redone by CTA 0 alone on the radix path.
+struct BkXch {
+    float mn, mx;
+    unsigned int nvalid, bad;
+};
+constexpr int kBkMaxCluster = 8;
+
+struct BkcHdr {
+    unsigned int warp_tmp[kRsWarps];
+    unsigned int red[kRsWarps];
+    unsigned int bstar, stored, bad;
+    unsigned int obase[kBkMaxCluster + 1];  // first output position owned by CTA o (0xffffffff: none)
+    BkXch xch[kBkMaxCluster];
+};
+
+struct BkcLayout {
+    size_t vbits, vpre, hist, start, off, sval, keyA, idxA, total;
+    int cper, capS;
+};
+static BkcLayout bkc_layout(int N, int cap, int nchunks, int S, bool staged) {
+    BkcLayout L;
+    L.cper = (nchunks + S - 1) / S;
+    L.capS = (cap + S - 1) / S + 256;
+    size_t o = up16(sizeof(BkcHdr));
+    L.vbits = o; o += 4 * (size_t)L.cper;
+    L.vpre = o;  o = up16(o + 4 * (size_t)L.cper);
+    L.hist = o;  o += 4 * (size_t)kBuckets;
+    L.start = o; o = up16(o + 2 * (size_t)(kBuckets + 1));
+    L.off = o;   o = up16(o + 2 * (size_t)kBuckets);
+    L.sval = o;  o = up16(o + (staged ? 4 * 32 * (size_t)L.cper : 0));
+    L.keyA = o;  o += 4 * (size_t)L.capS;
+    L.idxA = o;  o = up16(o + 2 * (size_t)L.capS);
+    L.total = o;
+    (void)N;
+    return L;
+}
+
+template <bool kStaged>
+__global__ void __launch_bounds__(kRsThreads, 1)
+    topk_bucket_cluster_kernel(const float* __restrict__ scores, const uint8_t* __restrict__ valid,
+                               const float4* __restrict__ boxes, int N, int k, int cap, int nchunks,
+                               float* __restrict__ out_scores, int32_t* __restrict__ out_idx, int32_t* __restrict__ out_cidx,
+                               float4* __restrict__ out_boxes, int32_t* __restrict__ out_count, RsLayout L, int kcap,
+                               BkcLayout Lc) {
+    namespace cg = cooperative_groups;
+    extern __shared__ __align__(16) unsigned char smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int S = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int b = (int)blockIdx.x / S;
+    BkcHdr* hd = reinterpret_cast<BkcHdr*>(smem);
+    unsigned int* vbits = reinterpret_cast<unsigned int*>(smem + Lc.vbits);
+    unsigned int* vpre = reinterpret_cast<unsigned int*>(smem + Lc.vpre);
+    unsigned int* hist = reinterpret_cast<unsigned int*>(smem + Lc.hist);
+    unsigned short* start = reinterpret_cast<unsigned short*>(smem + Lc.start);
+    unsigned short* off = reinterpret_cast<unsigned short*>(smem + Lc.off);
+    float* sval = reinterpret_cast<float*>(smem + Lc.sval);
+    unsigned int* keyA = reinterpret_cast<unsigned int*>(smem + Lc.keyA);
+    unsigned short* idxA = reinterpret_cast<unsigned short*>(smem + Lc.idxA);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* sc = scores + (size_t)b * N;
+    const uint8_t* va = valid ? valid + (size_t)b * N : nullptr;
+    const int c_lo = min(nchunks, rank * Lc.cper), c_hi = min(nchunks, c_lo + Lc.cper);
+
+    // ---- 0. own chunks: validity words, staged scores, min / max; zeroed histogram ---------------------------------
+    float lmin = 3.0e38f, lmax = -3.0e38f;
+    bool lbad = false;
+    constexpr int kLd = 4;
+    for (int c0 = c_lo + warp; c0 < c_hi; c0 += kLd * kRsWarps) {
+        uint8_t v4[kLd];
+        float s4[kLd];
+#pragma unroll
+        for (int j = 0; j < kLd; ++j) {
+            const int c = c0 + j * kRsWarps;
+            const int i = c * 32 + lane;
+            const bool in = c < c_hi && i < N;
+            v4[j] = (in && va) ? va[i] : (uint8_t)(in ? 1 : 0);
+            s4[j] = in ? sc[i] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < kLd; ++j) {
+            const int c = c0 + j * kRsWarps;
+            const int i = c * 32 + lane;
+            const bool ok = (c < c_hi) && (i < N) && (v4[j] != 0);
+            const unsigned int w = __ballot_sync(0xffffffffu, ok);
+            if (c < c_hi) {
+                if (lane == 0) vbits[c - c_lo] = w;
+                if (kStaged) sval[(c - c_lo) * 32 + lane] = s4[j];
+                if (ok) {
+                    lbad |= !(fabsf(s4[j]) <= 3.0e38f);
+                    lmin = fminf(lmin, s4[j]);
+                    lmax = fmaxf(lmax, s4[j]);
+                }
+            }
+        }
+    }
+    for (int i = tid; i < kBuckets; i += kRsThreads) hist[i] = 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+        lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    }
+    const bool wbad = __any_sync(0xffffffffu, lbad);
+    if (lane == 0) { hd->warp_tmp[warp] = __float_as_uint(lmin); hd->red[warp] = __float_as_uint(lmax); }
+    if (tid == 0) hd->bad = 0u;
+    __syncthreads();
+    if (wbad && lane == 0) hd->bad = 1u;
+    unsigned int nvalid_local = 0;
+    {   // exclusive prefix of the valid counts of the own chunks
+        unsigned int run = 0;
+        for (int base = 0; base < c_hi - c_lo; base += kRsThreads) {
+            const int c = base + tid;
+            const unsigned int v = (c < c_hi - c_lo) ? __popc(vbits[c]) : 0u;
+            unsigned int tot;
+            const unsigned int ex = block_exclusive_scan(v, hd->warp_tmp + 0, &tot);  // (warp_tmp reuse is fenced below)
+            if (c < c_hi - c_lo) vpre[c] = run + ex;
+            run += tot;
+        }
+        nvalid_local = run;
+    }
+    __syncthreads();
+    // (the min / max words were consumed?  no: recompute them here, after the scan reused warp_tmp)
+    {
+        float a = lmin, z = lmax;  // warp-level values are still in registers
+        if (lane == 0) { hd->warp_tmp[warp] = __float_as_uint(a); hd->red[warp] = __float_as_uint(z); }
+        __syncthreads();
+        if (warp == 0) {
+            a = __uint_as_float(hd->warp_tmp[lane]);
+            z = __uint_as_float(hd->red[lane]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o));
+                z = fmaxf(z, __shfl_xor_sync(0xffffffffu, z, o));
+            }
+            if (lane < S) {  // this CTA's summary into every CTA's exchange array
+                BkXch x;
+                x.mn = a; x.mx = z; x.nvalid = nvalid_local; x.bad = hd->bad;
+                *cluster.map_shared_rank(&hd->xch[rank], lane) = x;
+            }
+        }
+    }
+    cluster.sync();
+    float smin = 3.0e38f, smax = -3.0e38f;
+    unsigned int nvalid = 0, vbase = 0, anybad = 0;
+    for (int r = 0; r < S; ++r) {
+        const BkXch x = hd->xch[r];
+        smin = fminf(smin, x.mn);
+        smax = fmaxf(smax, x.mx);
+        if (r < rank) vbase += x.nvalid;
+        nvalid += x.nvalid;
+        anybad |= x.bad;
+    }
+    const int keff = min(k, (int)nvalid);
+    const float scale = (float)kBuckets / (smax - smin);
+    bool handover = anybad != 0u || (keff > 0 && !(scale <= 3.0e38f));
+    auto bucket_of = [&](float s) { return min(kBuckets - 1, (int)((smax - s) * scale)); };
+    auto score_at = [&](int i) -> float { return kStaged ? sval[i - c_lo * 32] : sc[i]; };
+
+    if (keff > 0 && !handover) {
+        // ---- 1. histogram of the own valid scores ----------------------------------------------------------------
+        for (int c = c_lo + warp; c < c_hi; c += kRsWarps) {
+            const int i = c * 32 + lane;
+            if ((vbits[c - c_lo] >> lane) & 1u) atomicAdd(&hist[bucket_of(score_at(i))], 1u);
+        }
+        cluster.sync();  // every CTA's counts are complete
+        // ---- 2. merged counts -> bucket starts (same in every CTA), offset of the own pairs inside every bucket ------
+        {
+            constexpr int kPerT = kBuckets / kRsThreads;
+            unsigned int h4[kPerT], o4[kPerT], t4 = 0;
+#pragma unroll
+            for (int q = 0; q < kPerT; ++q) { h4[q] = 0; o4[q] = 0; }
+            for (int r = 0; r < S; ++r) {
+                const uint4* ph = reinterpret_cast<const uint4*>(cluster.map_shared_rank(hist, r) + kPerT * tid);
+#pragma unroll
+                for (int q4 = 0; q4 < kPerT / 4; ++q4) {
+                    const uint4 v = ph[q4];
+                    h4[4 * q4 + 0] += v.x; h4[4 * q4 + 1] += v.y; h4[4 * q4 + 2] += v.z; h4[4 * q4 + 3] += v.w;
+                    if (r < rank) { o4[4 * q4 + 0] += v.x; o4[4 * q4 + 1] += v.y; o4[4 * q4 + 2] += v.z; o4[4 * q4 + 3] += v.w; }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < kPerT; ++q) { t4 += h4[q]; off[kPerT * tid + q] = (unsigned short)min(o4[q], 65535u); }
+            unsigned int tot;
+            unsigned int run = block_exclusive_scan(t4, hd->warp_tmp, &tot);
+            unsigned int big = 0;
+#pragma unroll
+            for (int q = 0; q < kPerT; ++q) {
+                start[kPerT * tid + q] = (unsigned short)min(run, 65535u);
+                if (run < (unsigned int)keff) {
+                    big = max(big, h4[q]);
+                    if (run + h4[q] >= (unsigned int)keff) { hd->bstar = kPerT * tid + q; hd->stored = run + h4[q]; }
+                }
+                run += h4[q];
+            }
+            if (tid == kRsThreads - 1) start[kBuckets] = (unsigned short)min(run, 65535u);
+            big = __reduce_max_sync(0xffffffffu, big);
+            __syncthreads();
+            if (lane == 0) hd->red[warp] = big;
+            if (tid <= kBkMaxCluster) hd->obase[tid] = 0xffffffffu;
+            __syncthreads();
+            if (warp == 0) {
+                big = __reduce_max_sync(0xffffffffu, hd->red[lane]);
+                if (lane == 0 && (big > kBucketMax || hd->stored > (unsigned int)cap)) hd->bad = 1u;
+            }
+            __syncthreads();
+            handover = hd->bad != 0u;
+        }
+        cluster.sync();  // every CTA has read the counts: they become the scatter cursors
+    }
+    if (handover) {  // cluster-uniform: CTA 0 redoes the image alone on the radix path
+        cluster.sync();
+        if (rank != 0) return;
+        if (L.staged) topk_radix_body<true>(smem, scores, valid, boxes, N, k, kcap, nchunks, L, out_scores, out_idx, out_cidx,
+                                            out_boxes, out_count, nullptr, b);
+        else topk_radix_body<false>(smem, scores, valid, boxes, N, k, kcap, nchunks, L, out_scores, out_idx, out_cidx,
+                                    out_boxes, out_count, nullptr, b);
+        return;
+    }
+    if (rank == 0 && tid == 0) out_count[b] = keff;
+    if (keff > 0) {
+        const int bstar = (int)hd->bstar;
+        const unsigned int stored = hd->stored;
+        const unsigned int per = (stored + (unsigned int)S - 1u) / (unsigned int)S;  // output positions per owner
+        auto owner_of = [&](unsigned int pos) { return min((unsigned int)S - 1u, pos / per); };
+        // first position of every owner (whole buckets: a bucket belongs to the owner of its start)
+        for (int bk = tid; bk <= bstar; bk += kRsThreads) {
+            const unsigned int o = owner_of(start[bk]);
+            if (bk == 0 || owner_of(start[bk - 1]) != o) hd->obase[o] = start[bk];
+        }
+        for (int i = tid; i < kBuckets; i += kRsThreads) hist[i] = 0u;
+        __syncthreads();
+        // ---- 3. scatter the own pairs of buckets <= b* into their owners' arrays ------------------------------------
+        for (int c = c_lo + warp; c < c_hi; c += kRsWarps) {
+            const int i = c * 32 + lane;
+            if ((vbits[c - c_lo] >> lane) & 1u) {
+                const float sv = score_at(i);
+                const int bk = bucket_of(sv);
+                if (bk <= bstar) {
+                    const unsigned int s0 = start[bk];
+                    const unsigned int pos = s0 + off[bk] + atomicAdd(&hist[bk], 1u);
+                    const unsigned int o = owner_of(s0);
+                    const unsigned int li = pos - hd->obase[o];
+                    cluster.map_shared_rank(keyA, o)[li] = float_to_ordered(sv);
+                    cluster.map_shared_rank(idxA, o)[li] = (unsigned short)i;
+                }
+            }
+        }
+        cluster.sync();
+        // ---- 4. rank the own range and write its piece of the output row ---------------------------------------------
+        const unsigned int my0 = hd->obase[rank];
+        unsigned int my1 = stored;
+        for (int o = rank + 1; o < S; ++o)
+            if (hd->obase[o] != 0xffffffffu) { my1 = hd->obase[o]; break; }
+        const int cnt = my0 == 0xffffffffu ? 0 : (int)(my1 - my0);
+        unsigned short* orow = reinterpret_cast<unsigned short*>(hist);  // cursors are dead: staged output piece
+        __syncthreads();
+        for (int p2 = tid; p2 < cnt; p2 += kRsThreads) {
+            const unsigned int ku = keyA[p2];
+            const unsigned int ki = idxA[p2];
+            const int bk = bucket_of(ordered_to_float(ku));
+            const int s0 = (int)start[bk] - (int)my0, s1 = (int)start[bk + 1] - (int)my0;
+            int r = s0;
+            for (int a = s0; a < s1; ++a) {
+                const unsigned int ka = keyA[a];
+                r += (ka > ku || (ka == ku && (unsigned int)idxA[a] < ki)) ? 1 : 0;
+            }
+            const int g = r + (int)my0;  // final rank
+            if (g < keff) {
+                const size_t oo = (size_t)b * k + g;
+                const int i = (int)ki;
+                orow[r] = (unsigned short)ki;
+                if (out_scores) out_scores[oo] = ordered_to_float(ku);
+                if (out_cidx) {
+                    const int hc = i >> 5, hr = min(S - 1, hc / Lc.cper);   // the anchor's home CTA holds its validity words
+                    const unsigned int hb = cluster.map_shared_rank(vbits, hr)[hc - hr * Lc.cper];
+                    const unsigned int hp = cluster.map_shared_rank(vpre, hr)[hc - hr * Lc.cper];
+                    unsigned int base_r = 0;
+                    for (int q = 0; q < hr; ++q) base_r += hd->xch[q].nvalid;
+                    out_cidx[oo] = (int)(base_r + hp + __popc(hb & ((1u << (i & 31)) - 1u)));
+                }
+                if (out_boxes) out_boxes[oo] = boxes[(size_t)b * N + i];
+            }
+        }
+        __syncthreads();
+        {
+            int32_t* orow_g = out_idx + (size_t)b * k + my0;
+            const int lim = min(cnt, keff - (int)my0);
+            for (int j2 = tid; j2 < lim; j2 += kRsThreads) orow_g[j2] = (int32_t)orow[j2];
+        }
+    }
+    // ---- 5. padding past the count (dealt over the cluster) ---------------------------------------------------------
+    for (int j2 = keff + rank * kRsThreads + tid; j2 < k; j2 += S * kRsThreads) {
+        const size_t oo = (size_t)b * k + j2;
+        out_idx[oo] = -1;
+        if (out_scores) out_scores[oo] = __uint_as_float(0xff800000u);
+        if (out_cidx) out_cidx[oo] = -1;
+        if (out_boxes) out_boxes[oo] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    (void)vbase;
+    cluster.sync();  // nobody leaves while a peer may still read its shared memory
+}
+
 static size_t bucket_smem(int N, int cap, int nchunks, bool staged) {
     size_t o = up16(sizeof(BkHdr));
     o = up16(o + 8 * (size_t)nchunks);
@@ -661,7 +975,7 @@ static size_t bucket_smem(int N, int cap, int nchunks, bool staged) {
 // Returns FRR_OK when the launch was done, 1 when the shape is outside the fast path (caller falls back).
 int topk_radix_launch(const float* scores, const uint8_t* valid, const float* boxes, int B, int N, int k,
                       float* out_scores, int32_t* out_idx, int32_t* out_cidx, float* out_boxes, int32_t* out_count,
-                      long long* dbg, frr_stream_t stream) {
+                      long long* dbg, frr_stream_t stream, int cluster_hint) {
     if (N > 65536 || k > 16384) return 1;
     const size_t limit = 227 * 1024;
     const int kcap = (k + 31) & ~31;
@@ -676,6 +990,43 @@ int topk_radix_launch(const float* scores, const uint8_t* valid, const float* bo
     const int cap = kcap + kBucketSlack;
     const bool bstaged = bucket_smem(N, cap, nchunks, true) <= limit;
     const size_t bsm = bucket_smem(N, cap, nchunks, bstaged);
+    // CTAs per image: small batches (B * S <= SMs) spread an image over a cluster; cluster_hint = 1 keeps one CTA per
+    // image (the least SM time: several batches in flight), the profiling entry (dbg) too
+    int S = 1;
+    if (bsm <= limit && cluster_hint != 1 && dbg == nullptr) {
+        const int nsm = num_sms();
+        // two CTAs per image when they fit: 26-27 us against 29-39 us; more do not pay (measured: 4 CTAs equal 2, 8 CTAs
+        // take 37-44 us -- five cluster barriers and an S-fold histogram merge against ~25 us of divisible work)
+        S = (long)B * 2 <= nsm ? 2 : 1;
+        static const int smax_dbg = getenv("FRR_TOPK_SMAX") ? atoi(getenv("FRR_TOPK_SMAX")) : 2;  // developer knob (tools/topk_latency.py)
+        if (smax_dbg != 2) S = (long)B * smax_dbg <= nsm ? smax_dbg : S;
+    }
+    if (S > 1) {
+        BkcLayout Lc = bkc_layout(N, cap, nchunks, S, true);
+        const bool cstaged = Lc.total <= limit;
+        if (!cstaged) Lc = bkc_layout(N, cap, nchunks, S, false);
+        if (Lc.total <= limit) {
+            auto ckern = cstaged ? topk_bucket_cluster_kernel<true> : topk_bucket_cluster_kernel<false>;
+            FRR_CUDA(cudaFuncSetAttribute(ckern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(B * S), 1, 1);
+            cfg.blockDim = dim3((unsigned)kRsThreads, 1, 1);
+            cfg.dynamicSmemBytes = Lc.total > L.total ? Lc.total : L.total;
+            cfg.stream = (cudaStream_t)stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)S;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            FRR_CUDA(cudaLaunchKernelEx(&cfg, ckern, scores, valid, (const float4*)boxes, N, k, cap, nchunks, out_scores, out_idx,
+                                        out_cidx, (float4*)out_boxes, out_count, L, kcap, Lc));
+            count_launch();
+            FRR_CHECK_LAUNCH("topk_bucket_cluster_kernel");
+            return FRR_OK;
+        }
+    }
     if (bsm <= limit) {
         auto bkern = bstaged ? topk_bucket_kernel<true> : topk_bucket_kernel<false>;
         FRR_CUDA(cudaFuncSetAttribute(bkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));

@@ -291,13 +291,15 @@ class InferPlan:
     Neither half synchronises with the host; ``capture_*`` record them into CUDA graphs (one graph launch per half)."""
 
     def __init__(self, B: int, image_hw, num_classes: int, device, stride: int = 16, max_det: int = 100,
-                 score_thres: float = 0.05, iou_thr: float = 0.3, mode: str = "test", logits: bool = True):
+                 score_thres: float = 0.05, iou_thr: float = 0.3, mode: str = "test", logits: bool = True,
+                 nms_cluster_size: int = 0):
         from . import dist as fdist
         self._fdist = fdist
         self.B, self.hw, self.NC, self.device = int(B), (int(image_hw[0]), int(image_hw[1])), int(num_classes), torch.device(device)
         self.fhw = (self.hw[0] // stride, self.hw[1] // stride)
         self.N = self.fhw[0] * self.fhw[1] * 9
-        self.proposal = ProposalPlan(self.B, self.N, self.device, image_hw=self.hw, mode=mode, stride=stride, logits=logits)
+        self.proposal = ProposalPlan(self.B, self.N, self.device, image_hw=self.hw, mode=mode, stride=stride, logits=logits,
+                                     nms_cluster_size=nms_cluster_size)
         self.R = self.proposal.post_k
         self.max_det, self.score_thres, self.iou_thr = int(max_det), float(score_thres), float(iou_thr)
         with torch.cuda.device(self.device):
