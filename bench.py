@@ -589,9 +589,10 @@ def run_rpn(ctx, args) -> dict:
 
     def k_topk(i, st):
         r = i % N_ROTATE
-        _lib.check(lib.frr_topk_desc(d_scores[r].data_ptr(), d_valid[r].data_ptr(), None, B, n, PRE_K,
-                                     None, t_idx[r].data_ptr(), None, None, t_cnt[r].data_ptr(), st),
-                   "frr_topk_desc")
+        _lib.check(lib.frr_topk_desc_opt(d_scores[r].data_ptr(), d_valid[r].data_ptr(), None, B, n, PRE_K,
+                                         None, t_idx[r].data_ptr(), None, None, t_cnt[r].data_ptr(),
+                                         1 if nms_cs == 1 else 0, st),     # (the geometry of the timed path)
+                   "frr_topk_desc_opt")
 
     nms_cs = 1 if pipe2 is not None else args.nms_cluster     # the launch geometry of the timed path
 

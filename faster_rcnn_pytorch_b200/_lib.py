@@ -31,6 +31,7 @@ SIGNATURES = {
     "frr_anchors": (_i, [_p, _i, _i, _i, _p, _i, _p]),
     "frr_rpn_decode": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _i, _i, _p]),
     "frr_topk_desc": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "frr_topk_desc_opt": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
     "frr_topk_desc_profile": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "frr_nms_sorted": (_i, [_p, _p, _i, _i, _d, _i, _p, _p, _p, _i, _p]),
     "frr_rpn_proposals_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i]),

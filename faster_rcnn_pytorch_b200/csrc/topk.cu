@@ -250,6 +250,14 @@ extern "C" int frr_topk_desc(const float* scores, const uint8_t* valid, const fl
     return frr::topk_desc_impl(scores, valid, boxes, B, N, k, out_scores, out_idx, out_cidx, out_boxes, out_count, 0, stream);
 }
 
+extern "C" int frr_topk_desc_opt(const float* scores, const uint8_t* valid, const float* boxes, int B, int N, int k,
+                                 float* out_scores, int32_t* out_idx, int32_t* out_cidx, float* out_boxes,
+                                 int32_t* out_count, int ctas_per_image, frr_stream_t stream) {
+    FRR_CHECK_ARG(ctas_per_image == 0 || ctas_per_image == 1, "frr_topk_desc_opt: ctas_per_image must be 0 (automatic) or 1");
+    return frr::topk_desc_impl(scores, valid, boxes, B, N, k, out_scores, out_idx, out_cidx, out_boxes, out_count,
+                               ctas_per_image, stream);
+}
+
 // cluster_hint: 0 = CTAs per image chosen for the lowest latency of this call, 1 = one CTA per image
 int frr::topk_desc_impl(const float* scores, const uint8_t* valid, const float* boxes, int B, int N, int k, float* out_scores,
                         int32_t* out_idx, int32_t* out_cidx, float* out_boxes, int32_t* out_count, int cluster_hint,

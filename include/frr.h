@@ -91,6 +91,13 @@ int frr_topk_desc(const float* scores /* [B,N] */, const uint8_t* valid /* [B,N]
                   float* out_scores /* [B,k] or NULL */, int32_t* out_idx /* [B,k] */,
                   int32_t* out_cidx /* [B,k] or NULL */, float* out_boxes /* [B,k,4] or NULL */,
                   int32_t* out_count /* [B] */, frr_stream_t stream);
+/* The same with the CTAs per image chosen by the caller: 0 = automatic (a 2-CTA cluster per image when B * 2 CTAs fit the
+ * SMs: lowest latency), 1 = one CTA per image (least SM time: several batches in flight).  Identical results.        */
+int frr_topk_desc_opt(const float* scores /* [B,N] */, const uint8_t* valid /* [B,N] or NULL */,
+                  const float* boxes /* [B,N,4] or NULL */, int B, int N, int k,
+                  float* out_scores /* [B,k] or NULL */, int32_t* out_idx /* [B,k] */,
+                  int32_t* out_cidx /* [B,k] or NULL */, float* out_boxes /* [B,k,4] or NULL */,
+                  int32_t* out_count /* [B] */, int ctas_per_image, frr_stream_t stream);
 /* Profiling variant: dbg_cycles = int64[16] accumulating clock64() cycles of CTA 0 per phase: [0..4] radix kernel
  * (load+validity, select, compaction, sort, write-out; only when image 0 was handed over), [8..13] bucket kernel
  * (load + min/max, histogram, scan, scatter, -, rank + write-out). */
