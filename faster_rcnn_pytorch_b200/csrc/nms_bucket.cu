@@ -296,7 +296,9 @@ __global__ void __launch_bounds__(kThreads)
         sm->work[0] = 0u;
         sm->work[1] = 0u;
     }
-    cluster.sync();  // every CTA's shared memory is initialised before a peer writes into it
+    // (one CTA per image: a block barrier does; the hardware cluster barrier costs ~1 us even for a cluster of one)
+    auto cluster_sync = [&]() { if (S == 1) __syncthreads(); else cluster.sync(); };
+    cluster_sync();  // every CTA's shared memory is initialised before a peer writes into it
 
     int nk = 0;   // kept so far (identical in every CTA of the cluster)
     int cur = 0;  // buffer that holds the kept list
@@ -375,7 +377,7 @@ __global__ void __launch_bounds__(kThreads)
             }
         }
         BK_TICK(BK_SCREEN);
-        cluster.sync();
+        cluster_sync();
         BK_TICK(BK_SYNC1);
         // ---- E: histogram of the survivors' keys; reset what the next chunk's phases A-D accumulate into
         for (int i = tid; i < kBkChunk; i += kThreads) sm->cstate[par ^ 1][i] = 0;
@@ -472,7 +474,7 @@ __global__ void __launch_bounds__(kThreads)
             if (tid < S) *cluster.map_shared_rank(&sm->ecount[rank], tid) = (unsigned int)ne;
         }
         BK_TICK(BK_PRED);
-        cluster.sync();
+        cluster_sync();
         BK_TICK(BK_SYNC2);
         // ---- I: fix-point (every CTA on all survivors and all edges)
         for (;;) {
