@@ -119,8 +119,9 @@ def rpn_decode(reg, cls, image_hw=None, anchors=None, stride: int = 16, table=No
     return boxes, scores, valid
 
 
-def topk_desc(scores, k: int, valid=None, boxes=None, want_cidx: bool = False):
-    """P4.  scores [B,N] -> dict(scores [B,k], idx int32 [B,k], cidx, boxes [B,k,4], count int32 [B])."""
+def topk_desc(scores, k: int, valid=None, boxes=None, want_cidx: bool = False, ctas_per_image: int = 0):
+    """P4.  scores [B,N] -> dict(scores [B,k], idx int32 [B,k], cidx, boxes [B,k,4], count int32 [B]).
+    ``ctas_per_image``: 0 = automatic (a 2-CTA cluster per image for small batches), 1 = one CTA per image."""
     lib = _lib.load()
     scores = _req(scores, "scores")
     if scores.dim() != 2:
@@ -137,8 +138,9 @@ def topk_desc(scores, k: int, valid=None, boxes=None, want_cidx: bool = False):
         o_c = torch.empty((B, k), dtype=torch.int32, device=dev) if want_cidx else None
         o_b = torch.empty((B, k, 4), dtype=torch.float32, device=dev) if boxes is not None else None
         cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
-        _lib.check(lib.frr_topk_desc(scores.data_ptr(), _ptr(valid), _ptr(boxes), B, N, int(k), o_s.data_ptr(),
-                                     o_i.data_ptr(), _ptr(o_c), _ptr(o_b), cnt.data_ptr(), _stream()), "frr_topk_desc")
+        _lib.check(lib.frr_topk_desc_opt(scores.data_ptr(), _ptr(valid), _ptr(boxes), B, N, int(k), o_s.data_ptr(),
+                                         o_i.data_ptr(), _ptr(o_c), _ptr(o_b), cnt.data_ptr(), int(ctas_per_image), _stream()),
+                   "frr_topk_desc_opt")
     return dict(scores=o_s, idx=o_i, cidx=o_c, boxes=o_b, count=cnt)
 
 

@@ -456,3 +456,32 @@ def test_proposal_plan_is_cuda_graph_capturable(oracle):
     assert torch.equal(got_cnt, want_cnt)
     assert torch.equal(got_rois, want_rois)
     assert int(got_cnt.min()) > 0
+
+
+@pytest.mark.parametrize("B,N,k", [(1, 21546, 12000), (3, 20646, 6000), (2, 37350, 6000), (5, 3000, 4000)])
+def test_topk_cluster_kernel_equals_one_cta_kernel(B, N, k):
+    """topk_bucket_cluster_kernel (two CTAs per image, histograms merged through distributed shared memory) against the
+    one-CTA kernel: every output identical -- random scores with an invalid mask, heavy ties (quantised scores), all scores
+    equal (handed to the radix path by CTA 0 alone), and a batch with empty images."""
+    rs = np.random.RandomState(77)
+    cases = {
+        "random": rs.rand(B, N).astype(np.float32),
+        "ties": (rs.randint(0, 500, size=(B, N)) / 500.0).astype(np.float32),
+        "equal": np.full((B, N), 0.25, np.float32),
+    }
+    boxes = dev(rs.rand(B, N, 4).astype(np.float32))
+    for name, sc in cases.items():
+        valid = (rs.rand(B, N) < 0.9)
+        if name == "random" and B > 1:
+            valid[B - 1] = False                              # an image without a valid score
+        v = dev(valid.astype(np.uint8))
+        a = ops.topk_desc(dev(sc), k, valid=v, boxes=boxes, want_cidx=True, ctas_per_image=0)
+        b = ops.topk_desc(dev(sc), k, valid=v, boxes=boxes, want_cidx=True, ctas_per_image=1)
+        for key in ("count", "idx", "cidx", "scores", "boxes"):
+            assert torch.equal(a[key], b[key]), (name, key)
+        # and against a stable sort on the host (ties: lower index first)
+        for i in range(B):
+            src = np.nonzero(valid[i])[0]
+            order = src[np.argsort(-sc[i][valid[i]], kind="stable")][:k]
+            n = int(a["count"][i])
+            assert n == len(order) and np.array_equal(a["idx"][i, :n].cpu().numpy(), order), (name, i)
