@@ -119,6 +119,7 @@ def _mixed_rois(seed, K, fh, fw, B, small_frac=0.4):
     (2, 20, 37, 62, 200, True, False),      # partial last channel group (20 = 8 + 8 + 4), post-ReLU ties at 0
     (1, 16, 30, 40, 1300, True, False),     # > 512 rois of one image: several list rounds
     (1, 16, 50, 83, 700, True, False),      # 800x1333 map: every roi through the streaming atomic kernel
+    (2, 12, 50, 83, 300, False, True),      # ... with a channels_last gradient
     (3, 16, 37, 62, 400, True, True),       # channels_last gradient
     (1, 8, 110, 110, 150, False, False),    # 48 KB planes
     (2, 7, 20, 20, 100, True, False),       # partial single channel group, odd channel count (a warp with one plane)
@@ -151,6 +152,22 @@ def test_roi_pool_backward_colour_kernel(oracle, B, C, fh, fw, K, relu, channels
     g1 = ops.roi_pool_backward(dev(go), arg_b, dev(big), feat.shape, channels_last=channels_last)
     g2 = ops.roi_pool_backward(dev(go), arg_b, dev(big), feat.shape, channels_last=channels_last)
     assert torch.equal(g1, g2)
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_roi_align_backward_stream_kernel(oracle, channels_last):
+    """50x84 map: the separable plane kernel would be left with 8 planes per SM, roi_align_bwd_stream_kernel (one CTA per
+    roi, merged taps in registers, global atomics) runs instead -- both memory formats, rois crossing the borders."""
+    B, C, fh, fw, K = 2, 40, 50, 84, 150
+    rois5 = synth.random_rois(751, K, fh, fw, B)
+    rois5[0, 1:] = [-30, -30, -20, -20]          # entirely outside: contributes nothing
+    rois5[1, 1:] = [10.2, 10.2, 10.6, 10.5]      # sub-pixel roi: all samples of a bin on the same pixels (merged taps)
+    go = np.random.RandomState(752).standard_normal((K, C, 7, 7)).astype(np.float32)
+    gin = ops.roi_align_backward(dev(go), dev(rois5), (B, C, fh, fw), spatial_scale=1.0, sampling_ratio=2, aligned=False,
+                                 channels_last=channels_last)
+    assert gin.is_contiguous(memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+    close_accum(gin.cpu().numpy(), oracle.roi_align_backward(go, rois5, (B, C, fh, fw), spatial_scale=1.0, sampling_ratio=2,
+                                                             aligned=False))
 
 
 def test_large_planes_take_the_direct_kernels(oracle):
