@@ -41,7 +41,9 @@ constexpr int kBkBins = 3;         // x bins of a walk whose bounds are prefetch
 constexpr int kBkUpBins = 2;       // same for the upward walk (bins above the own one)
 constexpr int kBkHits = 4;         // screen hits a thread parks per walk before it falls back to the slow walk
 
-static std::atomic<int> g_bk_kc0{1024}, g_bk_kcmax{2048}, g_bk_nsub1{4}, g_bk_nsub2{4};
+// lanes_screen 0 = automatic: 2 lanes per candidate when an image has 1-2 CTAs (batched launches: 146 vs 153 us with one
+// CTA per image, tools/nms_s1_sweep.py), 4 in the large clusters of the single-image form (81 vs 85 us)
+static std::atomic<int> g_bk_kc0{1024}, g_bk_kcmax{2048}, g_bk_nsub1{0}, g_bk_nsub2{4};
 
 struct BkSmem {
     unsigned int lhist[kKeyCap];  // kept list: key histogram, then scatter cursors
@@ -632,7 +634,9 @@ int nms_bucket_launch(const float* boxes, const int32_t* counts, int B, int n, c
     cfg.numAttrs = 1;
     FRR_CUDA(cudaLaunchKernelEx(&cfg, kern, (const float4*)boxes, counts, n, max_keep, thr, keep, keep_count,
                                 (float4*)out_boxes, dbg, gather_idx, src_n, kc0, kc_max,
-                                g_bk_nsub1.load(std::memory_order_relaxed), g_bk_nsub2.load(std::memory_order_relaxed)));
+                                g_bk_nsub1.load(std::memory_order_relaxed) ? g_bk_nsub1.load(std::memory_order_relaxed)
+                                                                           : (S <= 2 ? 2 : 4),
+                                g_bk_nsub2.load(std::memory_order_relaxed)));
     count_launch();
     FRR_CHECK_LAUNCH("nms_bucket_kernel");
     return FRR_OK;
@@ -651,7 +655,7 @@ extern "C" int frr_nms_bucket_tune(int first_chunk, int max_chunk, int lanes_scr
                   "frr_nms_bucket_tune: lanes per candidate must be a power of two <= 32");
     frr::g_bk_kc0.store(first_chunk);
     frr::g_bk_kcmax.store(max_chunk);
-    if (lanes_screen) frr::g_bk_nsub1.store(lanes_screen);
+    frr::g_bk_nsub1.store(lanes_screen);  // (0: back to automatic)
     if (lanes_pairs) frr::g_bk_nsub2.store(lanes_pairs);
     return FRR_OK;
 }

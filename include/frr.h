@@ -133,8 +133,9 @@ int frr_nms_variant(int B, int n, double iou_thr, int max_keep, int cluster_size
                     int32_t* out4);
 
 /* Developer knob for the profiling tools: sizes of the first and of the largest chunk of the bucketed variant
- * (multiples of 256 in [256, 2048]) and the lanes per candidate of its screen / pair phases (powers of two <= 32,
- * 0 = unchanged).  Process-wide; results never depend on them. */
+ * (multiples of 256 in [256, 2048]) and the lanes per candidate of its screen / pair phases (powers of two <= 32;
+ * lanes_screen 0 = automatic: 2 with 1-2 CTAs per image, else 4; lanes_pairs 0 = unchanged).  Process-wide; results
+ * never depend on them. */
 int frr_nms_bucket_tune(int first_chunk, int max_chunk, int lanes_screen, int lanes_pairs);
 
 /* Same, with the score order given as indices into an unsorted array: candidate i of image b is

@@ -51,4 +51,4 @@ for first, largest, n1, n2 in ((512, 2048, 4, 4), (512, 2048, 8, 8), (512, 2048,
         run(tb, tc, S, threads, dbg=True)
     for threads, S in ((1024, 16), (512, 16), (1024, 8)):
         run(one, onec, S, threads, reps=50, dbg=True)
-_lib.check(lib.frr_nms_bucket_tune(1024, 2048, 4, 4), "tune")
+_lib.check(lib.frr_nms_bucket_tune(1024, 2048, 0, 4), "tune")
