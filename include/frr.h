@@ -164,7 +164,7 @@ int frr_rpn_proposals(const float* reg /* [B,N,4] */, const float* cls /* [B,N,2
                       size_t workspace_bytes, frr_stream_t stream);
 /* The same call with the NMS launch geometry chosen by the caller: nms_cluster_size = CTAs per image (1, 2, 4, 8, 16;
  * 0 = automatic, the lowest latency of ONE call: 2 at 64 images, 8-16 for a single image).  1 spends the least SM time
- * per image (9.8 k vs 15.7 k SM-microseconds per 64 images): the setting for several batches in flight on different
+ * per image (9.4 k vs 15.5 k SM-microseconds per 64 images): the setting for several batches in flight on different
  * streams (region.ProposalPipeline), where the other batches' kernels fill the SMs a single CTA per image leaves idle.
  * Results are identical for every setting.                                                                        */
 int frr_rpn_proposals_opt(const float* reg, const float* cls, int cls_is_logits, const float* anchors,
