@@ -17,7 +17,7 @@ for name in (f"{R}_bench_launches.csv", f"{R}_stage_profile.log", f"{R}_nms_phas
 open(os.path.join(P, f"{R}_bench_launches_summary.txt"), "w").write(
     run(sys.executable, os.path.join(REPO, "tools", "launch_summary.py"), os.path.join(G, f"{R}_bench_launches.csv")))
 lines = []
-for w in ("all", "reference", "rpn", "train", "infer", "joint", "all_n2", "all_n8"):   # the multi-GPU lines come from separate gpurun --gpus N calls
+for w in ("all", "reference", "rpn", "train", "infer", "joint", "all_n2", "all_n4", "all_n8"):   # the multi-GPU lines come from separate gpurun --gpus N calls
     f = os.path.join(G, f"{R}_bench_{w}.json")
     if os.path.exists(f):
         js = [l for l in open(f).read().splitlines() if l.startswith("{")]   # (torchrun prints a banner on stdout)
