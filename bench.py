@@ -900,6 +900,49 @@ def run_predict(ctx, args, which: str) -> dict:
     e_steps = max(5, min(steps, 20))
     ms_e2e = ctx.median_ms(e2e_host, e_steps, runs=3)
     ms_e2r = ctx.median_ms(e2e_resident, e_steps, runs=3)
+    # the same with `depth` batches in flight: the detections of step i - depth are consumed on the host while steps
+    # i - depth + 1 .. i run; every step still copies its packed detections + counts into pinned memory
+    ms_e2f = None
+    if ms_multi:
+        hd_ = [torch.empty((nrows, 100, 6), dtype=torch.float32).pin_memory() for _ in range(depth)]
+        hc_ = [torch.empty((nrows,), dtype=torch.int32).pin_memory() for _ in range(depth)]
+        evs = [torch.cuda.Event() for _ in range(depth)]
+        live = [False] * depth
+
+        def consume(j):
+            if live[j]:
+                evs[j].synchronize()
+                sink[0] += int(hc_[j][0])
+                live[j] = False
+
+        def e2e_flight(i):
+            j = i % depth
+            consume(j)                                   # the host reads the result of the step that used this slot
+            g, out = mg[j][i % NR]
+
+            def go():
+                g.replay()
+                done[j].record()
+            fl.run(i, go)
+            cur = torch.cuda.current_stream()
+            cur.wait_event(done[j])
+            if gather:
+                p, c, _ = fdist.gather_detections(out["packed"], out["pc"], ids, equal_batch=True)
+            else:
+                p, c = out["packed"], out["pc"]
+            hd_[j].copy_(p, non_blocking=True)
+            hc_[j].copy_(c, non_blocking=True)
+            evs[j].record(cur)
+            live[j] = True
+
+        def e2e_flight_tail():
+            for j in range(depth):
+                consume(j)
+
+        for i in range(2 * depth):
+            e2e_flight(i)
+        e2e_flight_tail()
+        ms_e2f = ctx.median_ms(e2e_flight, e_steps, runs=3, tail=e2e_flight_tail)
     h2d = sum(int(np.prod(x.shape)) * 4 for x in (h["feats"][0], h["lgs"][0], h["rgs"][0], h["hcls"], h["hreg"]))
     d2h = nrows * 100 * 6 * 4 + nrows * 4
     pooled_bytes = B * 512 * fhw[0] * fhw[1] * 4 + B * R * 512 * 49 * 4
@@ -925,6 +968,10 @@ def run_predict(ctx, args, which: str) -> dict:
                          "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2r / e_steps,
                          "mode": "backbone / head outputs resident on the device as in the reference (models/model.py:315,352), "
                                  "packed detections [B,100,6] + counts read back on the host every step"},
+        "e2e_resident_in_flight": ({"value": ctx.world * B * e_steps / (ms_e2f * 1e-3), "unit": "images/s", "h2d_bytes_per_step": 0,
+                                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2f / e_steps,
+                                    "mode": f"the same, {depth} batches in flight: the host consumes the detections of step i - {depth} "
+                                            "while the next steps run"} if ms_e2f else None),
         "roofline": _hbm_roofline(ctx, "roi_pool_fwd_flat_kernel", pooled_bytes, ms_pool,
                                   note="RoIPool forward without argmax: features once + pooled output once"),
         "detections_last_step": int(keep["out"]["pc"].sum()),
