@@ -1036,6 +1036,8 @@ def run_train(ctx, args) -> dict:
     if not args.single_stream and args.sampling == "device":
         fl = InFlight(torch, dev, depth)
         tplans, tg = [], []
+        gt_j = [gt.clone() for _ in range(depth)]      # per-slot ground truth (the end-to-end form refills it every step)
+        lab_j = [lab.clone() for _ in range(depth)]
         for j in range(depth):
             with torch.cuda.stream(fl.streams[j]):
                 pj = region.TrainPlan(B, hw, dev, generator=targets.DeviceGenerator(dev))
@@ -1043,7 +1045,7 @@ def run_train(ctx, args) -> dict:
                 for r in range(NR):
                     # the two halves of the step as CUDA graphs (the head's forward / backward sits between them in a real
                     # step): targets + rois5 + RoIPool forward, then RoIPool backward on that forward's argmax
-                    g1, o1 = pj.capture_targets_and_pool(feats[r], gt, lab, props, pcnt)
+                    g1, o1 = pj.capture_targets_and_pool(feats[r], gt_j[j], lab_j[j], props, pcnt)
                     last = dict(pj.last)
                     g2, o2 = pj.capture_pool_backward(gouts[r])
                     row.append((g1, g2, o1, o2, last))
@@ -1107,6 +1109,43 @@ def run_train(ctx, args) -> dict:
         e2e(i)
     e_steps = max(5, min(steps, 20))
     ms_e2e = ctx.median_ms(e2e, e_steps, runs=3)
+    # the same with `depth` batches in flight (graph replays): H2D of the ground truth into the slot's tensors, both graphs,
+    # D2H of the sampled class targets, the host consuming the result of step i - depth
+    ms_e2f = None
+    if ms is not ms_one:
+        h_cls_j = [torch.empty((B, per), dtype=torch.int64).pin_memory() for _ in range(depth)]
+        evs = [torch.cuda.Event() for _ in range(depth)]
+        live_j = [False] * depth
+
+        def consume(j):
+            if live_j[j]:
+                evs[j].synchronize()
+                sink[0] += int(h_cls_j[j][0, 0])
+                live_j[j] = False
+
+        def e2e_flight(i):
+            j, r = i % depth, i % NR
+            consume(j)
+
+            def go():
+                g1, g2, o1, o2, last = tg[j][r]
+                gt_j[j].copy_(h_gt, non_blocking=True)
+                lab_j[j].copy_(h_lab, non_blocking=True)
+                g1.replay()
+                g2.replay()
+                h_cls_j[j].copy_(o1[0]["frcnn_cls"], non_blocking=True)
+                evs[j].record()
+            fl.run(i, go)
+            live_j[j] = True
+
+        def e2e_flight_tail():
+            for j in range(depth):
+                consume(j)
+
+        for i in range(2 * depth):
+            e2e_flight(i)
+        e2e_flight_tail()
+        ms_e2f = ctx.median_ms(e2e_flight, e_steps, runs=3, tail=e2e_flight_tail)
     fb = fbytes + 2 * obytes
     return {
         "value": world * B * steps / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms / steps, "steps": steps,
@@ -1127,6 +1166,11 @@ def run_train(ctx, args) -> dict:
                 "mode": "ground-truth boxes + labels from pinned host memory, sampled class targets read back, every step, "
                         "serialised; features / grad_out resident (backbone and head backward run on the device, "
                         "models/model.py:315)"},
+        "e2e_in_flight": ({"value": world * B * e_steps / (ms_e2f * 1e-3), "unit": "images/s",
+                           "h2d_bytes_per_step": int(gt_h.nbytes + lab_h.nbytes), "d2h_bytes_per_step": B * per * 8,
+                           "ms_per_step": ms_e2f / e_steps,
+                           "mode": f"the same copies every step, {depth} batches in flight (graph replays), the host consumes the "
+                                   f"result of step i - {depth}"} if ms_e2f else None),
         "roofline": _hbm_roofline(ctx, "roi_pool_fwd_flat_kernel", fb, ms_f),
         "roofline_bwd": _hbm_roofline(ctx, "roi_pool_bwd_color_kernel", fb, ms_b),
     }
