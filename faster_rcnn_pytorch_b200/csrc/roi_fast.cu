@@ -122,6 +122,12 @@ __device__ __forceinline__ AlignRec align_rec(float v, int size) {
 // A quarter-warp (8 lanes x 16 bytes) is conflict-free when its 8 chunks fall into 8 different 4-bank groups; the group
 // of (p, k) is ((p * NCH + slot) mod 8), so the rotation must depend on p / (8 / NCH): then pixels that differ mod 8 never
 // collide (with the rotation (k + p) pixels that agree mod 4 always collided: 8 lanes into 4 groups).
+// Element index of chunk k of pixel p in the staged array, two forms.  kPlanar: chunk-major ([chunk][pixel] of 16-byte
+// elements): RoIPool's lanes (neighbouring bins) read pixels 2-3 apart, i.e. elements 2-3 apart -> mostly different bank
+// groups (247 vs 260 us on RPN rois).  Pixel-major ([pixel][chunk], chunks rotated, below): RoIAlign's four taps per sample
+// are neighbouring pixels, and both chunks of a pixel share a 32-byte segment (305 vs 330 us).
+template <int CB, bool kPlanar>
+__device__ __forceinline__ size_t chunk_at(int p, int k, int HW);
 template <int CB>
 __device__ __forceinline__ int chunk_slot(int p, int k) {
     constexpr int NCH = CB / 4;
@@ -129,9 +135,14 @@ __device__ __forceinline__ int chunk_slot(int p, int k) {
     return (k + (p >> SH)) & (NCH - 1);
 }
 
+template <int CB, bool kPlanar>
+__device__ __forceinline__ size_t chunk_at(int p, int k, int HW) {
+    return kPlanar ? (size_t)k * HW + p : (size_t)p * (CB / 4) + chunk_slot<CB>(p, k);
+}
+
 // NCHW: consecutive threads read consecutive pixels of 4 planes (coalesced), 2 trips (8 loads) in flight; channels_last:
 // consecutive threads read consecutive 16-byte channel chunks of a pixel, 4 trips in flight.  No runtime divisions.
-template <int CB>
+template <int CB, bool kPlanar>
 __device__ __forceinline__ void load_pixels(float4* px, const float* __restrict__ feat, int b, int c0, int C, int HW,
                                             bool nhwc) {
     constexpr int NCH = CB / 4;
@@ -158,7 +169,7 @@ __device__ __forceinline__ void load_pixels(float4* px, const float* __restrict_
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int p = p0 + u * nt;
-                    if (p < HW) px[(size_t)p * NCH + chunk_slot<CB>(p, k)] = v[u];
+                    if (p < HW) px[chunk_at<CB, kPlanar>(p, k, HW)] = v[u];
                 }
             }
         }
@@ -190,7 +201,7 @@ __device__ __forceinline__ void load_pixels(float4* px, const float* __restrict_
                 const int i = i0 + u * nt;
                 if (i < n) {
                     const int p = i / NCH, k = i - p * NCH;
-                    px[(size_t)p * NCH + chunk_slot<CB>(p, k)] = v[u];
+                    px[chunk_at<CB, kPlanar>(p, k, HW)] = v[u];
                 }
             }
         }
@@ -218,7 +229,7 @@ __global__ void __launch_bounds__(kFastFwdThreads, (CB <= 8) ? 2 : 1)
     const int cb = min(CB, C - c0);
     const bool prof = (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0);
     long long t0_ = clock64();
-    load_pixels<CB>(px, feat, b, c0, C, HW, nhwc != 0);
+    load_pixels<CB, false>(px, feat, b, c0, C, HW, nhwc != 0);
     ROI_TICK(0);
 
     // thread -> (roi slot rs, bin): the 49 bins of a roi sit in consecutive lanes
@@ -263,10 +274,10 @@ __global__ void __launch_bounds__(kFastFwdThreads, (CB <= 8) ? 2 : 1)
                             const int i3 = yy.hi * W + xx.lo, i4 = yy.hi * W + xx.hi;
 #pragma unroll
                             for (int k = 0; k < NCH; ++k) {
-                                const float4 v1 = px[(size_t)i1 * NCH + chunk_slot<CB>(i1, k)];
-                                const float4 v2 = px[(size_t)i2 * NCH + chunk_slot<CB>(i2, k)];
-                                const float4 v3 = px[(size_t)i3 * NCH + chunk_slot<CB>(i3, k)];
-                                const float4 v4 = px[(size_t)i4 * NCH + chunk_slot<CB>(i4, k)];
+                                const float4 v1 = px[chunk_at<CB, false>(i1, k, HW)];
+                                const float4 v2 = px[chunk_at<CB, false>(i2, k, HW)];
+                                const float4 v3 = px[chunk_at<CB, false>(i3, k, HW)];
+                                const float4 v4 = px[chunk_at<CB, false>(i4, k, HW)];
 #define FRR_BIL(e, c)                                                                                                   \
     acc[4 * k + e] = __fadd_rn(acc[4 * k + e],                                                                          \
                                __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, v1.c), __fmul_rn(w2, v2.c)), __fmul_rn(w3, v3.c)), \
@@ -334,7 +345,7 @@ __global__ void __launch_bounds__(kFlatThreads, (CB <= 8) ? 2 : 1)
     const int cb = min(CB, C - c0);
     const bool prof = (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0);
     long long t0_ = clock64();
-    load_pixels<CB>(px, feat, b, c0, C, HW, nhwc != 0);
+    load_pixels<CB, true>(px, feat, b, c0, C, HW, nhwc != 0);
     ROI_TICK(0);
 
     for (int tile = 0; tile < K; tile += kFlatThreads) {
@@ -402,9 +413,9 @@ __global__ void __launch_bounds__(kFlatThreads, (CB <= 8) ? 2 : 1)
                         float4 va[NCH], vb[NCH];
 #pragma unroll
                         for (int k = 0; k < NCH; ++k) {
-                            va[k] = px[(size_t)idx * NCH + chunk_slot<CB>(idx, k)];
+                            va[k] = px[chunk_at<CB, true>(idx, k, HW)];
                             vb[k] = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
-                            if (two) vb[k] = px[(size_t)(idx + 1) * NCH + chunk_slot<CB>(idx + 1, k)];
+                            if (two) vb[k] = px[chunk_at<CB, true>(idx + 1, k, HW)];
                         }
 #pragma unroll
                         for (int k = 0; k < NCH; ++k) {
