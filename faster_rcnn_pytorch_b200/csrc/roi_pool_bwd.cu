@@ -487,12 +487,31 @@ __global__ void __launch_bounds__(256)
                 gv[u] = __ldg(grad_out + src0 + e);
             }
         }
+        const int lane = threadIdx.x & 31;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            if ((uint32_t)av[u] < uHW) {
-                const int c = (e0 + u * 256) / 49;
+            // neighbouring bins of a small roi often share their argmax pixel (windows coincide): consecutive lanes with the
+            // same (channel, pixel) are summed in registers (segmented sum over runs: 5 shuffle steps) and only the first
+            // lane of a run issues the atomic -- the kernel is bound by the L2 atomic rate, not by instructions
+            const int c = (e0 + u * 256) / 49;
+            const bool ok = (uint32_t)av[u] < uHW;
+            const int key = ok ? av[u] : (-1 - lane);   // (an invalid element is a run of its own)
+            const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+            const int prev_c = __shfl_up_sync(0xffffffffu, c, 1);
+            const bool head = lane == 0 || prev != key || prev_c != c;
+            const unsigned int heads = __ballot_sync(0xffffffffu, head);
+            // end of this lane's run: the next head above it
+            const unsigned int above = heads & ~((2u << lane) - 1u);
+            const int run_end = above ? __ffs(above) - 1 : 32;   // first lane of the next run
+            float sum = gv[u];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const float v = __shfl_down_sync(0xffffffffu, sum, d);
+                if (lane + d < run_end) sum = __fadd_rn(sum, v);
+            }
+            if (ok && head) {
                 const size_t o = nhwc ? img + (size_t)av[u] * C + c : img + (size_t)c * HW + av[u];
-                atomicAdd(grad_in + o, gv[u]);
+                atomicAdd(grad_in + o, sum);
             }
         }
     }
