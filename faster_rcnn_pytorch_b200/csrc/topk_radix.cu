@@ -680,7 +680,7 @@ struct BkcLayout {
     size_t vbits, vpre, hist, start, off, sval, keyA, idxA, total;
     int cper, capS;
 };
-static BkcLayout bkc_layout(int N, int cap, int nchunks, int S, bool staged) {
+static BkcLayout bkc_layout(int cap, int nchunks, int S, bool staged) {
     BkcLayout L;
     L.cper = (nchunks + S - 1) / S;
     L.capS = (cap + S - 1) / S + 256;
@@ -694,7 +694,6 @@ static BkcLayout bkc_layout(int N, int cap, int nchunks, int S, bool staged) {
     L.keyA = o;  o += 4 * (size_t)L.capS;
     L.idxA = o;  o = up16(o + 2 * (size_t)L.capS);
     L.total = o;
-    (void)N;
     return L;
 }
 
@@ -763,8 +762,7 @@ __global__ void __launch_bounds__(kRsThreads, 1)
         lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
         lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
     }
-    const bool wbad = __any_sync(0xffffffffu, lbad);
-    if (lane == 0) { hd->warp_tmp[warp] = __float_as_uint(lmin); hd->red[warp] = __float_as_uint(lmax); }
+    const bool wbad = __any_sync(0xffffffffu, lbad);   // (lmin / lmax: the warp's values, in every lane)
     if (tid == 0) hd->bad = 0u;
     __syncthreads();
     if (wbad && lane == 0) hd->bad = 1u;
@@ -775,16 +773,15 @@ __global__ void __launch_bounds__(kRsThreads, 1)
             const int c = base + tid;
             const unsigned int v = (c < c_hi - c_lo) ? __popc(vbits[c]) : 0u;
             unsigned int tot;
-            const unsigned int ex = block_exclusive_scan(v, hd->warp_tmp + 0, &tot);  // (warp_tmp reuse is fenced below)
+            const unsigned int ex = block_exclusive_scan(v, hd->warp_tmp, &tot);
             if (c < c_hi - c_lo) vpre[c] = run + ex;
             run += tot;
         }
         nvalid_local = run;
     }
     __syncthreads();
-    // (the min / max words were consumed?  no: recompute them here, after the scan reused warp_tmp)
-    {
-        float a = lmin, z = lmax;  // warp-level values are still in registers
+    {   // block min / max (after the scan: it uses warp_tmp), then this CTA's summary into every CTA of the cluster
+        float a = lmin, z = lmax;
         if (lane == 0) { hd->warp_tmp[warp] = __float_as_uint(a); hd->red[warp] = __float_as_uint(z); }
         __syncthreads();
         if (warp == 0) {
@@ -804,12 +801,11 @@ __global__ void __launch_bounds__(kRsThreads, 1)
     }
     cluster.sync();
     float smin = 3.0e38f, smax = -3.0e38f;
-    unsigned int nvalid = 0, vbase = 0, anybad = 0;
+    unsigned int nvalid = 0, anybad = 0;
     for (int r = 0; r < S; ++r) {
         const BkXch x = hd->xch[r];
         smin = fminf(smin, x.mn);
         smax = fmaxf(smax, x.mx);
-        if (r < rank) vbase += x.nvalid;
         nvalid += x.nvalid;
         anybad |= x.bad;
     }
@@ -959,7 +955,6 @@ __global__ void __launch_bounds__(kRsThreads, 1)
         if (out_cidx) out_cidx[oo] = -1;
         if (out_boxes) out_boxes[oo] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    (void)vbase;
     cluster.sync();  // nobody leaves while a peer may still read its shared memory
 }
 
@@ -1002,9 +997,9 @@ int topk_radix_launch(const float* scores, const uint8_t* valid, const float* bo
         if (smax_dbg != 2) S = (long)B * smax_dbg <= nsm ? smax_dbg : S;
     }
     if (S > 1) {
-        BkcLayout Lc = bkc_layout(N, cap, nchunks, S, true);
+        BkcLayout Lc = bkc_layout(cap, nchunks, S, true);
         const bool cstaged = Lc.total <= limit;
-        if (!cstaged) Lc = bkc_layout(N, cap, nchunks, S, false);
+        if (!cstaged) Lc = bkc_layout(cap, nchunks, S, false);
         if (Lc.total <= limit) {
             auto ckern = cstaged ? topk_bucket_cluster_kernel<true> : topk_bucket_cluster_kernel<false>;
             FRR_CUDA(cudaFuncSetAttribute(ckern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
