@@ -14,11 +14,12 @@
 //     class all <= 16 argmax pixels of the plane are distinct and the adds are plain LDS / FADD / STS in a fixed
 //     order (deterministic, unlike atomics);
 //   * smaller rois (a side under 6 pixels: bin size < 1, windows two apart may coincide) would need s_h x s_w > 4 classes
-//     (s = smallest stride with disjoint windows) -- more shared-memory steps than one global atomic per element costs.
-//     The plane kernel leaves them out and roi_pool_bwd_tail_kernel adds them afterwards: one CTA per roi streams the
-//     roi's C * 49 contiguous values and issues RED.ADD.F32 onto the stored planes (faster than torchvision's kernel of
-//     the same atomics: perfectly coalesced reads, no per-element index arithmetic).  The strided-class / MATCH.ANY
-//     code stays as the in-kernel path for any roi the list builder does not classify as small;
+//     (s = smallest stride with disjoint windows) -- more shared-memory steps than one global atomic per element costs
+//     (measured: strided classes 313 us, MATCH.ANY merging 640-970 us, atomics 180-200 us on rois of 1-7 pixels).  The plane
+//     kernel leaves them out and roi_pool_bwd_tail_kernel adds them afterwards: one CTA per roi streams the roi's C * 49
+//     contiguous values, sums the gradients of consecutive lanes that hit the same (channel, pixel) in registers and issues
+//     one RED.ADD.F32 per run onto the stored planes (faster than torchvision's kernel of the same atomics: coalesced
+//     reads, no per-element index arithmetic, fewer atomics);
 //   * every warp streams the grad_out / argmax rows of its two planes (2 x 98 contiguous words per roi) into its own
 //     shared-memory ring with cp.async, kPbDepth rois ahead of the adds, each word to a class-major position so that
 //     an adding lane fetches its four class values with one 16-byte read: HBM latency is covered without registers,
@@ -38,19 +39,10 @@ constexpr int kPbDepth = 8;     // rois in flight per warp (ring slots)
 constexpr int kPbSlotBytes = 1024;  // ring slot: [32 lanes][4 classes] argmax words, then the same for grad_out
 constexpr int kPbIdCap = 512;    // input rois scanned per round
 
-constexpr int kPbCombos = 7;  // (stride h, stride w) pairs with at most 12 classes besides (2, 2)
 struct PoolBwdHdr {
     int cnt[32];
-    int id[kPbIdCap];  // roi index (24 bits) | class stride in h << 24 | class stride in w << 27
-    // per (combo, slot i < 16): the ring word positions (plane half 0) of the slot's bin in each of the <= 12 classes
-    // (0xff = none), byte 12 = number of classes
-    unsigned char steps[kPbCombos][16][16];
+    int id[kPbIdCap];  // roi index (24 bits) | class stride in h << 24 | class stride in w << 27 (both 2 for every listed roi)
 };
-// combo index of a (stride h, stride w) pair, -1 = not tabulated ((2, 2) has its own path, the rest take MATCH.ANY)
-__host__ __device__ constexpr int pb_combo(int sh, int sw) {
-    return sh == 2 && sw == 3 ? 0 : sh == 3 && sw == 2 ? 1 : sh == 3 && sw == 3 ? 2 : sh == 2 && sw == 4 ? 3
-         : sh == 4 && sw == 2 ? 4 : sh == 3 && sw == 4 ? 5 : sh == 4 && sw == 3 ? 6 : -1;
-}
 constexpr int kPbHdrBytes = (sizeof(PoolBwdHdr) + 127) & ~127;
 constexpr int kPbIdMask = (1 << 24) - 1;
 
@@ -62,30 +54,6 @@ __host__ __device__ constexpr int ring_pos(int half, int bin) {
     const int i = (ph >> 1) * ((pw & 1) ? 3 : 4) + (pw >> 1);
     return (half * 16 + i) * 4 + q;
 }
-
-// Step table of the strided colour classes, built at compile time: per (combo, slot i < 16) the ring word positions
-// (plane half 0) of the slot's bin in each of the <= 12 classes (0xff = none), byte 12 = number of classes.
-struct PbStepTable {
-    unsigned char v[kPbCombos * 16 * 16];
-    constexpr PbStepTable() : v() {
-        for (int e = 0; e < kPbCombos * 16 * 16; ++e) {
-            const int combo = e >> 8, i = (e >> 4) & 15, t = e & 15;
-            const int sh = combo == 0 || combo == 3 ? 2 : combo == 4 || combo == 6 ? 4 : 3;
-            const int sw = combo == 1 || combo == 4 ? 2 : combo == 3 || combo == 5 ? 4 : 3;
-            const int nw = 6 / sw + 1, nh = 6 / sh + 1;
-            const int ih = i / nw, iw = i - ih * nw;
-            int x = 0xff;
-            if (t < sh * sw) {
-                const int ph = t / sw + sh * ih, pw = t % sw + sw * iw;
-                if (ih < nh && ph < 7 && pw < 7) x = ring_pos(0, ph * 7 + pw);
-            } else if (t == 12) {
-                x = sh * sw;
-            }
-            v[e] = (unsigned char)x;
-        }
-    }
-};
-__device__ const PbStepTable g_pb_steps = PbStepTable();
 
 // developer instrumentation: clock64() cycles of CTA (0,0) warp 0, accumulated over launches (0 accumulate loop, 5 roi
 // scan, 6 zero, 7 store); read through frr_roi_debug_cycles (slots 8-15)
@@ -140,8 +108,7 @@ __device__ __forceinline__ int class_stride(int r) {
     return s;
 }
 
-// rois of a side below ~3-6 pixels: their strided classes need more than 6 steps per roi, more than a global atomic
-// per element costs -> roi_pool_bwd_tail_kernel
+// rois that need more than the four (mod 2, mod 2) classes (a side below ~6 pixels) -> roi_pool_bwd_tail_kernel
 __device__ __forceinline__ bool pb_small(int sh, int sw) { return sh * sw > 4; }
 
 // block-wide exclusive prefix sum of one int per thread (blockDim a multiple of 32, <= 1024); *total = block sum
@@ -167,8 +134,7 @@ __device__ __forceinline__ int pb_block_scan(int v, int* warp_cnt, int* total) {
 }
 
 // One round of the roi scan over rois[k0, k0 + kPbIdCap): the rois of image b that take the shared-memory paths go to
-// hd->id with their class strides (rois whose strided classes need more than 6 steps are left to
-// roi_pool_bwd_tail_kernel).  The order of the list is a fixed function of the input (determinism of the sums).
+// hd->id with their class strides (pb_small rois are left to roi_pool_bwd_tail_kernel).  The order of the list is a fixed function of the input (determinism of the sums).
 // PER = kPbIdCap / blockDim.  Returns the length of hd->id.  Called by all threads.
 template <int PER>
 __device__ __forceinline__ int collect_rois(const float* __restrict__ rois, int K, int k0, int b, float scale, PoolBwdHdr* hd) {
@@ -265,8 +231,6 @@ __global__ void __launch_bounds__(CB * 16)
         for (int i = n4 * 4 + tid; i < CB * HW; i += blockDim.x) planes[i] = 0.f;
         // argmax positions of bins that do not exist (classes with fewer than 16 bins) stay -1 for good
         for (int i = tid; i < kWarps * D * (kPbSlotBytes / 4); i += blockDim.x) ring[i] = -1;
-        for (int e = tid; e < kPbCombos * 16 * 4; e += blockDim.x)
-            reinterpret_cast<uint32_t*>(&hd->steps[0][0][0])[e] = reinterpret_cast<const uint32_t*>(g_pb_steps.v)[e];
     }
     PB_TICK(6);
 
@@ -279,14 +243,12 @@ __global__ void __launch_bounds__(CB * 16)
         sbase = (uint32_t)t;
     }
     const uint32_t id0 = sbase + (uint32_t)offsetof(PoolBwdHdr, id);
-    const uint32_t steps0 = sbase + (uint32_t)offsetof(PoolBwdHdr, steps) + 16u * (uint32_t)(lane & 15);
     const uint32_t ring0 = sbase + kPbHdrBytes + (uint32_t)warp * (D * kPbSlotBytes);
     const uint32_t planes0 = sbase + kPbHdrBytes + kWarps * D * kPbSlotBytes;
     const int half = lane >> 4;
     const int my_pl = 2 * warp + half;
     const bool pl_ok = my_pl < cb;
     const uint32_t pl0 = planes0 + (uint32_t)(pl_ok ? my_pl : 0) * (uint32_t)HW * 4u;
-    const uint32_t pair0 = planes0 + (uint32_t)(2 * warp) * (uint32_t)HW * 4u;
     const int npl = min(2, cb - 2 * warp);  // planes of this warp that exist (<= 0: idle warp)
     // copy roles: lane l moves words l, l + 32, l + 64, l + 96 of the 49 * npl contiguous words of a roi's row pair to
     // their class-major positions
@@ -335,78 +297,10 @@ __global__ void __launch_bounds__(CB * 16)
             auto mask = [&](PbVals& v) {
                 if (!pl_ok || ((v.entry >> 24) & 63) != (2 | (2 << 3))) v.a0 = v.a1 = v.a2 = v.a3 = -1;
             };
-            // rois whose windows need more than the four (mod 2, mod 2) classes: straight from the ring slot
-            auto slow = [&](int entry, uint32_t so) {
-                const int sh = (entry >> 24) & 7, sw = (entry >> 27) & 7;
-                const uint32_t sa = ring0 + so;
-                const int combo = pb_combo(sh, sw);
-                if (combo >= 0) {
-                    // classes (ph mod sh, pw mod sw): <= 4 x 4 bins each, windows pairwise disjoint; the slot's bin per
-                    // class comes from the table (one 16-byte read), every step is branch-free
-                    uint32_t w0, w1, w2, w3;
-                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-                                 : "r"(steps0 + (uint32_t)combo * 256u) : "memory");
-                    const int nst = (int)(w3 & 0xffu);
-                    const uint32_t hoff = sa + (uint32_t)half * 256u;
-#define FRR_STEP(word, sh8, t)                                                                           \
-    if (t < nst) {                                                                                       \
-        const uint32_t pb_ = ((word) >> (sh8)) & 0xffu;                                                  \
-        const uint32_t o_ = hoff + 4u * pb_;                                                             \
-        int av_ = -1;                                                                                    \
-        float gv_ = 0.f, t_ = 0.f;                                                                       \
-        if (pl_ok && pb_ != 0xffu) {                                                                     \
-            av_ = lds_s32(o_);                                                                           \
-            gv_ = lds_f32(o_ + 512u);                                                                    \
-        }                                                                                                \
-        const uint32_t pa_ = pl0 + 4u * (uint32_t)av_;                                                   \
-        rmw_load(t_, av_, uHW, pa_);                                                                     \
-        rmw_store(__fadd_rn(t_, gv_), av_, uHW, pa_);                                                    \
-        __syncwarp();                                                                                    \
-    }
-                    FRR_STEP(w0, 0, 0) FRR_STEP(w0, 8, 1) FRR_STEP(w0, 16, 2) FRR_STEP(w0, 24, 3)
-                    FRR_STEP(w1, 0, 4) FRR_STEP(w1, 8, 5) FRR_STEP(w1, 16, 6) FRR_STEP(w1, 24, 7)
-                    FRR_STEP(w2, 0, 8) FRR_STEP(w2, 8, 9) FRR_STEP(w2, 16, 10) FRR_STEP(w2, 24, 11)
-#undef FRR_STEP
-                } else {
-                    // few distinct pixels: 32 bins of one plane per step, equal argmax merged with MATCH.ANY
-#pragma unroll 1
-                    for (int p = 0; p < npl; ++p) {
-                        const uint32_t pp = pair0 + (uint32_t)p * uHW * 4u;
-#pragma unroll 1
-                        for (int ch = 0; ch < 2; ++ch) {
-                            const int bin = ch * 32 + lane;
-                            int av = -1;
-                            float gv = 0.f;
-                            if (bin < 49) {
-                                const uint32_t o = sa + 4u * (uint32_t)ring_pos(p, bin);
-                                av = lds_s32(o);
-                                gv = lds_f32(o + 512u);
-                            }
-                            const bool valid = (uint32_t)av < uHW;
-                            const unsigned int m = __match_any_sync(0xffffffffu, valid ? av : -1 - lane);
-                            const bool leader = (m & (0u - m)) == (1u << lane);
-                            unsigned int rest = (leader && valid) ? (m & (m - 1u)) : 0u;
-                            float sum = gv;
-                            while (__any_sync(0xffffffffu, rest != 0u)) {
-                                const int src = rest ? __ffs(rest) - 1 : lane;
-                                const float v = __shfl_sync(0xffffffffu, gv, src);
-                                if (rest) sum = __fadd_rn(sum, v);
-                                rest &= rest - 1u;
-                            }
-                            if (leader && valid) {
-                                const uint32_t pa = pp + 4u * (uint32_t)av;
-                                sts_f32(pa, __fadd_rn(lds_f32(pa), sum));
-                            }
-                            __syncwarp();
-                        }
-                    }
-                }
-            };
             // One roi: `cur` (already in registers) is accumulated while its ring slot is refilled with roi r + D and the
             // values of roi r + 1 are fetched into `nxt` -- three independent instruction streams, interleaved in source
             // order so that each one's shared-memory latency is covered by the other two.
             auto body = [&](int r, uint32_t so, uint32_t so_next, PbVals& cur, PbVals& nxt) {
-                if (((cur.entry >> 24) & 63) != (2 | (2 << 3))) slow(cur.entry, so);  // warp-uniform, rare
                 __syncwarp();  // every lane is done with slot `so`
                 float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
                 const uint32_t p0 = pl0 + 4u * (uint32_t)cur.a0, p1 = pl0 + 4u * (uint32_t)cur.a1;
