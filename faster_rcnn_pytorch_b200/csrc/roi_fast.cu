@@ -74,6 +74,56 @@ __device__ __forceinline__ int stage_ids(const float* __restrict__ rois, int K, 
     return tot;
 }
 
+// The same list for a WIDE window: every thread looks at PER consecutive rois of rois[k0, k0 + PER * blockDim) with all
+// its loads in flight, so a batch of a few thousand rois is scanned once per CTA instead of once per 448 rois (the scan
+// is a chain of global-load and barrier latencies: ~5 K cycles a round, 30 % of a CTA's life when every 448-roi tile
+// paid it).  Returns the number of matches; *mine (bit j = roi k0 + tid * PER + j matches) and *pos (list position of
+// the thread's first match) stay in registers and ids_emit() writes the list out 'cap' entries at a time.
+template <int PER>
+__device__ __forceinline__ int ids_scan(const float* __restrict__ rois, int K, int k0, int b, FastHdr* hd, unsigned int* mine,
+                                        int* pos) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int lo = k0 + tid * PER;
+    float bi[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) bi[j] = __ldg(rois + 5 * (size_t)min(lo + j, K - 1));
+    unsigned int m = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j)
+        if (lo + j < K && (int)bi[j] == b) m |= 1u << j;
+    const int v = __popc(m);
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __syncthreads();  // cnt reuse
+    if (lane == 31) hd->cnt[warp] = inc;
+    __syncthreads();
+    int pre = 0, tot = 0;
+    for (int w = 0; w < nwarps; ++w) {
+        const int c = hd->cnt[w];
+        if (w < warp) pre += c;
+        tot += c;
+    }
+    *mine = m;
+    *pos = pre + inc - v;
+    return tot;
+}
+// entries [r0, r0 + cap) of the list go to hd->id[0, cap) (ids ascending).  Called by all threads.
+template <int PER>
+__device__ __forceinline__ void ids_emit(int k0, unsigned int mine, int pos, int r0, int cap, FastHdr* hd) {
+    const int lo = k0 + (int)threadIdx.x * PER;
+    while (mine) {
+        const int j = __ffs(mine) - 1;
+        mine &= mine - 1u;
+        if (pos >= r0 && pos < r0 + cap) hd->id[pos - r0] = lo + j;
+        ++pos;
+    }
+    __syncthreads();
+}
+
 // RoIPool forward processes RS rois per pass with a barrier per pass, so a pass costs as much as its LARGEST window:
 // order the image's rois by their per-bin window size (descending rank sort, ns <= 512 keys in shared memory) so that
 // every pass works on rois of similar cost.  The output position of a roi is its id, so the order is free.
@@ -314,6 +364,30 @@ __global__ void __launch_bounds__(kFastFwdThreads, (CB <= 8) ? 2 : 1)
     ROI_TICK(5);
 }
 
+// NCHW planes -> the planar staging layout ([chunk][pixel] of float4 = 4 channels) with 4-byte cp.async: no registers
+// between the load and the shared-memory write, so ALL of a thread's ~40 words are in flight at once (the register
+// version above pays six dependent load round trips, ~10 K cycles per CTA) and the roi scan / ordering / bin geometry
+// of the CTA run while they land.  Channels past C are zero-filled.  The caller waits (cp_async_wait_all) before the
+// barrier that precedes the first read.
+__device__ __forceinline__ void cp_async4_zfill(uint32_t dst, const void* src, bool ok) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(ok ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int CB>
+__device__ __forceinline__ void load_planes_async(float4* px, const float* __restrict__ feat, int b, int c0, int C, int HW) {
+    const uint32_t base = smem_u32(px);
+#pragma unroll
+    for (int ce = 0; ce < CB; ++ce) {
+        const int c = c0 + ce;
+        const bool ok = c < C;
+        const float* src = feat + ((size_t)b * C + (ok ? c : c0)) * HW;
+        const uint32_t dst = base + (uint32_t)(((ce >> 2) * HW) * 16 + (ce & 3) * 4);
+        for (int p = threadIdx.x; p < HW; p += blockDim.x) cp_async4_zfill(dst + (uint32_t)p * 16u, src + p, ok);
+    }
+    cp_async_commit_group();
+}
+
 // ---------------------------------------------------------------------------------------------
 // RoIPool forward without per-pass barriers (R1/R2)
 // ---------------------------------------------------------------------------------------------
@@ -345,12 +419,20 @@ __global__ void __launch_bounds__(kFlatThreads, (CB <= 8) ? 2 : 1)
     const int cb = min(CB, C - c0);
     const bool prof = (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0);
     long long t0_ = clock64();
-    load_pixels<CB, true>(px, feat, b, c0, C, HW, nhwc != 0);
+    if (nhwc)
+        load_pixels<CB, true>(px, feat, b, c0, C, HW, true);
+    else
+        load_planes_async<CB>(px, feat, b, c0, C, HW);  // lands behind the roi scan and the bin geometry
     ROI_TICK(0);
 
-    for (int tile = 0; tile < K; tile += kFlatThreads) {
-        int ns = stage_ids(rois, K, tile, b, hd);
-        if (ns == 0) continue;  // block-uniform
+    constexpr int kScanPer = 6;  // 448 x 6 = 2688 rois per scan round
+    for (int k0 = 0; k0 < K; k0 += kScanPer * kFlatThreads) {
+    unsigned int match_bits;
+    int match_pos;
+    const int nmatch = ids_scan<kScanPer>(rois, K, k0, b, hd, &match_bits, &match_pos);
+    for (int r0 = 0; r0 < nmatch; r0 += kFlatThreads) {  // block-uniform trip count
+        int ns = min(kFlatThreads, nmatch - r0);
+        ids_emit<kScanPer>(k0, match_bits, match_pos, r0, kFlatThreads, hd);
         if (ns > kWarps) order_ids_by_window(rois, scale, ns, hd);
         if (gridDim.z > 1) {
             // thin grids (one image): the rois of the image are dealt to gridDim.z CTAs that hold the same planes, every
@@ -367,22 +449,22 @@ __global__ void __launch_bounds__(kFlatThreads, (CB <= 8) ? 2 : 1)
         ROI_TICK(1);
         for (int g0 = 0; g0 < ns; g0 += kFlatGeoCap) {
             const int ng = min(kFlatGeoCap, ns - g0);
-            for (int t = tid; t < ng * 28; t += kFlatThreads) {
-                const int s = t / 28, j = t - s * 28;
-                const int kind = j / 7, p = j - kind * 7;
+            // one thread per (roi, dimension): the rounded roi once, then the 7 window starts and 7 window ends
+            for (int t = tid; t < ng * 2; t += kFlatThreads) {
+                const int s = t >> 1, isw = t & 1;
                 const PoolGeom gm = pool_geom(rois + 5 * (size_t)hd->id[g0 + s], scale);
-                int v;
-                if (kind < 2) {
-                    const float bsz = __fdiv_rn((float)gm.rh, 7.0f);
-                    v = (kind == 0 ? (int)floorf(__fmul_rn((float)p, bsz)) : (int)ceilf(__fmul_rn((float)(p + 1), bsz))) + gm.sh;
-                    v = min(max(v, 0), H);
-                } else {
-                    const float bsz = __fdiv_rn((float)gm.rw, 7.0f);
-                    v = (kind == 2 ? (int)floorf(__fmul_rn((float)p, bsz)) : (int)ceilf(__fmul_rn((float)(p + 1), bsz))) + gm.sw;
-                    v = min(max(v, 0), W);
+                const int len = isw ? gm.rw : gm.rh, start = isw ? gm.sw : gm.sh, lim = isw ? W : H;
+                const float bsz = __fdiv_rn((float)len, 7.0f);
+                short* o = geo + s * 28 + isw * 14;
+#pragma unroll
+                for (int p = 0; p < 7; ++p) {
+                    const int lo = (int)floorf(__fmul_rn((float)p, bsz)) + start;
+                    const int hi = (int)ceilf(__fmul_rn((float)(p + 1), bsz)) + start;
+                    o[p] = (short)min(max(lo, 0), lim);
+                    o[7 + p] = (short)min(max(hi, 0), lim);
                 }
-                geo[t] = (short)v;
             }
+            cp_async_wait_all();  // this thread's share of the planes (first group only; nothing pending afterwards)
             __syncthreads();
             ROI_TICK(2);
             // rois of this warp: one of every 14 consecutive ranks, in boustrophedon order (rank 14 g + warp for even g,
@@ -457,6 +539,8 @@ __global__ void __launch_bounds__(kFlatThreads, (CB <= 8) ? 2 : 1)
             ROI_TICK(4);
         }
     }
+    }
+    cp_async_wait_all();  // (a CTA without rois leaves with nothing in flight)
     ROI_TICK(5);
 }
 

@@ -85,6 +85,24 @@ def test_roi_pool_full_size_vs_oracle(oracle, B, C, fh, fw, K):
     assert arg_na is None and torch.equal(out_na, out)
 
 
+@pytest.mark.parametrize("K,B,want_argmax", [(3000, 2, True), (6000, 3, True), (1500, 1, False)])
+def test_roi_pool_forward_long_roi_lists(K, B, want_argmax):
+    """more rois than one scan round of the forward kernel holds (2688) and more rois of one image than one list round
+    (448), images interleaved, a few masked rows -- max and argmax bit-equal to torchvision's CUDA kernel"""
+    import torchvision  # noqa: F401  (registers torch.ops.torchvision)
+    C, fh, fw = 24, 37, 62
+    feat = dev(synth.features(710, B, C, fh, fw))
+    rois5 = _mixed_rois(711, K, fh, fw, B, small_frac=0.2)
+    keep = rois5[:, 0] >= 0
+    r = dev(rois5)
+    out, arg = ops.roi_pool_forward(feat, r, want_argmax=want_argmax)
+    tv_out, tv_arg = torch.ops.torchvision.roi_pool(feat, dev(rois5[keep]), 1.0, 7, 7)
+    k = torch.from_numpy(keep).to(DEV)
+    assert torch.equal(out[k], tv_out)
+    if want_argmax:
+        assert torch.equal(arg[k], tv_arg.to(arg.dtype))
+
+
 @pytest.mark.parametrize("B,C,fh,fw,K,scale,sr,aligned", [(2, 256, 50, 84, 200, 1.0, 2, False), (1, 256, 25, 42, 100, 0.5, 2, True),
                                                           (1, 16, 30, 30, 50, 1.0, -1, False)])
 def test_roi_align_full_size_vs_oracle(oracle, B, C, fh, fw, K, scale, sr, aligned):
