@@ -393,8 +393,8 @@ __device__ __forceinline__ void load_planes_async(float4* px, const float* __res
 // ---------------------------------------------------------------------------------------------
 // The staged version above spends more issue slots waiting at its per-pass barriers (compute -> copy-out -> next 9
 // rois) than in any other stall (ncu: 3.7 of 12 stall cycles per issued instruction).  Here the WARPS of a CTA take
-// 32-bin slices of the flattened (roi, bin) sequence of the image's rois (ordered by window size) from a shared counter:
-// every lane always has a bin (49 bins per roi do not leave 15 of 64 lanes idle), neighbouring lanes work on the same
+// 32-bin slices of the flattened (roi, bin) sequence of the image's rois (ordered by window size), from a shared counter
+// or as fixed shares: every lane always has a bin (49 bins per roi do not leave 15 of 64 lanes idle), neighbouring lanes work on the same
 // or a similarly sized roi, and the only barriers left are the ones around the per-image roi list.  Results are stored directly: the lanes of a warp hold consecutive
 // bins of one (roi, channel) row, i.e. consecutive addresses of the [K,C,7,7] output -- no staging tile, which also
 // frees ~28 KB of shared memory per CTA.
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(kFlatThreads, (CB <= 8) ? 2 : 1)
     short* geo = reinterpret_cast<short*>(smem_raw + kHdrBytes);  // [kFlatGeoCap][28]: hs[7] he[7] ws[7] we[7]
     float4* px = reinterpret_cast<float4*>(smem_raw + kHdrBytes + ((kFlatGeoCap * 56 + 127) & ~127));
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y, c0 = blockIdx.x * CB;
     const int HW = H * W;
     const int cb = min(CB, C - c0);
@@ -467,21 +467,29 @@ __global__ void __launch_bounds__(kFlatThreads, (CB <= 8) ? 2 : 1)
             cp_async_wait_all();    // this thread's share of the planes (first group only; nothing pending afterwards)
             __syncthreads();
             ROI_TICK(2);
-            // The (roi, bin) sequence of the group -- rois in descending window size -- is cut into slices of 32 consecutive
-            // bins and the warps take the next slice from a shared counter as they finish (largest first: the warps of a
-            // CTA end within one small slice of each other; fixed shares of ~9 rois per warp left them ~12 % apart:
-            // 201 -> 188 us, 226 -> 217 us at 128 rois per image, no change at 300).  The counter is read one slice
-            // ahead, so the shared-memory atomic of the NEXT slice is in flight during the body.  The lanes of a slice
-            // hold bins of one roi or of two rois of neighbouring rank, i.e. windows of similar size.
-            const int nbins = ng * 49, nslices = (nbins + 31) >> 5;
-            int ahead = 0;
-            if (lane == 0) ahead = atomicAdd(&hd->cnt[15], 1);
-#pragma unroll 1
-            for (int sl = __shfl_sync(0xffffffffu, ahead, 0); sl < nslices; sl = __shfl_sync(0xffffffffu, ahead, 0)) {
+            // With argmax (training): the (roi, bin) sequence of the group -- rois in descending window size -- is cut into
+            // slices of 32 consecutive bins and the warps take the next slice from a shared counter as they finish (largest
+            // first: the warps of a CTA end within one small slice of each other; fixed shares of ~9 rois per warp left them
+            // 12 % and more apart: 176 -> 145 us, 226 -> 216 us at 128 rois per image, no change at 300).  The counter is
+            // read one slice ahead, so the shared-memory atomic of the NEXT slice is in flight during the body.
+            // Without argmax (inference) the body is a third shorter and the counter costs more than the balance gains
+            // (109 -> 113 us, 181 -> 190 us): every warp walks a fixed share instead, one roi of each group of 14
+            // consecutive ranks in boustrophedon order (rank 14 g + warp for even g, 14 g + 13 - warp for odd g).
+            // Either way the lanes of a trip hold bins of one roi or of two rois of similar window size.
+            constexpr bool kDealt = kArg;
+            const int total = kDealt ? ng * 49 : ((ng + kWarps - 1) / kWarps) * 49;
+            int ahead = 0, trip = 0;
+            if (kDealt) {
                 if (lane == 0) ahead = atomicAdd(&hd->cnt[15], 1);
-                const int f = sl * 32 + lane;
-                const int s = f / 49, bin = f - s * 49;
-                if (s >= ng) continue;  // tail of the last slice
+                trip = __shfl_sync(0xffffffffu, ahead, 0);
+            }
+#pragma unroll 1
+            for (; trip * 32 < total; trip = kDealt ? __shfl_sync(0xffffffffu, ahead, 0) : trip + 1) {
+                if (kDealt && lane == 0) ahead = atomicAdd(&hd->cnt[15], 1);
+                const int f = trip * 32 + lane;
+                const int li = f / 49, bin = f - li * 49;
+                const int s = kDealt ? li : li * kWarps + ((li & 1) ? kWarps - 1 - warp : warp);
+                if (f >= total || s >= ng) continue;  // last, partial trip / group
                 const int ph = bin / 7, pw = bin - ph * 7;
                 const short* bnd = geo + s * 28;
                 const int hs = bnd[ph], he = bnd[7 + ph], ws = bnd[14 + pw], we = bnd[21 + pw];
